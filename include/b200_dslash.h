@@ -1,0 +1,153 @@
+/*
+ * b200_dslash.h -- C ABI of the B200-native Wilson / Wilson-clover Dslash engine (libquda_b200.so).
+ *
+ * This is the drop-in boundary for QUDA's Dslash free functions.  Each entry point names the reference
+ * interface it replaces (paths relative to the lattice/quda tree); INTEGRATION.md shows the C++ shim that
+ * fills these PODs from quda::ColorSpinorField / GaugeField / CloverField accessors.
+ *
+ * All pointers are DEVICE pointers unless stated otherwise.  Fields are in QUDA's native ("FloatN") orders
+ * (include/color_spinor_field_order.h:1191-1300, include/gauge_field_order.h:1516-1588,
+ * include/clover_field_order.h:587-720), spinors in the UKQCD gamma basis -- exactly what the reference
+ * kernels consume, so resident QUDA fields can be passed unchanged.  Nothing is allocated per call; work is
+ * enqueued on `stream` and the call returns without synchronising (as the reference does).
+ *
+ * Every function returns 0 on success or a negative b200_status; b200_last_error() gives the message
+ * (the QUDA-side shim turns a non-zero status into errorQuda(), include/util_quda.h:73-78).
+ */
+#ifndef B200_DSLASH_H
+#define B200_DSLASH_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+typedef enum {
+  B200_SUCCESS = 0,
+  B200_ERR_INVALID = -1,     /* bad argument / unsupported combination */
+  B200_ERR_CUDA = -2,        /* CUDA runtime error (launch, memcpy, IPC) */
+  B200_ERR_UNSUPPORTED = -3, /* valid request outside the built instantiation set */
+  B200_ERR_NO_DEVICE = -4    /* no usable CUDA device: the product has no CPU fallback */
+} b200_status;
+
+/* QudaPrecision values (include/enum_quda.h): bytes per real */
+enum { B200_DOUBLE = 8, B200_SINGLE = 4, B200_HALF = 2 };
+
+/* which operator; mirrors the three reference entry points */
+typedef enum {
+  B200_OP_WILSON = 0,   /* ApplyWilson:                    out = D in            | a != 0: out = x + a D in       */
+  B200_OP_CLOVER = 1,   /* ApplyWilsonClover:              out = A x + a D in  (xpay form only)                   */
+  B200_OP_CLOVER_PC = 2 /* ApplyWilsonCloverPreconditioned: out = A^-1 D in      | a != 0: out = x + a A^-1 D in  */
+} b200_op;
+
+typedef enum {
+  B200_KERNEL_AUTO = 0,     /* interior, then (if any comm_dim set) wait for halos and run the exterior update */
+  B200_KERNEL_INTERIOR = 1, /* interior kernel only (hops across partitioned boundaries are skipped)           */
+  B200_KERNEL_EXTERIOR = 2  /* fused exterior kernel only (adds ghost hops to the partial result in `out`)      */
+} b200_kernel;
+
+/* One ColorSpinorField in native order.  n_parity == 1: a single-parity field (QUDA_PARITY_SITE_SUBSET);
+ * n_parity == 2: full field, parity blocks `parity_stride_bytes` (= Bytes()/2) apart.
+ * Half precision: `norm` may be NULL, in which case it is derived exactly like the reference accessor does,
+ * (float*)((short*)v + 24*volume_cb), second parity parity_stride_bytes further on. */
+typedef struct {
+  void *v;
+  void *norm;
+  size_t parity_stride_bytes;
+  int volume_cb;
+  int n_parity;
+} b200_spinor;
+
+/* GaugeField in native order with the neighbour's backward links in the pad (QUDA_GHOST_EXCHANGE_PAD). */
+typedef struct {
+  const void *gauge;
+  size_t parity_stride_bytes; /* Bytes()/2 */
+  int stride;                 /* volume_cb + pad */
+  int reconstruct;            /* 18, 12 or 8 */
+  double anisotropy;          /* GaugeField::Anisotropy() */
+  double link_max;            /* GaugeField::LinkMax(): fixed-point scale of reconstruct-18 half links */
+  int t_boundary;             /* +1 periodic, -1 anti-periodic (QudaTboundary) */
+  int first_time_slice;       /* comm_coord(3) == 0 */
+  int last_time_slice;        /* comm_coord(3) == comm_dim(3)-1 */
+} b200_gauge;
+
+/* CloverField in native order (field holding A, or A^-1 when is_inverse). */
+typedef struct {
+  const void *clover;
+  size_t parity_stride_bytes;
+  int compressed;     /* clover::reconstruct(): 28 reals per chiral block instead of 36 */
+  int dynamic_inverse; /* clover::dynamic_inverse(): field holds A; A^-1 is applied by per-site Cholesky solve */
+  double diagonal;    /* CloverField::Diagonal() (compressed format only) */
+  double max_element; /* CloverField::max_element(is_inverse) (fixed point only) */
+} b200_clover;
+
+/* Halo state for partitioned dimensions.  ghost[d][dir]: received, spin-projected faces for dimension d,
+ * dir 0 = data that came from the backward neighbour (used by the x[d]==0 sites), dir 1 = from the forward
+ * neighbour.  Layout per face: both parities back to back, each [M_ghost planes][face_cb] (+ float norms for
+ * half precision) as in include/color_spinor_field_order.h:1065-1180. */
+typedef struct {
+  int comm_dim[4];
+  void *ghost[4][2];
+  void *ghost_norm[4][2]; /* half precision only; NULL -> directly after the 12*face_cb shorts of each parity block */
+} b200_halo;
+
+typedef struct {
+  int abi_version;    /* B200_ABI_VERSION */
+  int op;             /* b200_op */
+  int kernel;         /* b200_kernel */
+  int precision;      /* B200_DOUBLE / B200_SINGLE / B200_HALF: storage precision of out/in/x/U/A */
+  int X[4];           /* local lattice extents (full sites), all even */
+  int parity;         /* destination parity (n_parity == 1); ignored for full fields */
+  int dagger;
+  double a;           /* 0 => no xpay (include/kernels/dslash_wilson.cuh:54) */
+  b200_spinor out, in, x;
+  b200_gauge U;
+  b200_clover A;      /* ignored for B200_OP_WILSON */
+  b200_halo halo;
+  int tile[4];        /* launch-geometry override (cb-sites in x, sites in y,z,t); all 0 => built-in default */
+  void *stream;       /* cudaStream_t */
+} b200_dslash_args;
+
+/* replaces quda::ApplyWilson / ApplyWilsonClover / ApplyWilsonCloverPreconditioned
+ * (include/dslash_quda.h:83,137,234; lib/dslash_wilson.cu:9-20) */
+int b200_dslash_apply(const b200_dslash_args *args);
+
+/* replaces quda::ApplyClover(out, in, clover, inverse, parity) (include/dslash_quda.h:811;
+ * lib/dslash_clover_helper.cu:46-54): out = A in or A^-1 in on one parity */
+int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_clover *A, int precision, int inverse,
+                      int parity, void *stream);
+
+/* replaces quda::PackGhost (include/dslash_quda.h:919; lib/dslash_pack2.cu:55-425): spin-project the boundary
+ * sites of `in` (parity 1-parity... see b200_pack_args) and store 12-real half spinors into the send targets,
+ * which may be local buffers or peer-GPU ghost buffers mapped over NVLink. */
+typedef struct {
+  int abi_version;
+  int precision;
+  int X[4];
+  int parity;      /* parity of the sites being packed (= the input parity of the Dslash that follows) */
+  int dagger;
+  b200_spinor in;
+  int comm_dim[4];
+  void *dst[4][2];      /* [d][0]: where our x[d]==0 face goes (the backward neighbour's ghost[d][1] slot);
+                           [d][1]: where our x[d]==X[d]-1 face goes (the forward neighbour's ghost[d][0] slot) */
+  void *dst_norm[4][2]; /* half precision */
+  void *stream;
+} b200_pack_args;
+int b200_pack_ghost(const b200_pack_args *args);
+
+/* bytes of one face buffer holding BOTH parities (what b200_halo.ghost[d][dir] must point to), and of one parity */
+size_t b200_ghost_face_bytes(int precision, const int X[4], int dim);
+
+const char *b200_last_error(void);
+int b200_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches evidence) */
+long b200_launch_count(void);
+void b200_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

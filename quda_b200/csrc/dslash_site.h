@@ -1,0 +1,230 @@
+// The Wilson / Wilson-clover stencil for ONE output site, written once and shared by every kernel
+// flavour (interior, exterior, tiled, fused-pack) and by the test-only host twin.
+//
+// Reference behaviour being reproduced (not copied): /root/reference/include/kernels/dslash_wilson.cuh:84-197
+// (applyWilson + wilson::operator()), dslash_wilson_clover.cuh:38-105, dslash_wilson_clover_preconditioned.cuh:37-117,
+// dslash_helper.cuh:32-242 (isActive / isComplete / doHalo / doBulk).
+#pragma once
+
+#include "core.h"
+#include "clover.h"
+
+namespace b200
+{
+
+  enum KernelType { K_INTERIOR = 0, K_EXTERIOR_ALL = 1 };
+  enum OpType { OP_WILSON = 0, OP_CLOVER = 1, OP_CLOVER_PC = 2 };
+
+  constexpr int kMaxParity = 2;
+
+  // Kernel parameter block (passed by value; ~0.5 KB).
+  template <class P, int recon> struct DslashArgs {
+    using real = typename P::real;
+    Geom geom;
+    SpinorView<P> out[kMaxParity], in[kMaxParity], x[kMaxParity]; // indexed by the parity the view holds
+    GaugeView<P, recon> U;
+    CloverView<P> A;          // clover term (OP_CLOVER) or its inverse / itself for dynamic inversion (OP_CLOVER_PC)
+    GhostView<P> ghost[4][2]; // received half spinors: [dim][0 = from the backward neighbour, 1 = from the forward one]
+    size_t ghost_parity_stride[4]; // elements of P::store between the parity-0 and parity-1 halves of a face buffer
+    size_t ghost_norm_parity_stride[4];
+    real a;                   // xpay coefficient
+    int n_parity;             // 1: `parity` only; 2: both (blockIdx.y / loop selects)
+    int parity;
+    int comm_dim[4];          // dimension d is partitioned: hops across its boundary come from ghost[d]
+    int threads_ext[5];       // EXTERIOR_ALL: prefix sums of 2*face_cb[d] over partitioned dims
+  };
+
+  // which spin pair the t-direction projector keeps: P(3,+1) -> upper (spins 0,1), P(3,-1) -> lower
+  template <class P, bool upper, Cache c = Cache::REUSE>
+  B2_HD void load_spin_pair(typename P::real *h, const SpinorView<P> &f, int x_cb)
+  {
+    if constexpr (P::Ns == 8) { // fixed point, 3 planes of 8: reals 0..11 live in planes 0,1 ; 12..23 in planes 1,2
+      typename P::real t[16];
+      f.template load_planes<upper ? 0 : 1, 2, c>(t, x_cb);
+      const float n = f.load_norm(x_cb);
+#pragma unroll
+      for (int i = 0; i < 12; i++) h[i] = (upper ? t[i] : t[i + 4]) * n;
+    } else {
+      constexpr int np = 12 / P::Ns;
+      f.template load_planes<upper ? 0 : np, np, c>(h, x_cb);
+    }
+  }
+
+  // Accumulate the hops of one output site.
+  //   kt == K_INTERIOR     : every hop whose source is local (periodic wrap inside non-partitioned dims)
+  //   kt == K_EXTERIOR_ALL : only hops that cross a partitioned boundary, sources read from the ghost buffers
+  template <class P, int recon, bool dagger, KernelType kt>
+  B2_HD void wilson_hops(typename P::real *acc, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    const SpinorView<P> &in = arg.in[1 - parity];
+
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      // ---------------- forward hop: U_d(x) P(d, dagger ? + : -) in(x + d)
+      {
+        constexpr int sign = dagger ? +1 : -1;
+        const bool boundary = (x[d] + 1 >= g.X[d]);
+        const bool ghost = boundary && arg.comm_dim[d];
+        if (kt == K_INTERIOR ? !ghost : ghost) {
+          real u[18], h[12], r[12];
+          arg.U.load(u, d, x_cb, parity);
+          if (kt == K_EXTERIOR_ALL) {
+            GhostView<P> gv = arg.ghost[d][1];
+            gv.v += (1 - parity) * arg.ghost_parity_stride[d];
+            if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
+            gv.load(h, face_index(x, g, d));
+          } else {
+            int y[4] = {x[0], x[1], x[2], x[3]};
+            y[d] = boundary ? 0 : x[d] + 1;
+            const int n_cb = cb_from_coords(y, g);
+            if (d == 3) {
+              real t[12];
+              load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+#pragma unroll
+              for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+            } else {
+              real v[24];
+              in.load(v, n_cb);
+              project(h, v, d, sign);
+            }
+          }
+          su3_mul<false>(r, u, h);
+          reconstruct_add(acc, r, d, sign);
+        }
+      }
+      // ---------------- backward hop: U_d(x - d)^dagger P(d, dagger ? - : +) in(x - d)
+      {
+        constexpr int sign = dagger ? -1 : +1;
+        const bool boundary = (x[d] - 1 < 0);
+        const bool ghost = boundary && arg.comm_dim[d];
+        if (kt == K_INTERIOR ? !ghost : ghost) {
+          real u[18], h[12], r[12];
+          if (kt == K_EXTERIOR_ALL) {
+            const int fidx = face_index(x, g, d);
+            arg.U.load(u, d, g.volume_cb + fidx, 1 - parity); // ghost link lives in the pad
+            GhostView<P> gv = arg.ghost[d][0];
+            gv.v += (1 - parity) * arg.ghost_parity_stride[d];
+            if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
+            gv.load(h, fidx);
+          } else {
+            int y[4] = {x[0], x[1], x[2], x[3]};
+            y[d] = boundary ? g.X[d] - 1 : x[d] - 1;
+            const int n_cb = cb_from_coords(y, g);
+            arg.U.load(u, d, n_cb, 1 - parity);
+            if (d == 3) {
+              real t[12];
+              load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+#pragma unroll
+              for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+            } else {
+              real v[24];
+              in.load(v, n_cb);
+              project(h, v, d, sign);
+            }
+          }
+          su3_mul<true>(r, u, h);
+          reconstruct_add(acc, r, d, sign);
+        }
+      }
+    }
+  }
+
+  // true if every hop of this site is accounted for once the current kernel has run
+  // (dslash_helper.cuh:70-89 isComplete): interior kernel -> site touches no partitioned boundary.
+  template <class P, int recon> B2_HD bool site_is_interior(const DslashArgs<P, recon> &arg, const int *x)
+  {
+    bool inner = true;
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+      if (arg.comm_dim[d] && (x[d] == 0 || x[d] == arg.geom.X[d] - 1)) inner = false;
+    return inner;
+  }
+
+  // Full site update for the interior kernel.
+  //   OP_WILSON    : out = D in                     | xpay: out = x + a D in
+  //   OP_CLOVER    : (xpay only)                      out = A x + a D in
+  //   OP_CLOVER_PC : out = A^{-1} D in              | xpay: out = x + a A^{-1} D in
+  // With partitioned dims, boundary sites only store their partial sum (the exterior kernel finishes them).
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  B2_HD void dslash_site_interior(const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
+  {
+    using real = typename P::real;
+    real acc[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) acc[i] = 0;
+    wilson_hops<P, recon, dagger, K_INTERIOR>(acc, arg, x, x_cb, parity);
+
+    const bool complete = site_is_interior(arg, x);
+    if constexpr (op == OP_CLOVER_PC) {
+      if (complete) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+    }
+    if constexpr (xpay) {
+      real xv[24];
+      arg.x[parity].template load<Cache::STREAM>(xv, x_cb);
+      if constexpr (op == OP_CLOVER) clover_apply_site<P, false>(xv, arg.A, x_cb, parity);
+      if (op != OP_CLOVER_PC || complete) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
+      }
+      // OP_CLOVER_PC on an incomplete site: store the bare partial sum; x and a are applied by the exterior kernel
+      // after A^{-1} (dslash_wilson_clover_preconditioned.cuh:74-101)
+    }
+    arg.out[parity].save(acc, x_cb);
+  }
+
+  // Exterior update: out += ghost hops (read-modify-write), applying what the interior kernel had to defer.
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  B2_HD void dslash_site_exterior(const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
+  {
+    using real = typename P::real;
+    real acc[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) acc[i] = 0;
+    wilson_hops<P, recon, dagger, K_EXTERIOR_ALL>(acc, arg, x, x_cb, parity);
+    real partial[24];
+    arg.out[parity].template load<Cache::STREAM>(partial, x_cb);
+    if constexpr (op == OP_CLOVER_PC) {
+#pragma unroll
+      for (int i = 0; i < 24; i++) acc[i] += partial[i];
+      clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+      if constexpr (xpay) {
+        real xv[24];
+        arg.x[parity].template load<Cache::STREAM>(xv, x_cb);
+#pragma unroll
+        for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 24; i++) acc[i] = partial[i] + (xpay ? arg.a * acc[i] : acc[i]);
+    }
+    arg.out[parity].save(acc, x_cb);
+  }
+
+  // Fused-exterior thread -> (dim, face, face index) decode and the corner-ownership rule: a boundary site that lies
+  // on several partitioned faces is updated once, by the thread of the highest such dimension (backward face before
+  // forward face when X[d] == 2 would alias; we require X[d] >= 4 for partitioned dims so faces never alias).
+  // Returns false if this thread has nothing to do.  (dslash_helper.cuh:202-242 restated.)
+  template <class P, int recon>
+  B2_HD bool exterior_thread_site(int *x, int &x_cb, const DslashArgs<P, recon> &arg, int tid, int parity)
+  {
+    const Geom &g = arg.geom;
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (tid >= arg.threads_ext[k + 1]) d = k + 1;
+    // threads_ext[k+1]-threads_ext[k] is 0 for non-partitioned dims, so d lands on a partitioned dim
+    const int local = tid - arg.threads_ext[d];
+    const int face = local >= g.face_cb[d] ? 1 : 0;
+    const int idx = local - face * g.face_cb[d];
+    coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, parity);
+    // ownership: skip if a higher partitioned dimension also has this site on one of its faces
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+      if (e > d && arg.comm_dim[e] && (x[e] == 0 || x[e] == g.X[e] - 1)) return false;
+    x_cb = cb_from_coords(x, g);
+    return true;
+  }
+
+} // namespace b200

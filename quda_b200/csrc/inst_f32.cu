@@ -1,0 +1,9 @@
+// Instantiates every Dslash / clover / pack kernel for storage precision PrecF32.
+#include "kernels.cuh"
+
+namespace b200
+{
+  template int launch_precision<PrecF32>(const LaunchRequest &);
+  template int launch_clover_precision<PrecF32>(const CloverRequest &);
+  template int launch_pack_precision<PrecF32>(const PackRequest &);
+} // namespace b200

@@ -1,0 +1,9 @@
+// Instantiates every Dslash / clover / pack kernel for storage precision PrecF64.
+#include "kernels.cuh"
+
+namespace b200
+{
+  template int launch_precision<PrecF64>(const LaunchRequest &);
+  template int launch_clover_precision<PrecF64>(const CloverRequest &);
+  template int launch_pack_precision<PrecF64>(const PackRequest &);
+} // namespace b200

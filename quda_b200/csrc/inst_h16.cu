@@ -1,0 +1,9 @@
+// Instantiates every Dslash / clover / pack kernel for storage precision PrecH16.
+#include "kernels.cuh"
+
+namespace b200
+{
+  template int launch_precision<PrecH16>(const LaunchRequest &);
+  template int launch_clover_precision<PrecH16>(const CloverRequest &);
+  template int launch_pack_precision<PrecH16>(const PackRequest &);
+} // namespace b200

@@ -1,0 +1,230 @@
+// __global__ wrappers around the site functions + the per-precision launch dispatcher.
+// One translation unit per storage precision includes this header (inst_f64.cu, inst_f32.cu, inst_h16.cu)
+// so the three compile in parallel.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "dslash_site.h"
+#include "launch.h"
+
+namespace b200
+{
+
+  // CTA -> 4-d tile of checkerboard sites, thread -> site inside the tile (x fastest so that a warp's 16-byte
+  // plane loads cover contiguous 128..512-byte runs).  A 4-d tile (instead of the reference's linear
+  // checkerboard index) keeps most +-y/z/t neighbours of a CTA's sites inside the CTA's own working set,
+  // so they are served by the SM's L1 instead of L2.
+  struct TileMap {
+    int t[4];  // tile extents: t[0] in checkerboard sites (x/2), t[1..3] in sites
+    int nt[4]; // tiles per dimension
+  };
+
+  __device__ __forceinline__ bool tile_site(int *x, int &x_cb, const Geom &g, const TileMap &tm, int parity)
+  {
+    int b = blockIdx.x;
+    const int b0 = b % tm.nt[0];
+    b /= tm.nt[0];
+    const int b1 = b % tm.nt[1];
+    b /= tm.nt[1];
+    const int b2 = b % tm.nt[2];
+    const int b3 = b / tm.nt[2];
+    int l = threadIdx.x;
+    const int l0 = l % tm.t[0];
+    l /= tm.t[0];
+    const int l1 = l % tm.t[1];
+    l /= tm.t[1];
+    const int l2 = l % tm.t[2];
+    const int l3 = l / tm.t[2];
+    const int xh = b0 * tm.t[0] + l0;
+    x[1] = b1 * tm.t[1] + l1;
+    x[2] = b2 * tm.t[2] + l2;
+    x[3] = b3 * tm.t[3] + l3;
+    if (xh >= g.Xh0 || x[1] >= g.X[1] || x[2] >= g.X[2] || x[3] >= g.X[3]) return false;
+    x[0] = 2 * xh + ((x[1] + x[2] + x[3] + parity) & 1);
+    x_cb = ((x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.Xh0 + xh;
+    return true;
+  }
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  __global__ void __launch_bounds__(512) dslash_interior_kernel(const __grid_constant__ DslashArgs<P, recon> arg,
+                                                                const __grid_constant__ TileMap tm)
+  {
+    const int parity = arg.n_parity == 2 ? blockIdx.y : arg.parity;
+    int x[4], x_cb;
+    if (!tile_site(x, x_cb, arg.geom, tm, parity)) return;
+    dslash_site_interior<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
+  }
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  __global__ void __launch_bounds__(256) dslash_exterior_kernel(const __grid_constant__ DslashArgs<P, recon> arg)
+  {
+    const int parity = arg.n_parity == 2 ? blockIdx.y : arg.parity;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= arg.threads_ext[4]) return;
+    int x[4], x_cb;
+    if (!exterior_thread_site(x, x_cb, arg, tid, parity)) return;
+    dslash_site_exterior<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
+  }
+
+  template <class P, bool inverse>
+  __global__ void __launch_bounds__(256) clover_apply_kernel(SpinorView<P> out, SpinorView<P> in, CloverView<P> A,
+                                                             int volume_cb, int parity)
+  {
+    const int x_cb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x_cb >= volume_cb) return;
+    typename P::real v[24];
+    in.template load<Cache::STREAM>(v, x_cb);
+    clover_apply_site<P, inverse>(v, A, x_cb, parity);
+    out.save(v, x_cb);
+  }
+
+  // Halo packing: one thread per (dim, face, face site); spin-project the boundary site and store the 12-real
+  // half spinor to the destination face buffer (local, or a peer GPU's ghost buffer mapped over NVLink).
+  // Face 0 (x[d] == 0) feeds the backward neighbour's forward hop, which uses P(d, dagger ? + : -);
+  // face 1 (x[d] == X[d]-1) feeds the forward neighbour's backward hop, P(d, dagger ? - : +).
+  // (reference: include/kernels/dslash_pack.cuh:134-200)
+  template <class P> struct PackArgs {
+    Geom geom;
+    SpinorView<P> in;
+    GhostView<P> dst[4][2];
+    int threads[5];
+    int parity;
+    int dagger;
+  };
+
+  template <class P> __device__ __forceinline__ void pack_site(const PackArgs<P> &arg, int tid)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (tid >= arg.threads[k + 1]) d = k + 1;
+    const int local = tid - arg.threads[d];
+    const int face = local >= g.face_cb[d] ? 1 : 0;
+    const int idx = local - face * g.face_cb[d];
+    int x[4];
+    coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, arg.parity);
+    const int x_cb = cb_from_coords(x, g);
+    const int sign = (face == 0) ? (arg.dagger ? +1 : -1) : (arg.dagger ? -1 : +1);
+    real v[24], h[12];
+    arg.in.load(v, x_cb);
+    switch (d) {
+    case 0: project(h, v, 0, sign); break;
+    case 1: project(h, v, 1, sign); break;
+    case 2: project(h, v, 2, sign); break;
+    default: project(h, v, 3, sign); break;
+    }
+    arg.dst[d][face].save(h, idx);
+  }
+
+  template <class P> __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackArgs<P> arg)
+  {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= arg.threads[4]) return;
+    pack_site(arg, tid);
+  }
+
+  // ------------------------------------------------------------------ host-side dispatch for one precision
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  int launch_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
+  {
+    cudaStream_t s = (cudaStream_t)rq.stream;
+    if (rq.kernel != B200_KERNEL_EXTERIOR) {
+      TileMap tm;
+      int threads = 1, blocks = 1;
+      for (int d = 0; d < 4; d++) {
+        tm.t[d] = rq.tile[d];
+        const int ext = d == 0 ? arg.geom.Xh0 : arg.geom.X[d];
+        tm.nt[d] = (ext + tm.t[d] - 1) / tm.t[d];
+        threads *= tm.t[d];
+        blocks *= tm.nt[d];
+      }
+      if (threads > 512 || threads < 1) return set_error(B200_ERR_INVALID, "tile volume %d outside [1,512]", threads);
+      dim3 grid(blocks, arg.n_parity, 1);
+      dslash_interior_kernel<P, recon, dagger, xpay, op><<<grid, threads, 0, s>>>(arg, tm);
+      count_launch();
+    }
+    if (rq.kernel != B200_KERNEL_INTERIOR && arg.threads_ext[4] > 0) {
+      dim3 grid((arg.threads_ext[4] + 127) / 128, arg.n_parity, 1);
+      dslash_exterior_kernel<P, recon, dagger, xpay, op><<<grid, 128, 0, s>>>(arg);
+      count_launch();
+    }
+    return check_cuda(cudaGetLastError(), "dslash launch");
+  }
+
+  template <class P, int recon> int launch_recon(const LaunchRequest &rq)
+  {
+    DslashArgs<P, recon> arg;
+    if (int rc = fill_args(arg, rq)) return rc;
+    const bool xp = rq.xpay, dg = rq.dagger;
+    switch (rq.op) {
+    case OP_WILSON:
+      if (dg)
+        return xp ? launch_config<P, recon, true, true, OP_WILSON>(rq, arg) :
+                    launch_config<P, recon, true, false, OP_WILSON>(rq, arg);
+      else
+        return xp ? launch_config<P, recon, false, true, OP_WILSON>(rq, arg) :
+                    launch_config<P, recon, false, false, OP_WILSON>(rq, arg);
+    case OP_CLOVER:
+      if (!xp) return set_error(B200_ERR_INVALID, "ApplyWilsonClover exists in xpay form only (a != 0)");
+      return dg ? launch_config<P, recon, true, true, OP_CLOVER>(rq, arg) :
+                  launch_config<P, recon, false, true, OP_CLOVER>(rq, arg);
+    case OP_CLOVER_PC:
+      if (dg)
+        return xp ? launch_config<P, recon, true, true, OP_CLOVER_PC>(rq, arg) :
+                    launch_config<P, recon, true, false, OP_CLOVER_PC>(rq, arg);
+      else
+        return xp ? launch_config<P, recon, false, true, OP_CLOVER_PC>(rq, arg) :
+                    launch_config<P, recon, false, false, OP_CLOVER_PC>(rq, arg);
+    }
+    return set_error(B200_ERR_INVALID, "unknown op %d", rq.op);
+  }
+
+  template <class P> int launch_precision(const LaunchRequest &rq)
+  {
+    switch (rq.reconstruct) {
+    case 18: return launch_recon<P, 18>(rq);
+    case 12: return launch_recon<P, 12>(rq);
+    case 8: return launch_recon<P, 8>(rq);
+    }
+    return set_error(B200_ERR_INVALID, "reconstruct %d not in {18,12,8}", rq.reconstruct);
+  }
+
+  template <class P> int launch_clover_precision(const CloverRequest &rq)
+  {
+    SpinorView<P> out, in;
+    CloverView<P> A;
+    fill_spinor(out, rq.out, rq.out_norm, rq.volume_cb);
+    fill_spinor(in, rq.in, rq.in_norm, rq.volume_cb);
+    fill_clover(A, rq.A, rq.volume_cb);
+    const int blocks = (rq.volume_cb + 127) / 128;
+    cudaStream_t s = (cudaStream_t)rq.stream;
+    if (rq.inverse)
+      clover_apply_kernel<P, true><<<blocks, 128, 0, s>>>(out, in, A, rq.volume_cb, rq.parity);
+    else
+      clover_apply_kernel<P, false><<<blocks, 128, 0, s>>>(out, in, A, rq.volume_cb, rq.parity);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "clover launch");
+  }
+
+  template <class P> int launch_pack_precision(const PackRequest &rq)
+  {
+    PackArgs<P> arg;
+    geom_init(arg.geom, rq.X);
+    fill_spinor(arg.in, rq.in, rq.in_norm, arg.geom.volume_cb);
+    arg.parity = rq.parity;
+    arg.dagger = rq.dagger;
+    arg.threads[0] = 0;
+    for (int d = 0; d < 4; d++) {
+      arg.threads[d + 1] = arg.threads[d] + (rq.comm_dim[d] ? 2 * arg.geom.face_cb[d] : 0);
+      for (int dir = 0; dir < 2; dir++) fill_ghost(arg.dst[d][dir], rq.dst[d][dir], rq.dst_norm[d][dir], arg.geom.face_cb[d]);
+    }
+    if (arg.threads[4] == 0) return 0;
+    pack_kernel<P><<<(arg.threads[4] + 127) / 128, 128, 0, (cudaStream_t)rq.stream>>>(arg);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "pack launch");
+  }
+
+} // namespace b200

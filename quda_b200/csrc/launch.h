@@ -1,0 +1,204 @@
+// Host-side glue between the precision-erased C ABI (include/b200_dslash.h) and the typed kernel arguments.
+#pragma once
+
+#include <cstdarg>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/b200_dslash.h"
+#include "dslash_site.h"
+
+namespace b200
+{
+
+  int set_error(int code, const char *fmt, ...);
+  int check_cuda(cudaError_t e, const char *what);
+  void count_launch();
+
+  struct LaunchRequest {
+    int op, kernel, reconstruct, dagger, xpay, parity, n_parity;
+    int X[4], tile[4];
+    double a;
+    b200_spinor out, in, x;
+    b200_gauge U;
+    b200_clover A;
+    b200_halo halo;
+    void *stream;
+  };
+
+  struct CloverRequest {
+    void *out, *out_norm, *in, *in_norm;
+    b200_clover A;
+    int volume_cb, inverse, parity;
+    void *stream;
+  };
+
+  struct PackRequest {
+    int X[4], parity, dagger, comm_dim[4];
+    void *in, *in_norm;
+    void *dst[4][2], *dst_norm[4][2];
+    void *stream;
+  };
+
+  template <class P> void fill_spinor(SpinorView<P> &v, void *base, void *norm, int volume_cb)
+  {
+    v.v = reinterpret_cast<typename P::store *>(base);
+    v.stride = volume_cb;
+    if (P::fixed)
+      v.norm = norm ? reinterpret_cast<float *>(norm) :
+                      reinterpret_cast<float *>(reinterpret_cast<short *>(base) + (size_t)24 * volume_cb);
+    else
+      v.norm = nullptr;
+  }
+
+  // parity block `p` of a b200_spinor
+  template <class P> void fill_spinor_parity(SpinorView<P> &v, const b200_spinor &f, int p)
+  {
+    char *base = reinterpret_cast<char *>(f.v) + (size_t)p * f.parity_stride_bytes;
+    char *norm = f.norm ? reinterpret_cast<char *>(f.norm) + (size_t)p * f.parity_stride_bytes : nullptr;
+    fill_spinor(v, base, norm, f.volume_cb);
+  }
+
+  template <class P> void fill_clover(CloverView<P> &A, const b200_clover &c, int volume_cb)
+  {
+    A.c[0] = reinterpret_cast<const typename P::store *>(c.clover);
+    A.c[1] = reinterpret_cast<const typename P::store *>(reinterpret_cast<const char *>(c.clover) + c.parity_stride_bytes);
+    A.volume_cb = volume_cb;
+    A.compressed = c.compressed;
+    A.dynamic = c.dynamic_inverse;
+    A.diagonal = (typename P::real)c.diagonal;
+    A.nrm = (float)(c.max_element / (2.0 * 32767.0)); // clover_field_order.h:621-624
+  }
+
+  template <class P> void fill_ghost(GhostView<P> &g, void *base, void *norm, int face_cb)
+  {
+    g.v = reinterpret_cast<typename P::store *>(base);
+    g.face_cb = face_cb;
+    if (P::fixed)
+      g.norm = norm ? reinterpret_cast<float *>(norm) :
+                      (base ? reinterpret_cast<float *>(reinterpret_cast<short *>(base) + (size_t)12 * face_cb) : nullptr);
+    else
+      g.norm = nullptr;
+  }
+
+  template <class P, int recon> int fill_args(DslashArgs<P, recon> &arg, const LaunchRequest &rq)
+  {
+    geom_init(arg.geom, rq.X);
+    const Geom &g = arg.geom;
+    arg.n_parity = rq.n_parity;
+    arg.parity = rq.parity;
+    arg.a = (typename P::real)rq.a;
+    if (rq.out.volume_cb != g.volume_cb || rq.in.volume_cb != g.volume_cb)
+      return set_error(B200_ERR_INVALID, "spinor volume_cb (%d/%d) does not match lattice (%d)", rq.out.volume_cb,
+                       rq.in.volume_cb, g.volume_cb);
+    if (rq.n_parity == 2) {
+      for (int p = 0; p < 2; p++) {
+        fill_spinor_parity(arg.out[p], rq.out, p);
+        fill_spinor_parity(arg.in[p], rq.in, p);
+        if (rq.xpay) fill_spinor_parity(arg.x[p], rq.x, p);
+      }
+    } else { // single-parity fields: `out`/`x` hold parity `parity`, `in` holds the other one
+      fill_spinor_parity(arg.out[rq.parity], rq.out, 0);
+      fill_spinor_parity(arg.in[1 - rq.parity], rq.in, 0);
+      if (rq.xpay) fill_spinor_parity(arg.x[rq.parity], rq.x, 0);
+    }
+    GaugeMeta m;
+    m.anisotropy = rq.U.anisotropy;
+    m.link_max = rq.U.link_max;
+    m.t_boundary = rq.U.t_boundary;
+    m.first_time_slice = rq.U.first_time_slice;
+    m.last_time_slice = rq.U.last_time_slice;
+    m.t_bound_cb = (g.X[3] - 1) * g.X[0] * g.X[1] * g.X[2] / 2;
+    m.volume_cb = g.volume_cb;
+    arg.U.init(rq.U.gauge, rq.U.parity_stride_bytes, rq.U.stride, m);
+    if (rq.op != OP_WILSON) fill_clover(arg.A, rq.A, g.volume_cb);
+    arg.threads_ext[0] = 0;
+    for (int d = 0; d < 4; d++) {
+      arg.comm_dim[d] = rq.halo.comm_dim[d] ? 1 : 0;
+      if (arg.comm_dim[d] && g.X[d] < 4)
+        return set_error(B200_ERR_INVALID, "partitioned dimension %d needs local extent >= 4 (got %d)", d, g.X[d]);
+      arg.threads_ext[d + 1] = arg.threads_ext[d] + (arg.comm_dim[d] ? 2 * g.face_cb[d] : 0);
+      const size_t parity_elems = (size_t)12 * g.face_cb[d] + (P::fixed ? 2 * g.face_cb[d] : 0); // norms: 1 float = 2 shorts
+      arg.ghost_parity_stride[d] = rq.n_parity == 2 ? parity_elems : 0;
+      arg.ghost_norm_parity_stride[d] = rq.n_parity == 2 ? parity_elems / 2 : 0;
+      for (int dir = 0; dir < 2; dir++) {
+        if (arg.comm_dim[d] && rq.kernel != B200_KERNEL_INTERIOR && !rq.halo.ghost[d][dir])
+          return set_error(B200_ERR_INVALID, "dimension %d is partitioned but halo.ghost[%d][%d] is NULL", d, d, dir);
+        fill_ghost(arg.ghost[d][dir], rq.halo.ghost[d][dir], rq.halo.ghost_norm[d][dir], g.face_cb[d]);
+      }
+    }
+    return 0;
+  }
+
+
+  // default launch geometry per precision: tile of checkerboard sites (x/2, y, z, t); tuned on B200, see DESIGN.md
+  inline void default_tile(int *tile, int precision, const int *X)
+  {
+    int t[4] = {8, 4, 4, 2};
+    if (precision == B200_DOUBLE) { t[0] = 8; t[1] = 4; t[2] = 2; t[3] = 2; }
+    for (int d = 0; d < 4; d++) {
+      const int ext = d == 0 ? X[0] / 2 : X[d];
+      while (t[d] > 1 && ext % t[d] != 0) t[d] /= 2;
+      if (t[d] > ext) t[d] = ext;
+      tile[d] = t[d];
+    }
+  }
+
+  // Validate a b200_dslash_args block and turn it into the precision-erased launch request
+  // (shared by the CUDA library and the test-only host twin so both see identical argument semantics).
+  inline int make_request(LaunchRequest &rq, const b200_dslash_args *a, bool &nothing_to_do)
+  {
+    nothing_to_do = false;
+    if (!a) return set_error(B200_ERR_INVALID, "null args");
+    if (a->abi_version != B200_ABI_VERSION)
+      return set_error(B200_ERR_INVALID, "ABI version mismatch: caller %d, library %d", a->abi_version, B200_ABI_VERSION);
+    for (int d = 0; d < 4; d++)
+      if (a->X[d] < 2 || (a->X[d] & 1)) return set_error(B200_ERR_INVALID, "X[%d]=%d must be even and >= 2", d, a->X[d]);
+    if (!a->out.v || !a->in.v || !a->U.gauge) return set_error(B200_ERR_INVALID, "null field pointer");
+    if (a->out.v == a->in.v) return set_error(B200_ERR_INVALID, "out and in must not alias (dslash_helper.cuh:355)");
+    if (a->out.n_parity != a->in.n_parity || (a->out.n_parity != 1 && a->out.n_parity != 2))
+      return set_error(B200_ERR_INVALID, "out/in site subsets differ or are invalid (%d/%d)", a->out.n_parity, a->in.n_parity);
+    if (a->out.n_parity == 1 && a->parity != 0 && a->parity != 1)
+      return set_error(B200_ERR_INVALID, "parity %d invalid for single-parity fields", a->parity);
+    if (a->op != B200_OP_WILSON && a->op != B200_OP_CLOVER && a->op != B200_OP_CLOVER_PC)
+      return set_error(B200_ERR_INVALID, "unknown op %d", a->op);
+    if (a->op != B200_OP_WILSON && !a->A.clover) return set_error(B200_ERR_INVALID, "clover operator without clover field");
+    if (a->op == B200_OP_CLOVER_PC && a->out.n_parity != 1)
+      return set_error(B200_ERR_INVALID, "preconditioned clover operator only defined on single-parity fields");
+    if (a->op == B200_OP_CLOVER_PC && a->a != 0.0 && a->dagger)
+      return set_error(B200_ERR_INVALID, "xpay with dagger is not defined for the preconditioned clover operator");
+    if (a->precision != B200_DOUBLE && a->precision != B200_SINGLE && a->precision != B200_HALF)
+      return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
+    rq.op = a->op;
+    rq.kernel = a->kernel;
+    rq.reconstruct = a->U.reconstruct;
+    rq.dagger = a->dagger ? 1 : 0;
+    rq.xpay = (a->a != 0.0) ? 1 : 0;
+    rq.a = a->a;
+    rq.parity = a->parity;
+    rq.n_parity = a->out.n_parity;
+    for (int d = 0; d < 4; d++) rq.X[d] = a->X[d];
+    if (a->tile[0] > 0) {
+      for (int d = 0; d < 4; d++) rq.tile[d] = a->tile[d] > 0 ? a->tile[d] : 1;
+    } else {
+      default_tile(rq.tile, a->precision, a->X);
+    }
+    rq.out = a->out;
+    rq.in = a->in;
+    rq.x = a->x;
+    if (rq.xpay && !rq.x.v) return set_error(B200_ERR_INVALID, "a != 0 but x is null");
+    rq.U = a->U;
+    rq.A = a->A;
+    rq.halo = a->halo;
+    rq.stream = a->stream;
+    bool any_comm = false;
+    for (int d = 0; d < 4; d++) any_comm |= (a->halo.comm_dim[d] != 0);
+    if (rq.kernel == B200_KERNEL_EXTERIOR && !any_comm) nothing_to_do = true;
+    return 0;
+  }
+
+  template <class P> int launch_precision(const LaunchRequest &rq);
+  template <class P> int launch_clover_precision(const CloverRequest &rq);
+  template <class P> int launch_pack_precision(const PackRequest &rq);
+
+} // namespace b200

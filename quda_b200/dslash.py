@@ -1,0 +1,176 @@
+"""Python mirror of the reference's Dslash entry points (include/dslash_quda.h:83-921) on top of the C ABI.
+
+`ApplyWilson`, `ApplyWilsonClover`, `ApplyWilsonCloverPreconditioned`, `ApplyClover`, `PackGhost` keep the
+reference's names and argument meaning (a == 0 -> no xpay; `parity` = destination parity; `comm_override[d] == 0`
+switches communications in dimension d off).  Fields are thin descriptors around device memory owned by the
+caller (torch tensors are used for allocation only).  Errors raise B200Error -- the equivalent of errorQuda().
+
+`backend` selects which shared object executes the call: the default (None) is libquda_b200.so on the current
+CUDA device.  Tests may pass the CPU "host twin" of the site code explicitly; it is never chosen automatically.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import fields as F
+from . import lib as L
+
+QUDA_INVALID_PARITY = -1
+
+
+class Backend:
+    def __init__(self, cdll, prefix):
+        self.lib, self.prefix = cdll, prefix
+
+    def call(self, name, *args):
+        rc = getattr(self.lib, f"{self.prefix}_{name}")(*args)
+        L.check(rc, self.lib, self.prefix)
+
+
+_cuda_backend = None
+
+
+def cuda_backend():
+    global _cuda_backend
+    if _cuda_backend is None:
+        _cuda_backend = Backend(L.load(), "b200")
+    return _cuda_backend
+
+
+def _ptr(buf):
+    if buf is None:
+        return None
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr()
+    return buf.ctypes.data
+
+
+class ColorSpinorField:
+    """Native-order spinor: n_parity blocks of [24/N planes][volume_cb][N] (+ float norms for half)."""
+
+    def __init__(self, buf, X, prec, n_parity=1):
+        self.buf, self.X, self.prec, self.n_parity = buf, [int(v) for v in X], prec, n_parity
+        self.volume_cb = F.volume_cb(X)
+        self.parity_bytes = F.spinor_bytes(X, prec)
+
+    def desc(self):
+        return L.Spinor(_ptr(self.buf), None, self.parity_bytes if self.n_parity == 2 else 0, self.volume_cb, self.n_parity)
+
+
+class GaugeField:
+    def __init__(self, buf, X, prec, recon, meta, anisotropy=1.0, t_boundary=1, first_time_slice=True, last_time_slice=True):
+        self.buf, self.X, self.prec, self.recon, self.meta = buf, [int(v) for v in X], prec, recon, meta
+        self.anisotropy, self.t_boundary = anisotropy, t_boundary
+        self.first_time_slice, self.last_time_slice = first_time_slice, last_time_slice
+
+    def desc(self):
+        return L.Gauge(_ptr(self.buf), self.meta["parity_stride_bytes"], self.meta["stride"], self.recon,
+                       self.anisotropy, self.meta["link_max"], self.t_boundary, int(self.first_time_slice),
+                       int(self.last_time_slice))
+
+
+class CloverField:
+    """Native clover (A or, for static inversion, A^{-1}); `dynamic` -> the inverse is applied by Cholesky solve."""
+
+    def __init__(self, buf, X, prec, meta, dynamic=True):
+        self.buf, self.X, self.prec, self.meta, self.dynamic = buf, [int(v) for v in X], prec, meta, dynamic
+
+    def desc(self):
+        return L.Clover(_ptr(self.buf), self.meta["parity_stride_bytes"], self.meta["compressed"], int(self.dynamic),
+                        self.meta["diagonal"], self.meta["max_element"])
+
+
+class Halo:
+    """Ghost buffers of one field exchange: ghost[d][dir] device buffers (both parities if the field is full)."""
+
+    def __init__(self):
+        self.comm_dim = [0, 0, 0, 0]
+        self.ghost = [[None, None] for _ in range(4)]
+
+    def desc(self, comm_override=None):
+        h = L.Halo()
+        for d in range(4):
+            on = self.comm_dim[d] and (comm_override is None or comm_override[d])
+            h.comm_dim[d] = 1 if on else 0
+            for dir_ in range(2):
+                h.ghost[d][dir_] = _ptr(self.ghost[d][dir_]) if on else None
+                h.ghost_norm[d][dir_] = None
+        return h
+
+
+def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=None, kernel=L.KERNEL_AUTO, tile=None,
+           stream=None, backend=None):
+    be = backend or cuda_backend()
+    args = L.DslashArgs()
+    args.abi_version = L.ABI_VERSION
+    args.op, args.kernel, args.precision = op, kernel, out.prec
+    for d in range(4):
+        args.X[d] = U.X[d]
+        args.tile[d] = tile[d] if tile else 0
+    args.parity = 0 if parity == QUDA_INVALID_PARITY else parity
+    args.dagger = int(bool(dagger))
+    args.a = float(a)
+    args.out, args.in_ = out.desc(), in_.desc()
+    if x is not None:
+        args.x = x.desc()
+    args.U = U.desc()
+    if A is not None:
+        args.A = A.desc()
+    args.halo = (halo or Halo()).desc(comm_override)
+    args.stream = stream
+    be.call("dslash_apply", C.byref(args))
+
+
+def ApplyWilson(out, in_, U, a, x, parity, dagger, comm_override=None, halo=None, **kw):
+    """out = D in (a == 0) or x + a D in.  Reference: lib/dslash_wilson.cu:9-20."""
+    _apply(L.OP_WILSON, out, in_, U, a, x, parity, dagger, comm_override, halo=halo, **kw)
+
+
+def ApplyWilsonClover(out, in_, U, A, a, x, parity, dagger, comm_override=None, halo=None, **kw):
+    """out = A x + a D in.  Reference: lib/dslash_wilson_clover.cu."""
+    _apply(L.OP_CLOVER, out, in_, U, a, x, parity, dagger, comm_override, A=A, halo=halo, **kw)
+
+
+def ApplyWilsonCloverPreconditioned(out, in_, U, A, a, x, parity, dagger, comm_override=None, halo=None, **kw):
+    """out = A^-1 D in (a == 0) or x + a A^-1 D in.  Reference: lib/dslash_wilson_clover_preconditioned.cu:13-27."""
+    _apply(L.OP_CLOVER_PC, out, in_, U, a, x, parity, dagger, comm_override, A=A, halo=halo, **kw)
+
+
+def ApplyClover(out, in_, A, inverse, parity, stream=None, backend=None):
+    """out = A in or A^-1 in on one parity.  Reference: lib/dslash_clover_helper.cu:46-54."""
+    be = backend or cuda_backend()
+    o, i, c = out.desc(), in_.desc(), A.desc()
+    be.call("clover_apply", C.byref(o), C.byref(i), C.byref(c), out.prec, int(bool(inverse)), parity, stream)
+
+
+def PackGhost(dst, in_, parity, dagger, comm_dim, stream=None, backend=None):
+    """Spin-project the faces of `in_` (sites of `parity`) into dst[d][face] (local or peer ghost buffers).
+    Reference: lib/dslash_pack2.cu:55-425."""
+    be = backend or cuda_backend()
+    a = L.PackArgs()
+    a.abi_version, a.precision = L.ABI_VERSION, in_.prec
+    for d in range(4):
+        a.X[d] = in_.X[d]
+        a.comm_dim[d] = 1 if comm_dim[d] else 0
+        for f in range(2):
+            a.dst[d][f] = _ptr(dst[d][f]) if comm_dim[d] else None
+            a.dst_norm[d][f] = None
+    a.parity, a.dagger = parity, int(bool(dagger))
+    a.in_ = in_.desc()
+    a.stream = stream
+    be.call("pack_ghost", C.byref(a))
+
+
+def flops_per_site(op=L.OP_WILSON, xpay=False):
+    """Reference flop model: include/dslash.h:475-528, lib/dslash_wilson_clover_preconditioned.hpp:52-57."""
+    f = 1320 + (48 if xpay else 0)
+    if op != L.OP_WILSON:
+        f += 552
+    return f
+
+
+def min_bytes_per_site(prec, recon, xpay=False, clover_bytes=0):
+    """Compulsory traffic B_min = 8 G + 2 S (+S xpay) (+C clover), SURVEY.md 8d / BASELINE.md section 2."""
+    G = recon * prec
+    S = 24 * prec + (4 if prec == F.HALF else 0)
+    return 8 * G + 2 * S + (S if xpay else 0) + clover_bytes

@@ -1,0 +1,97 @@
+"""ctypes binding of libquda_b200.so (C ABI: include/b200_dslash.h).
+
+The structures mirror the header field by field.  There is NO CPU fallback: if the shared library is missing,
+or no CUDA device is present, every entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libquda_b200.so")
+ABI_VERSION = 1
+
+DOUBLE, SINGLE, HALF = 8, 4, 2
+OP_WILSON, OP_CLOVER, OP_CLOVER_PC = 0, 1, 2
+KERNEL_AUTO, KERNEL_INTERIOR, KERNEL_EXTERIOR = 0, 1, 2
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Spinor(C.Structure):
+    _fields_ = [("v", C.c_void_p), ("norm", C.c_void_p), ("parity_stride_bytes", C.c_size_t),
+                ("volume_cb", C.c_int), ("n_parity", C.c_int)]
+
+
+class Gauge(C.Structure):
+    _fields_ = [("gauge", C.c_void_p), ("parity_stride_bytes", C.c_size_t), ("stride", C.c_int),
+                ("reconstruct", C.c_int), ("anisotropy", C.c_double), ("link_max", C.c_double),
+                ("t_boundary", C.c_int), ("first_time_slice", C.c_int), ("last_time_slice", C.c_int)]
+
+
+class Clover(C.Structure):
+    _fields_ = [("clover", C.c_void_p), ("parity_stride_bytes", C.c_size_t), ("compressed", C.c_int),
+                ("dynamic_inverse", C.c_int), ("diagonal", C.c_double), ("max_element", C.c_double)]
+
+
+class Halo(C.Structure):
+    _fields_ = [("comm_dim", C.c_int * 4), ("ghost", (C.c_void_p * 2) * 4), ("ghost_norm", (C.c_void_p * 2) * 4)]
+
+
+class DslashArgs(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("op", C.c_int), ("kernel", C.c_int), ("precision", C.c_int),
+                ("X", C.c_int * 4), ("parity", C.c_int), ("dagger", C.c_int), ("a", C.c_double),
+                ("out", Spinor), ("in_", Spinor), ("x", Spinor), ("U", Gauge), ("A", Clover), ("halo", Halo),
+                ("tile", C.c_int * 4), ("stream", C.c_void_p)]
+
+
+class PackArgs(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("precision", C.c_int), ("X", C.c_int * 4), ("parity", C.c_int),
+                ("dagger", C.c_int), ("in_", Spinor), ("comm_dim", C.c_int * 4), ("dst", (C.c_void_p * 2) * 4),
+                ("dst_norm", (C.c_void_p * 2) * 4), ("stream", C.c_void_p)]
+
+
+def declare(lib, prefix="b200"):
+    """Attach argtypes/restypes for the entry points shared by the CUDA library and the test-only host twin."""
+    f = getattr(lib, prefix + "_dslash_apply")
+    f.argtypes, f.restype = [C.POINTER(DslashArgs)], C.c_int
+    f = getattr(lib, prefix + "_clover_apply")
+    f.argtypes = [C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(Clover), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    f.restype = C.c_int
+    f = getattr(lib, prefix + "_pack_ghost")
+    f.argtypes, f.restype = [C.POINTER(PackArgs)], C.c_int
+    f = getattr(lib, prefix + "_last_error")
+    f.argtypes, f.restype = [], C.c_char_p
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Load libquda_b200.so (raises if it has not been built: run __graft_entry__.build() / make -C quda_b200/csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} not built -- the engine has no fallback path; run __graft_entry__.build()")
+        lib = C.CDLL(LIB_PATH)
+        declare(lib)
+        lib.b200_abi_version.restype = C.c_int
+        lib.b200_launch_count.restype = C.c_long
+        lib.b200_ghost_face_bytes.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
+        lib.b200_ghost_face_bytes.restype = C.c_size_t
+        if lib.b200_abi_version() != ABI_VERSION:
+            raise B200Error("libquda_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc, lib=None, prefix="b200"):
+    if rc != 0:
+        lib = lib or load()
+        msg = getattr(lib, prefix + "_last_error")().decode()
+        raise B200Error(f"{prefix} error {rc}: {msg}")
+
+
+EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
+                    "b200_last_error", "b200_abi_version", "b200_launch_count", "b200_reset_launch_count"]

@@ -1,0 +1,167 @@
+// TEST-ONLY "host twin": runs the product's site code (quda_b200/csrc/dslash_site.h, core.h, clover.h --
+// the exact functions the CUDA kernels call) in plain CPU loops, through the same b200_dslash_args ABI and
+// the same argument validation (launch.h::make_request / fill_args).  It exists so that layouts, gauge
+// reconstruction, fixed-point handling, clover compression and the halo index maps can be checked against the
+// CPU oracle in the CPU-only test tier.  It is NOT part of the product: nothing under quda_b200/ loads it, and
+// libquda_b200.so has no CPU path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../quda_b200/csrc/launch.h"
+
+namespace b200
+{
+  static char g_err[512] = "";
+  int set_error(int code, const char *fmt, ...)
+  {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+  }
+  int check_cuda(cudaError_t, const char *) { return 0; }
+  void count_launch() { }
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op> int run_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
+  {
+    const Geom &g = arg.geom;
+    for (int pp = 0; pp < arg.n_parity; pp++) {
+      const int parity = arg.n_parity == 2 ? pp : arg.parity;
+      if (rq.kernel != B200_KERNEL_EXTERIOR) {
+#pragma omp parallel for
+        for (int x_cb = 0; x_cb < g.volume_cb; x_cb++) {
+          int x[4];
+          coords_from_cb(x, g, x_cb, parity);
+          dslash_site_interior<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
+        }
+      }
+      if (rq.kernel != B200_KERNEL_INTERIOR) {
+#pragma omp parallel for
+        for (int tid = 0; tid < arg.threads_ext[4]; tid++) {
+          int x[4], x_cb;
+          if (exterior_thread_site(x, x_cb, arg, tid, parity)) dslash_site_exterior<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
+        }
+      }
+    }
+    return 0;
+  }
+
+  template <class P, int recon> int run_recon(const LaunchRequest &rq)
+  {
+    DslashArgs<P, recon> arg;
+    if (int rc = fill_args(arg, rq)) return rc;
+    const bool xp = rq.xpay, dg = rq.dagger;
+#define GO(D, X, O) return run_config<P, recon, D, X, O>(rq, arg)
+    switch (rq.op) {
+    case OP_WILSON:
+      if (dg) { if (xp) GO(true, true, OP_WILSON); else GO(true, false, OP_WILSON); }
+      else { if (xp) GO(false, true, OP_WILSON); else GO(false, false, OP_WILSON); }
+    case OP_CLOVER:
+      if (!xp) return set_error(B200_ERR_INVALID, "ApplyWilsonClover exists in xpay form only (a != 0)");
+      if (dg) GO(true, true, OP_CLOVER); else GO(false, true, OP_CLOVER);
+    case OP_CLOVER_PC:
+      if (dg) { if (xp) GO(true, true, OP_CLOVER_PC); else GO(true, false, OP_CLOVER_PC); }
+      else { if (xp) GO(false, true, OP_CLOVER_PC); else GO(false, false, OP_CLOVER_PC); }
+    }
+#undef GO
+    return set_error(B200_ERR_INVALID, "unknown op");
+  }
+
+  template <class P> int run_precision(const LaunchRequest &rq)
+  {
+    switch (rq.reconstruct) {
+    case 18: return run_recon<P, 18>(rq);
+    case 12: return run_recon<P, 12>(rq);
+    case 8: return run_recon<P, 8>(rq);
+    }
+    return set_error(B200_ERR_INVALID, "reconstruct %d", rq.reconstruct);
+  }
+
+  template <class P> int run_clover(const b200_spinor *out, const b200_spinor *in, const b200_clover *Ac, int inverse, int parity)
+  {
+    SpinorView<P> o, i;
+    CloverView<P> A;
+    fill_spinor(o, out->v, out->norm, out->volume_cb);
+    fill_spinor(i, in->v, in->norm, in->volume_cb);
+    fill_clover(A, *Ac, out->volume_cb);
+    for (int x_cb = 0; x_cb < out->volume_cb; x_cb++) {
+      typename P::real v[24];
+      i.load(v, x_cb);
+      if (inverse)
+        clover_apply_site<P, true>(v, A, x_cb, parity);
+      else
+        clover_apply_site<P, false>(v, A, x_cb, parity);
+      o.save(v, x_cb);
+    }
+    return 0;
+  }
+
+  // same body as kernels.cuh::pack_site (which is __device__-only because of its blockIdx plumbing)
+  template <class P> int run_pack(const b200_pack_args *a)
+  {
+    Geom g;
+    geom_init(g, a->X);
+    SpinorView<P> in;
+    fill_spinor(in, a->in.v, a->in.norm, g.volume_cb);
+    for (int d = 0; d < 4; d++) {
+      if (!a->comm_dim[d]) continue;
+      for (int face = 0; face < 2; face++) {
+        GhostView<P> dst;
+        fill_ghost(dst, a->dst[d][face], a->dst_norm[d][face], g.face_cb[d]);
+        for (int idx = 0; idx < g.face_cb[d]; idx++) {
+          int x[4];
+          coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, a->parity);
+          const int x_cb = cb_from_coords(x, g);
+          const int sign = (face == 0) ? (a->dagger ? +1 : -1) : (a->dagger ? -1 : +1);
+          typename P::real v[24], h[12];
+          in.load(v, x_cb);
+          project(h, v, d, sign);
+          dst.save(h, idx);
+        }
+      }
+    }
+    return 0;
+  }
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+const char *twin_last_error(void) { return g_err; }
+
+int twin_dslash_apply(const b200_dslash_args *a)
+{
+  LaunchRequest rq;
+  bool nothing = false;
+  if (int rc = make_request(rq, a, nothing)) return rc;
+  if (nothing) return 0;
+  switch (a->precision) {
+  case B200_DOUBLE: return run_precision<PrecF64>(rq);
+  case B200_SINGLE: return run_precision<PrecF32>(rq);
+  case B200_HALF: return run_precision<PrecH16>(rq);
+  }
+  return -1;
+}
+
+int twin_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_clover *A, int precision, int inverse, int parity, void *)
+{
+  switch (precision) {
+  case B200_DOUBLE: return run_clover<PrecF64>(out, in, A, inverse, parity);
+  case B200_SINGLE: return run_clover<PrecF32>(out, in, A, inverse, parity);
+  case B200_HALF: return run_clover<PrecH16>(out, in, A, inverse, parity);
+  }
+  return -1;
+}
+
+int twin_pack_ghost(const b200_pack_args *a)
+{
+  switch (a->precision) {
+  case B200_DOUBLE: return run_pack<PrecF64>(a);
+  case B200_SINGLE: return run_pack<PrecF32>(a);
+  case B200_HALF: return run_pack<PrecH16>(a);
+  }
+  return -1;
+}
+}
