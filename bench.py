@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- Wilson-Dslash GFLOPS / HBM GB/s on a 32^4 local volume (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libquda_b200.so on B200)
+  python bench.py --impl reference ...                     the reference's CPU dslash (oracle/_ref) on host cores
+  python bench.py --sweep                                  (dev) launch-geometry sweep, writes gpurun_out/sweep.json
+
+A "step" is ONE application of the single-parity Wilson Dslash (out_p = D in_{1-p}) to a 32^4 local lattice,
+fp32 storage/compute, 12-parameter gauge reconstruction (BASELINE.json configs[1]).  `value` = GFLOP/s with the
+reference's flop model (1320 flop per output site, include/dslash.h:475-528), whole job over all ranks, fields
+resident in HBM.  `e2e` = same metric through the C ABI with HOST (pinned) spinor buffers: H2D of the input
+spinor, Dslash, D2H of the result every step; the gauge field stays resident, as it does after loadGaugeQuda.
+Per-step working set = 302 MB (> 126 MB L2): inputs larger than L2, no explicit flush.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PREC_BYTES = {"double": 8, "single": 4, "half": 2}
+DTYPE = {"double": "f64", "single": "f32", "half": "i16-blockfloat"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--prec", default="single", choices=list(PREC_BYTES))
+    ap.add_argument("--recon", type=int, default=12, choices=[18, 12, 8])
+    ap.add_argument("--dim", type=int, nargs=4, default=[32, 32, 32, 32])
+    ap.add_argument("--tile", type=int, nargs=4, default=None)
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.check_output(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                             "-i", str(self.index)], timeout=5).decode().strip()
+                self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(X, prec, budget_s=20.0, min_reps=2):
+    """Time the reference's own host Dslash (oracle/_ref, kind 'reference'; our restatement 'port' otherwise)
+    on all host cores.  Returns (gflops, info dict)."""
+    import numpy as np
+    import oracle
+    hp = 8 if prec == "double" else 4
+    g = oracle.random_gauge(X, hp, seed=137)
+    s = oracle.random_spinor(X, hp, seed=137)
+    Vh = oracle.volume(X) // 2
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if oracle.have_ref():
+        R = oracle.Reference(X)
+        fn, kind = (lambda: R.wil_dslash(g, s, 0, 0)), "reference"
+    else:
+        fn, kind = (lambda: oracle.wil_dslash(g, s, X, 0, 0)), "port"
+    fn()
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < min_reps or (time.perf_counter() - t0 < budget_s and reps < 1000):
+        fn()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    gf = 1320.0 * Vh / dt * 1e-9
+    return gf, {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "ms_per_call": dt * 1e3,
+                "sample": f"{reps} applications of the single-parity Wilson Dslash on {'x'.join(map(str, X))} "
+                          f"({'fp64' if hp == 8 else 'fp32'} host fields), OpenMP over {cores} threads"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X = a.dim
+    per = []
+    info = None
+    for i in range(a.warmup + a.steps):
+        gf, info = cpu_reference(X, a.prec, budget_s=max(1.0, 60.0 / max(1, a.warmup + a.steps)), min_reps=1)
+        if i >= a.warmup:
+            per.append(info["ms_per_call"])
+    ms = sum(per) / len(per)
+    Vh = X[0] * X[1] * X[2] * X[3] // 2
+    val = 1320.0 * Vh / (ms * 1e-3) * 1e-9
+    info["value"] = val
+    out = {"impl": "reference", "metric": "wilson_dslash_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": a.gpus,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": DTYPE[a.prec], "data": "synthetic",
+           "config": workload(a), "cpu_baseline": info,
+           "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload(a):
+    return {"workload": f"Wilson Dslash (single parity, no xpay), {'x'.join(map(str, a.dim))} local lattice, "
+                        f"{a.prec} recon-{a.recon}, interior kernel" + (" + halo" if a.gpus > 1 else ""),
+            "l2": "per-step working set 8G+2S per site > 126 MB L2 at 32^4; no explicit flush",
+            "grid": process_grid(a.gpus)}
+
+
+def process_grid(n):
+    # split t first, then z, then y (x keeps the contiguous rows local): 2 -> (1,1,1,2) ... 8 -> (1,2,2,2)
+    g = [1, 1, 1, 1]
+    d = 3
+    while n > 1:
+        g[d] *= 2
+        n //= 2
+        d = d - 1 if d > 1 else 3
+    return g
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_b200(a):
+    import numpy as np
+    import torch
+    import oracle
+    from common import CudaMem, Problem
+    from quda_b200 import dslash as D
+    from quda_b200 import fields as F
+    from quda_b200 import lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    X = a.dim
+    prec = PREC_BYTES[a.prec]
+    Vh = F.volume_cb(X)
+
+    # synthetic fields: random SU(3) links (unitary, so all recon modes are exact) and uniform spinors, built
+    # directly in native order on the device to keep set-up time bounded
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    P = make_device_problem(X, prec, a.recon, gen)
+    src, dst = P["in"], P["out"]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(tile=None):
+        D.ApplyWilson(dst, src, P["U"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
+
+    if a.sweep:
+        return sweep(a, P, lib)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    barrier()
+    lib.b200_reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        barrier()
+        ev0.record()
+        for _ in range(a.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.b200_launch_count()
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms = ms_total / a.steps
+    flops = D.flops_per_site() * Vh * world
+    gflops = flops / (ms * 1e-3) * 1e-9
+    bmin = D.min_bytes_per_site(prec, a.recon)
+    S = 24 * prec + (4 if prec == 2 else 0)
+    bquda = 8 * a.recon * prec + 8 * S
+    peak, peak_src = measured_peaks()
+    ach = bmin * Vh / (ms * 1e-3) * 1e-9  # per GPU: per-rank bytes / per-step time
+    out = {"metric": "wilson_dslash_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps,
+           "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": DTYPE[a.prec], "data": "synthetic", "config": workload(a),
+           "hbm_gbs_effective": ach, "gbytes_quda_model": bquda * Vh / (ms * 1e-3) * 1e-9,
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": ncu_traffic(a), "peak_source": peak_src,
+                        "kernel": "dslash_interior_kernel", "algorithmic_bytes_per_launch": bmin * Vh},
+           "clocks": cs.summary()}
+
+    if rank == 0 and not a.no_e2e:
+        out["e2e"] = e2e(a, P, lib, Vh, prec, world)
+    if rank == 0 and not a.no_cpu_baseline:
+        try:
+            _, info = cpu_reference(X, a.prec, budget_s=15.0)
+            out["cpu_baseline"] = info
+        except Exception as e:  # the checker is optional for the measurement itself
+            out["cpu_baseline"] = {"value": None, "error": str(e)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ncu_traffic(a):
+    """dram bytes per launch of the interior kernel from the committed ncu capture (profiles/), if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get(f"{a.prec}-r{a.recon}")
+    return None
+
+
+def make_device_problem(X, prec, recon, gen):
+    """Native-order synthetic fields generated on the device (random unitary links via QR, uniform spinors)."""
+    import numpy as np
+    import torch
+    from quda_b200 import dslash as D
+    from quda_b200 import fields as F
+
+    Vh = F.volume_cb(X)
+    V = 2 * Vh
+    # random SU(3): QR of a complex Gaussian matrix, phases fixed, det normalised
+    z = torch.randn(4 * V, 3, 3, dtype=torch.complex128, device="cuda", generator=None)
+    q, r = torch.linalg.qr(z)
+    ph = torch.diagonal(r, dim1=-2, dim2=-1)
+    q = q * (ph / ph.abs()).conj().unsqueeze(-2)
+    det = torch.linalg.det(q)
+    q = q / det.pow(1.0 / 3.0).reshape(-1, 1, 1)
+    u = torch.view_as_real(q).reshape(4, V, 3, 3, 2).cpu().numpy()
+    gbuf, gmeta = F.gauge_to_native(u, X, prec, recon)
+    U = D.GaugeField(torch.from_numpy(gbuf).cuda(), X, prec, recon, gmeta, anisotropy=1.0, t_boundary=1)
+    rng = np.random.default_rng(7)
+    s = rng.random((Vh, 4, 3, 2))
+    sbuf = F.spinor_to_native(s, prec, rotate=False)
+    inp = D.ColorSpinorField(torch.from_numpy(sbuf).cuda(), X, prec, 1)
+    out = D.ColorSpinorField(torch.zeros(len(sbuf), dtype=torch.uint8, device="cuda"), X, prec, 1)
+    return {"U": U, "in": inp, "out": out, "host_in": sbuf}
+
+
+def e2e(a, P, lib, Vh, prec, world):
+    """Same metric through the public call with HOST spinor buffers (pinned): H2D input, Dslash, D2H result."""
+    import torch
+    from quda_b200 import dslash as D
+    nbytes = len(P["host_in"])
+    h_in = torch.from_numpy(P["host_in"]).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in, d_out = P["in"], P["out"]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def one():
+        d_in.buf.copy_(h_in, non_blocking=True)
+        D.ApplyWilson(d_out, d_in, P["U"], 0.0, None, 0, 0, tile=a.tile, stream=stream)
+        h_out.copy_(d_out.buf, non_blocking=True)
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    n = max(5, min(a.steps, 50))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(n):
+        one()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / n
+    return {"value": D.flops_per_site() * Vh * world / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": n,
+            "note": "host spinor in/out (native order, pinned); gauge resident as after loadGaugeQuda"}
+
+
+def sweep(a, P, lib):
+    """Dev tool: time the interior kernel for a list of tilings; results -> gpurun_out/sweep.json."""
+    import torch
+    from quda_b200 import dslash as D
+    from quda_b200 import fields as F
+    X = a.dim
+    prec = PREC_BYTES[a.prec]
+    Vh = F.volume_cb(X)
+    tiles = []
+    for t0 in (2, 4, 8, 16):
+        for t1 in (1, 2, 4, 8, 16, 32):
+            for t2 in (1, 2, 4, 8):
+                for t3 in (1, 2, 4, 8):
+                    v = t0 * t1 * t2 * t3
+                    if v in (64, 128, 256, 512) and t0 <= X[0] // 2 and t1 <= X[1] and t2 <= X[2] and t3 <= X[3]:
+                        tiles.append((t0, t1, t2, t3))
+    stream = torch.cuda.current_stream().cuda_stream
+    res = []
+    bmin = D.min_bytes_per_site(prec, a.recon)
+    for t in tiles:
+        for _ in range(3):
+            D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, tile=t, stream=stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 20
+        for _ in range(n):
+            D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, tile=t, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        res.append({"tile": t, "us": us, "gbs": bmin * Vh / us * 1e-3})
+    res.sort(key=lambda r: r["us"])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    name = f"sweep_{a.prec}_r{a.recon}.json"
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=0)
+    for r in res[:8]:
+        print("sweep", a.prec, a.recon, r)
+    print("sweep worst", res[-1])
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
