@@ -1,0 +1,116 @@
+"""Operator-level parity cases shared by the CPU tier (host twin) and the GPU tier (libquda_b200.so)."""
+import itertools
+
+import numpy as np
+
+import oracle
+from common import Problem, assert_close
+from quda_b200 import dslash as D
+from quda_b200 import fields as F
+
+
+def check_xpay_fullfield(mem, be, prec, recon, X=(4, 6, 4, 8)):
+    P = Problem(X, prec, recon, mem, anisotropy=1.3)
+    kappa = 0.12195
+    s, xs = P.spinor(seed=3), P.spinor(seed=4)
+    for parity, dagger in itertools.product((0, 1), (0, 1)):
+        ref = xs.astype(np.float64) - kappa * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
+        out = P.empty()
+        D.ApplyWilson(out, P.to_dev(s), P.U, -kappa, P.to_dev(xs), parity, dagger, backend=be)
+        assert_close(ref, P.to_host(out), prec, recon, f"xpay p={parity} dag={dagger}")
+    full = P.spinor(seed=9, nparity=2)
+    for dagger in (0, 1):
+        out, inp = P.empty(2), P.to_dev(full, 2)
+        D.ApplyWilson(out, inp, P.U, -kappa, inp, D.QUDA_INVALID_PARITY, dagger, backend=be)
+        assert_close(oracle.wil_mat(P.gauge, full, X, kappa, dagger), P.to_host(out), prec, recon, "full-field M")
+        out2 = P.empty(2)
+        D.ApplyWilson(out2, inp, P.U, 0.0, None, D.QUDA_INVALID_PARITY, dagger, backend=be)
+        ref = np.concatenate([oracle.wil_dslash(P.gauge, full[P.Vh:], X, 0, dagger), oracle.wil_dslash(P.gauge, full[:P.Vh], X, 1, dagger)])
+        assert_close(ref, P.to_host(out2), prec, recon, "full-field D")
+
+
+def check_clover(mem, be, prec, recon, compressed, dynamic, X=(4, 4, 6, 4)):
+    P = Problem(X, prec, recon, mem, clover=True, compressed=compressed, dynamic=dynamic)
+    kappa = 0.12195
+    s, xs = P.spinor(seed=21), P.spinor(seed=22)
+    Ainv_field = P.A if dynamic else P.Ainv
+    tolr = recon
+    for parity in (0, 1):
+        # ApplyClover: A x and A^{-1} x
+        out = P.empty()
+        D.ApplyClover(out, P.to_dev(s), P.A, False, parity, backend=be)
+        assert_close(oracle.apply_clover(P.clover, s, X, parity), P.to_host(out), prec, tolr, "ApplyClover A")
+        out = P.empty()
+        D.ApplyClover(out, P.to_dev(s), Ainv_field, True, parity, backend=be)
+        assert_close(oracle.apply_clover(P.clover_inv, s, X, parity), P.to_host(out), prec, tolr, "ApplyClover Ainv")
+        for dagger in (0, 1):
+            # preconditioned: A^{-1} D in
+            out = P.empty()
+            D.ApplyWilsonCloverPreconditioned(out, P.to_dev(s), P.U, Ainv_field, 0.0, None, parity, dagger, backend=be)
+            ref = oracle.clover_dslash(P.gauge, P.clover_inv, s, X, parity, dagger)
+            assert_close(ref, P.to_host(out), prec, tolr, f"clover-pc p={parity} dag={dagger}")
+            # unpreconditioned xpay form: A x + a D in
+            out = P.empty()
+            D.ApplyWilsonClover(out, P.to_dev(s), P.U, P.A, -kappa, P.to_dev(xs), parity, dagger, backend=be)
+            ref = oracle.apply_clover(P.clover, xs, X, parity).astype(np.float64) \
+                - kappa * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
+            assert_close(ref, P.to_host(out), prec, tolr, f"clover xpay p={parity} dag={dagger}")
+        # x + a A^{-1} D in (no dagger)
+        out = P.empty()
+        D.ApplyWilsonCloverPreconditioned(out, P.to_dev(s), P.U, Ainv_field, -kappa * kappa, P.to_dev(xs), parity, 0, backend=be)
+        ref = xs.astype(np.float64) - kappa * kappa * oracle.clover_dslash(P.gauge, P.clover_inv, s, X, parity, 0).astype(np.float64)
+        assert_close(ref, P.to_host(out), prec, tolr, "clover-pc xpay")
+
+
+def self_halo(P, mem, comm_dim, nparity=1):
+    """Ghost buffers for a single rank that is its own neighbour in every partitioned dimension."""
+    h = D.Halo()
+    for d in range(4):
+        if comm_dim[d]:
+            h.comm_dim[d] = 1
+            for dir_ in range(2):
+                h.ghost[d][dir_] = mem.empty(nparity * F.ghost_parity_bytes(P.X, P.prec, d))
+    return h
+
+
+def self_exchange(P, halo, in_field, in_parity, dagger, be, parity_slot=0):
+    """PackGhost into our own receive buffers: our low face is what the backward neighbour receives from its forward
+    side (ghost[d][1]); our high face is what the forward neighbour receives from its backward side (ghost[d][0])."""
+    dst = [[None, None] for _ in range(4)]
+    for d in range(4):
+        if halo.comm_dim[d]:
+            off = parity_slot * F.ghost_parity_bytes(P.X, P.prec, d)
+            dst[d][0] = halo.ghost[d][1][off:]
+            dst[d][1] = halo.ghost[d][0][off:]
+    D.PackGhost(dst, in_field, in_parity, dagger, halo.comm_dim, backend=be)
+
+
+def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4), xpay=False, dagger=0, clover_kw=None):
+    """Self-partitioned run (the reference's --partition trick, tests/utils/host_utils.cpp:425): pack -> ghost buffers
+    -> interior + fused exterior must reproduce the plain periodic operator."""
+    P = Problem(X, prec, recon, mem, clover=(op != "wilson"), **(clover_kw or {}))
+    kappa = 0.12195
+    s, xs = P.spinor(seed=31), P.spinor(seed=32)
+    for parity in (0, 1):
+        halo = self_halo(P, mem, comm_dim)
+        din = P.to_dev(s)
+        self_exchange(P, halo, din, 1 - parity, dagger, be)
+        out = P.empty()
+        a = -kappa if xpay else 0.0
+        xdev = P.to_dev(xs) if xpay else None
+        if op == "wilson":
+            D.ApplyWilson(out, din, P.U, a, xdev, parity, dagger, halo=halo, backend=be)
+            ref = oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
+            if xpay:
+                ref = xs.astype(np.float64) - kappa * ref
+        elif op == "clover_pc":
+            D.ApplyWilsonCloverPreconditioned(out, din, P.U, P.A if P.A.dynamic else P.Ainv, a, xdev, parity, dagger,
+                                              halo=halo, backend=be)
+            ref = oracle.clover_dslash(P.gauge, P.clover_inv, s, X, parity, dagger).astype(np.float64)
+            if xpay:
+                ref = xs.astype(np.float64) - kappa * ref
+        else:
+            D.ApplyWilsonClover(out, din, P.U, P.A, -kappa, P.to_dev(xs), parity, dagger, halo=halo, backend=be)
+            ref = oracle.apply_clover(P.clover, xs, X, parity).astype(np.float64) \
+                - kappa * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
+        assert_close(ref, P.to_host(out), prec, recon, f"partitioned {comm_dim} op={op} p={parity}")

@@ -1,0 +1,43 @@
+"""CPU tier: operator-level parity of the product's site code (host twin) against the oracle:
+xpay / dagger / full fields, clover (compressed + dynamic Cholesky, uncompressed + static inverse),
+self-partitioned halo (pack + interior + fused exterior) for all 16 partition masks."""
+import itertools
+
+import pytest
+
+import ops
+from common import HostMem, twin_backend
+
+
+@pytest.mark.parametrize("prec", [8, 4, 2])
+@pytest.mark.parametrize("recon", [18, 12, 8])
+def test_xpay_dagger_fullfield(prec, recon):
+    ops.check_xpay_fullfield(HostMem, twin_backend(), prec, recon)
+
+
+@pytest.mark.parametrize("prec", [8, 4, 2])
+@pytest.mark.parametrize("compressed,dynamic", [(True, True), (False, True), (False, False), (True, False)])
+def test_clover(prec, compressed, dynamic):
+    ops.check_clover(HostMem, twin_backend(), prec, 12, compressed, dynamic)
+
+
+MASKS = [tuple((m >> d) & 1 for d in range(4)) for m in range(1, 16)]
+
+
+@pytest.mark.parametrize("comm_dim", MASKS)
+def test_partitioned_wilson_all_masks(comm_dim):
+    ops.check_partitioned(HostMem, twin_backend(), 8, 18, comm_dim, X=(4, 6, 4, 8))
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 12), (4, 12), (4, 8), (2, 18), (2, 8)])
+@pytest.mark.parametrize("comm_dim", [(1, 0, 0, 0), (0, 0, 0, 1), (1, 1, 1, 1)])
+def test_partitioned_wilson_precisions(prec, recon, comm_dim):
+    ops.check_partitioned(HostMem, twin_backend(), prec, recon, comm_dim, xpay=True, dagger=1)
+
+
+@pytest.mark.parametrize("op", ["clover_pc", "clover"])
+@pytest.mark.parametrize("prec", [8, 2])
+@pytest.mark.parametrize("comm_dim", [(0, 1, 0, 1), (1, 1, 1, 1)])
+def test_partitioned_clover(op, prec, comm_dim):
+    ops.check_partitioned(HostMem, twin_backend(), prec, 12, comm_dim, op=op, xpay=True,
+                          clover_kw=dict(compressed=True, dynamic=True))
