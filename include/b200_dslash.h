@@ -92,6 +92,12 @@ typedef struct {
   int comm_dim[4];
   void *ghost[4][2];
   void *ghost_norm[4][2]; /* half precision only; NULL -> directly after the 12*face_cb shorts of each parity block */
+  /* Arrival flags (optional).  If wait_flag[d][dir] is non-NULL the exterior kernel spins until the 32-bit word it
+   * points to (in THIS GPU's memory, written by the neighbour's pack kernel over NVLink) has reached `seq`
+   * before it reads ghost[d][dir].  NULL: arrival is guaranteed by stream order (copy-engine / NCCL path). */
+  void *wait_flag[4][2];
+  unsigned seq;
+  int *timeout_flag; /* device word set to 1 if a wait gave up after ~2 s (never hangs the GPU); may be NULL */
 } b200_halo;
 
 typedef struct {
@@ -134,12 +140,32 @@ typedef struct {
   void *dst[4][2];      /* [d][0]: where our x[d]==0 face goes (the backward neighbour's ghost[d][1] slot);
                            [d][1]: where our x[d]==X[d]-1 face goes (the forward neighbour's ghost[d][0] slot) */
   void *dst_norm[4][2]; /* half precision */
+  /* Remote-write completion signalling (QUDA_P2P_REMOTE_WRITE without MPI in the critical path, cf.
+   * lib/dslash_policy.hpp:1682-1687, include/shmem_pack_helper.cuh:60-190): once every store of face (d,f) has
+   * been made visible system-wide, the 32-bit word signal[d][f] (in the RECEIVER's memory) is set to `seq`.
+   * `block_counter` is an 8-int zero-initialised scratch array in local device memory. */
+  void *signal[4][2];
+  int *block_counter;
+  unsigned seq;
   void *stream;
 } b200_pack_args;
 int b200_pack_ghost(const b200_pack_args *args);
 
 /* bytes of one face buffer holding BOTH parities (what b200_halo.ghost[d][dir] must point to), and of one parity */
 size_t b200_ghost_face_bytes(int precision, const int X[4], int dim);
+
+/* Halo buffers that peer GPUs must be able to map: plain cudaMalloc allocations (zero-filled) plus CUDA-IPC
+ * export / import.  Replaces the reference's static ghost buffers + IPC handle exchange
+ * (lib/lattice_field.cpp:252-470, lib/targets/cuda/comm_target.cpp:37-167); the 64-byte handles travel between
+ * ranks over whatever bootstrap the host uses (torch.distributed here, MPI in QUDA). */
+#define B200_IPC_HANDLE_BYTES 64
+int b200_comm_alloc(void **ptr, size_t bytes);
+int b200_comm_free(void *ptr);
+int b200_ipc_get_handle(void *ptr, unsigned char handle[B200_IPC_HANDLE_BYTES]);
+int b200_ipc_open_handle(const unsigned char handle[B200_IPC_HANDLE_BYTES], void **peer_ptr);
+int b200_ipc_close_handle(void *peer_ptr);
+/* synchronous cudaMemcpy(dst, src, bytes, cudaMemcpyDefault) for the small control words living in comm memory */
+int b200_comm_copy(void *dst, const void *src, size_t bytes);
 
 const char *b200_last_error(void);
 int b200_abi_version(void);

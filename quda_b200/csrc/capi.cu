@@ -98,6 +98,39 @@ int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", precision);
 }
 
+int b200_comm_alloc(void **ptr, size_t bytes)
+{
+  if (!ptr || bytes == 0) return set_error(B200_ERR_INVALID, "b200_comm_alloc: null pointer or zero size");
+  if (int rc = require_device()) return rc;
+  if (int rc = check_cuda(cudaMalloc(ptr, bytes), "cudaMalloc")) return rc;
+  return check_cuda(cudaMemset(*ptr, 0, bytes), "cudaMemset");
+}
+
+int b200_comm_free(void *ptr) { return check_cuda(cudaFree(ptr), "cudaFree"); }
+
+int b200_ipc_get_handle(void *ptr, unsigned char handle[B200_IPC_HANDLE_BYTES])
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (int rc = check_cuda(cudaIpcGetMemHandle(&h, ptr), "cudaIpcGetMemHandle")) return rc;
+  memcpy(handle, &h, sizeof(h));
+  return B200_SUCCESS;
+}
+
+int b200_ipc_open_handle(const unsigned char handle[B200_IPC_HANDLE_BYTES], void **peer_ptr)
+{
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  return check_cuda(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int b200_ipc_close_handle(void *peer_ptr) { return check_cuda(cudaIpcCloseMemHandle(peer_ptr), "cudaIpcCloseMemHandle"); }
+
+int b200_comm_copy(void *dst, const void *src, size_t bytes)
+{
+  return check_cuda(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault), "cudaMemcpy");
+}
+
 int b200_pack_ghost(const b200_pack_args *a)
 {
   if (!a || !a->in.v) return set_error(B200_ERR_INVALID, "null argument");
@@ -114,9 +147,12 @@ int b200_pack_ghost(const b200_pack_args *a)
     for (int dir = 0; dir < 2; dir++) {
       rq.dst[d][dir] = a->dst[d][dir];
       rq.dst_norm[d][dir] = a->dst_norm[d][dir];
+      rq.signal[d][dir] = a->signal[d][dir];
       if (a->comm_dim[d] && !a->dst[d][dir]) return set_error(B200_ERR_INVALID, "dst[%d][%d] is NULL", d, dir);
     }
   }
+  rq.block_counter = a->block_counter;
+  rq.seq = a->seq;
   rq.stream = a->stream;
   switch (a->precision) {
   case B200_DOUBLE: return launch_pack_precision<PrecF64>(rq);

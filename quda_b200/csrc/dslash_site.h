@@ -32,6 +32,9 @@ namespace b200
     int parity;
     int comm_dim[4];          // dimension d is partitioned: hops across its boundary come from ghost[d]
     int threads_ext[5];       // EXTERIOR_ALL: prefix sums of 2*face_cb[d] over partitioned dims
+    const unsigned *wait_flag[4][2]; // arrival flags written by the neighbours' pack kernels (nullptr: stream-ordered)
+    unsigned seq;             // value the flags must have reached
+    int *timeout_flag;        // set to 1 if a wait gives up
   };
 
   // which spin pair the t-direction projector keeps: P(3,+1) -> upper (spins 0,1), P(3,-1) -> lower

@@ -56,9 +56,47 @@ namespace b200
     dslash_site_interior<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
   }
 
+  // ---- system-scope flag helpers for the NVLink remote-write halo path
+  __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+  {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+  {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  }
+
+  // Block until every partitioned face has arrived (flag >= seq, wrap-safe).  One thread polls, the CTA follows.
+  // Gives up after ~2 s of SM clock so that a lost peer can never hang the GPU; the host sees timeout_flag.
+  template <class Arg> __device__ __forceinline__ void wait_for_halo(const Arg &arg)
+  {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+#pragma unroll
+        for (int dir = 0; dir < 2; dir++) {
+          const unsigned *f = arg.wait_flag[d][dir];
+          if (!f) continue;
+          while ((int)(ld_acquire_sys(f) - arg.seq) < 0) {
+            if (clock64() - t0 > 4000000000LL) {
+              if (arg.timeout_flag) *arg.timeout_flag = 1;
+              break;
+            }
+            __nanosleep(100);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   __global__ void __launch_bounds__(256) dslash_exterior_kernel(const __grid_constant__ DslashArgs<P, recon> arg)
   {
+    wait_for_halo(arg);
     const int parity = arg.n_parity == 2 ? blockIdx.y : arg.parity;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= arg.threads_ext[4]) return;
@@ -88,42 +126,54 @@ namespace b200
     Geom geom;
     SpinorView<P> in;
     GhostView<P> dst[4][2];
-    int threads[5];
+    unsigned *signal[4][2]; // remote arrival flags (nullptr: none)
+    int *counter;           // 8 local block counters (zero between launches)
+    unsigned seq;
+    int comm_dim[4];
     int parity;
     int dagger;
   };
 
-  template <class P> __device__ __forceinline__ void pack_site(const PackArgs<P> &arg, int tid)
+  // grid: x = blocks over the largest face, y = face id (2*d + face)
+  template <class P> __global__ void __launch_bounds__(128) pack_kernel(const __grid_constant__ PackArgs<P> arg)
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
-    int d = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (tid >= arg.threads[k + 1]) d = k + 1;
-    const int local = tid - arg.threads[d];
-    const int face = local >= g.face_cb[d] ? 1 : 0;
-    const int idx = local - face * g.face_cb[d];
-    int x[4];
-    coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, arg.parity);
-    const int x_cb = cb_from_coords(x, g);
-    const int sign = (face == 0) ? (arg.dagger ? +1 : -1) : (arg.dagger ? -1 : +1);
-    real v[24], h[12];
-    arg.in.load(v, x_cb);
-    switch (d) {
-    case 0: project(h, v, 0, sign); break;
-    case 1: project(h, v, 1, sign); break;
-    case 2: project(h, v, 2, sign); break;
-    default: project(h, v, 3, sign); break;
+    const int d = blockIdx.y >> 1, face = blockIdx.y & 1;
+    if (!arg.comm_dim[d]) return;
+    const int nblk = (g.face_cb[d] + blockDim.x - 1) / blockDim.x;
+    if ((int)blockIdx.x >= nblk) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < g.face_cb[d]) {
+      int x[4];
+      coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, arg.parity);
+      const int x_cb = cb_from_coords(x, g);
+      const int sign = (face == 0) ? (arg.dagger ? +1 : -1) : (arg.dagger ? -1 : +1);
+      real v[24], h[12];
+      arg.in.load(v, x_cb);
+      switch (d) {
+      case 0: project(h, v, 0, sign); break;
+      case 1: project(h, v, 1, sign); break;
+      case 2: project(h, v, 2, sign); break;
+      default: project(h, v, 3, sign); break;
+      }
+      arg.dst[d][face].save(h, idx);
     }
-    arg.dst[d][face].save(h, idx);
-  }
-
-  template <class P> __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackArgs<P> arg)
-  {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= arg.threads[4]) return;
-    pack_site(arg, tid);
+    unsigned *sig = arg.signal[d][face];
+    if (sig) {
+      // make this thread's (possibly remote) stores visible system-wide, then count the CTA in; the last CTA of the
+      // face publishes the sequence number in the receiver's memory
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int prev = atomicAdd(arg.counter + blockIdx.y, 1);
+        if (prev == nblk - 1) {
+          arg.counter[blockIdx.y] = 0;
+          __threadfence_system();
+          st_release_sys(sig, arg.seq);
+        }
+      }
+    }
   }
 
   // ------------------------------------------------------------------ host-side dispatch for one precision
@@ -216,13 +266,23 @@ namespace b200
     fill_spinor(arg.in, rq.in, rq.in_norm, arg.geom.volume_cb);
     arg.parity = rq.parity;
     arg.dagger = rq.dagger;
-    arg.threads[0] = 0;
+    arg.counter = rq.block_counter;
+    arg.seq = rq.seq;
+    int max_face = 0;
+    bool any_signal = false;
     for (int d = 0; d < 4; d++) {
-      arg.threads[d + 1] = arg.threads[d] + (rq.comm_dim[d] ? 2 * arg.geom.face_cb[d] : 0);
-      for (int dir = 0; dir < 2; dir++) fill_ghost(arg.dst[d][dir], rq.dst[d][dir], rq.dst_norm[d][dir], arg.geom.face_cb[d]);
+      arg.comm_dim[d] = rq.comm_dim[d] ? 1 : 0;
+      if (arg.comm_dim[d] && arg.geom.face_cb[d] > max_face) max_face = arg.geom.face_cb[d];
+      for (int dir = 0; dir < 2; dir++) {
+        fill_ghost(arg.dst[d][dir], rq.dst[d][dir], rq.dst_norm[d][dir], arg.geom.face_cb[d]);
+        arg.signal[d][dir] = arg.comm_dim[d] ? reinterpret_cast<unsigned *>(rq.signal[d][dir]) : nullptr;
+        any_signal |= (arg.signal[d][dir] != nullptr);
+      }
     }
-    if (arg.threads[4] == 0) return 0;
-    pack_kernel<P><<<(arg.threads[4] + 127) / 128, 128, 0, (cudaStream_t)rq.stream>>>(arg);
+    if (max_face == 0) return 0;
+    if (any_signal && !arg.counter) return set_error(B200_ERR_INVALID, "signal[] given without block_counter scratch");
+    dim3 grid((max_face + 127) / 128, 8, 1);
+    pack_kernel<P><<<grid, 128, 0, (cudaStream_t)rq.stream>>>(arg);
     count_launch();
     return check_cuda(cudaGetLastError(), "pack launch");
   }

@@ -37,6 +37,9 @@ namespace b200
     int X[4], parity, dagger, comm_dim[4];
     void *in, *in_norm;
     void *dst[4][2], *dst_norm[4][2];
+    void *signal[4][2];
+    int *block_counter;
+    unsigned seq;
     void *stream;
   };
 
@@ -125,8 +128,11 @@ namespace b200
         if (arg.comm_dim[d] && rq.kernel != B200_KERNEL_INTERIOR && !rq.halo.ghost[d][dir])
           return set_error(B200_ERR_INVALID, "dimension %d is partitioned but halo.ghost[%d][%d] is NULL", d, d, dir);
         fill_ghost(arg.ghost[d][dir], rq.halo.ghost[d][dir], rq.halo.ghost_norm[d][dir], g.face_cb[d]);
+        arg.wait_flag[d][dir] = arg.comm_dim[d] ? reinterpret_cast<const unsigned *>(rq.halo.wait_flag[d][dir]) : nullptr;
       }
     }
+    arg.seq = rq.halo.seq;
+    arg.timeout_flag = rq.halo.timeout_flag;
     return 0;
   }
 

@@ -35,7 +35,8 @@ class Clover(C.Structure):
 
 
 class Halo(C.Structure):
-    _fields_ = [("comm_dim", C.c_int * 4), ("ghost", (C.c_void_p * 2) * 4), ("ghost_norm", (C.c_void_p * 2) * 4)]
+    _fields_ = [("comm_dim", C.c_int * 4), ("ghost", (C.c_void_p * 2) * 4), ("ghost_norm", (C.c_void_p * 2) * 4),
+                ("wait_flag", (C.c_void_p * 2) * 4), ("seq", C.c_uint), ("timeout_flag", C.c_void_p)]
 
 
 class DslashArgs(C.Structure):
@@ -48,7 +49,8 @@ class DslashArgs(C.Structure):
 class PackArgs(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("precision", C.c_int), ("X", C.c_int * 4), ("parity", C.c_int),
                 ("dagger", C.c_int), ("in_", Spinor), ("comm_dim", C.c_int * 4), ("dst", (C.c_void_p * 2) * 4),
-                ("dst_norm", (C.c_void_p * 2) * 4), ("stream", C.c_void_p)]
+                ("dst_norm", (C.c_void_p * 2) * 4), ("signal", (C.c_void_p * 2) * 4), ("block_counter", C.c_void_p),
+                ("seq", C.c_uint), ("stream", C.c_void_p)]
 
 
 def declare(lib, prefix="b200"):
@@ -80,6 +82,13 @@ def load():
         lib.b200_launch_count.restype = C.c_long
         lib.b200_ghost_face_bytes.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
         lib.b200_ghost_face_bytes.restype = C.c_size_t
+        lib.b200_comm_alloc.argtypes, lib.b200_comm_alloc.restype = [C.POINTER(C.c_void_p), C.c_size_t], C.c_int
+        lib.b200_comm_free.argtypes, lib.b200_comm_free.restype = [C.c_void_p], C.c_int
+        lib.b200_ipc_get_handle.argtypes, lib.b200_ipc_get_handle.restype = [C.c_void_p, C.c_char_p], C.c_int
+        lib.b200_ipc_open_handle.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.b200_ipc_open_handle.restype = C.c_int
+        lib.b200_ipc_close_handle.argtypes, lib.b200_ipc_close_handle.restype = [C.c_void_p], C.c_int
+        lib.b200_comm_copy.argtypes, lib.b200_comm_copy.restype = [C.c_void_p, C.c_void_p, C.c_size_t], C.c_int
         if lib.b200_abi_version() != ABI_VERSION:
             raise B200Error("libquda_b200.so ABI version mismatch")
         _lib = lib
@@ -94,4 +103,6 @@ def check(rc, lib=None, prefix="b200"):
 
 
 EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
+                    "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
+                    "b200_ipc_close_handle", "b200_comm_copy",
                     "b200_last_error", "b200_abi_version", "b200_launch_count", "b200_reset_launch_count"]
