@@ -156,7 +156,7 @@ def process_grid(n):
     while n > 1:
         g[d] *= 2
         n //= 2
-        d = d - 1 if d > 1 else 3
+        d = d - 1 if d > 0 else 3
     return g
 
 
@@ -185,13 +185,31 @@ def run_b200(a):
 
     # synthetic fields: random SU(3) links (unitary, so all recon modes are exact) and uniform spinors, built
     # directly in native order on the device to keep set-up time bounded
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    P = make_device_problem(X, prec, a.recon, gen)
+    torch.manual_seed(1234 + rank)
+    grid = ex = None
+    if world > 1:
+        from quda_b200 import comm
+        grid = comm.ProcessGrid(comm.ProcessGrid.default_dims(world), rank)
+    P = make_device_problem(X, prec, a.recon, grid)
     src, dst = P["in"], P["out"]
     stream = torch.cuda.current_stream().cuda_stream
+    halo_mode = None
+    if world > 1:
+        # fused pack + NVLink peer-write halo; NCCL send/recv only if CUDA IPC is unavailable on this box
+        try:
+            ex = comm.HaloExchange(grid, X, prec, mode="p2p", dist=dist)
+            halo_mode = "p2p-remote-write"
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA-IPC halo unavailable ({e}); falling back to NCCL send/recv", file=sys.stderr)
+            ex = comm.HaloExchange(grid, X, prec, mode="nccl", dist=dist)
+            halo_mode = "nccl-sendrecv"
 
     def step(tile=None):
-        D.ApplyWilson(dst, src, P["U"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
+        if ex is None:
+            D.ApplyWilson(dst, src, P["U"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
+        else:
+            comm.apply_wilson_distributed(ex, dst, src, P["U"], 0.0, None, 0, 0, stream=stream, tile=tile or a.tile)
 
     if a.sweep:
         return sweep(a, P, lib)
@@ -201,13 +219,19 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, a.warmup)):
-        step()
-    barrier()
-    lib.b200_reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as cs:
+        # untimed warm-up: at least W steps, padded to ~1.5 s of the identical kernel so that the clocks the sampler
+        # sees are the clocks the timed steps (which follow without a gap) run at
+        t_w = time.perf_counter()
+        n_w = 0
+        while n_w < max(3, a.warmup) or time.perf_counter() - t_w < 1.5:
+            for _ in range(50):
+                step()
+            n_w += 50
+            torch.cuda.synchronize()
         barrier()
+        lib.b200_reset_launch_count()
         ev0.record()
         for _ in range(a.steps):
             step()
@@ -236,6 +260,10 @@ def run_b200(a):
                         "traffic": ncu_traffic(a), "peak_source": peak_src,
                         "kernel": "dslash_interior_kernel", "algorithmic_bytes_per_launch": bmin * Vh},
            "clocks": cs.summary()}
+    if world > 1:
+        out["halo"] = {"mode": halo_mode, "grid": grid.dims, "bytes_per_step_per_gpu": int(sum(
+            2 * ex.face_bytes[d] for d in range(4) if ex.comm_dim[d])), "timed_out": bool(ex.timed_out()) if halo_mode.startswith("p2p") else False}
+        out["halo"]["gbs_per_gpu"] = out["halo"]["bytes_per_step_per_gpu"] / (ms * 1e-3) * 1e-9
 
     if rank == 0 and not a.no_e2e:
         out["e2e"] = e2e(a, P, lib, Vh, prec, world)
@@ -260,8 +288,9 @@ def ncu_traffic(a):
     return None
 
 
-def make_device_problem(X, prec, recon, gen):
-    """Native-order synthetic fields generated on the device (random unitary links via QR, uniform spinors)."""
+def make_device_problem(X, prec, recon, grid=None):
+    """Native-order synthetic fields (random unitary links via QR on the device, uniform spinors).  With a process grid
+    the pad of every partitioned dimension is filled with the backward neighbour's boundary links (NCCL exchange)."""
     import numpy as np
     import torch
     from quda_b200 import dslash as D
@@ -269,16 +298,38 @@ def make_device_problem(X, prec, recon, gen):
 
     Vh = F.volume_cb(X)
     V = 2 * Vh
-    # random SU(3): QR of a complex Gaussian matrix, phases fixed, det normalised
-    z = torch.randn(4 * V, 3, 3, dtype=torch.complex128, device="cuda", generator=None)
-    q, r = torch.linalg.qr(z)
-    ph = torch.diagonal(r, dim1=-2, dim2=-1)
-    q = q * (ph / ph.abs()).conj().unsqueeze(-2)
-    det = torch.linalg.det(q)
-    q = q / det.pow(1.0 / 3.0).reshape(-1, 1, 1)
-    u = torch.view_as_real(q).reshape(4, V, 3, 3, 2).cpu().numpy()
-    gbuf, gmeta = F.gauge_to_native(u, X, prec, recon)
-    U = D.GaugeField(torch.from_numpy(gbuf).cuda(), X, prec, recon, gmeta, anisotropy=1.0, t_boundary=1)
+    # random SU(3) the way the reference's tests build it (tests/utils/host_utils.cpp:1022-1098): two random rows,
+    # Gram-Schmidt, third row = conjugate cross product -- all element-wise torch ops on the device
+    r1 = torch.randn(4 * V, 3, dtype=torch.complex128, device="cuda")
+    r2 = torch.randn(4 * V, 3, dtype=torch.complex128, device="cuda")
+    r1 = r1 / torch.linalg.vector_norm(r1, dim=1, keepdim=True)
+    r2 = r2 - (r1.conj() * r2).sum(dim=1, keepdim=True) * r1
+    r2 = r2 / torch.linalg.vector_norm(r2, dim=1, keepdim=True)
+    r0 = torch.stack([r1[:, 1] * r2[:, 2] - r1[:, 2] * r2[:, 1], r1[:, 2] * r2[:, 0] - r1[:, 0] * r2[:, 2],
+                      r1[:, 0] * r2[:, 1] - r1[:, 1] * r2[:, 0]], dim=1).conj()
+    q = torch.stack([r0, r1, r2], dim=1)
+    u = torch.view_as_real(q).reshape(4, V, 3, 3, 2).contiguous()
+    del r0, r1, r2, q
+    ghost_faces = None
+    if grid is not None:
+        import torch.distributed as dist
+        ghost_faces = [None] * 4
+        for d in range(4):
+            if grid.dims[d] == 1:
+                continue
+            g6 = u.reshape(4, 2, Vh, 3, 3, 2)
+            mine = torch.stack([g6[d, p][torch.from_numpy(F.face_sites(X, d, X[d] - 1, p)).cuda()] for p in range(2)]).contiguous()
+            theirs = torch.empty_like(mine)
+            ops = [dist.P2POp(dist.isend, mine, grid.neighbor(d, +1)), dist.P2POp(dist.irecv, theirs, grid.neighbor(d, -1))]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            torch.cuda.synchronize()
+            ghost_faces[d] = theirs
+    gbuf, gmeta = F.gauge_to_native_torch(u, X, prec, recon, ghost_faces=ghost_faces)
+    del u
+    U = D.GaugeField(gbuf, X, prec, recon, gmeta, anisotropy=1.0, t_boundary=1,
+                     first_time_slice=grid.first_time_slice() if grid else True,
+                     last_time_slice=grid.last_time_slice() if grid else True)
     rng = np.random.default_rng(7)
     s = rng.random((Vh, 4, 3, 2))
     sbuf = F.spinor_to_native(s, prec, rotate=False)
@@ -288,34 +339,52 @@ def make_device_problem(X, prec, recon, gen):
 
 
 def e2e(a, P, lib, Vh, prec, world):
-    """Same metric through the public call with HOST spinor buffers (pinned): H2D input, Dslash, D2H result."""
+    """Same metric through the public call with HOST spinor buffers (pinned): every step copies its input spinor
+    host->device, applies the Dslash and copies the result device->host.  Steps are software-pipelined over three
+    streams with double-buffered device fields (copy-in of step i+1 and copy-out of step i-1 overlap the kernel of
+    step i), the way a multi-source workload drives dslashQuda; every step still moves all of its bytes."""
     import torch
     from quda_b200 import dslash as D
     nbytes = len(P["host_in"])
     h_in = torch.from_numpy(P["host_in"]).pin_memory()
-    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    d_in, d_out = P["in"], P["out"]
-    stream = torch.cuda.current_stream().cuda_stream
+    h_out = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    d_in = [D.ColorSpinorField(torch.empty(nbytes, dtype=torch.uint8, device="cuda"), P["in"].X, prec) for _ in range(2)]
+    d_out = [D.ColorSpinorField(torch.empty(nbytes, dtype=torch.uint8, device="cuda"), P["in"].X, prec) for _ in range(2)]
+    s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_k = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def one():
-        d_in.buf.copy_(h_in, non_blocking=True)
-        D.ApplyWilson(d_out, d_in, P["U"], 0.0, None, 0, 0, tile=a.tile, stream=stream)
-        h_out.copy_(d_out.buf, non_blocking=True)
+    def run(n):
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_k[b])       # d_in[b] free once the kernel two steps back has read it
+                d_in[b].buf.copy_(h_in, non_blocking=True)
+                ev_in[b].record(s_in)
+            with torch.cuda.stream(s_k):
+                s_k.wait_event(ev_in[b])
+                s_k.wait_event(ev_out[b])      # d_out[b] free once its previous content went to the host
+                D.ApplyWilson(d_out[b], d_in[b], P["U"], 0.0, None, 0, 0, tile=a.tile, stream=s_k.cuda_stream)
+                ev_k[b].record(s_k)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_k[b])
+                h_out[b].copy_(d_out[b].buf, non_blocking=True)
+                ev_out[b].record(s_out)
 
-    for _ in range(3):
-        one()
+    run(4)
     torch.cuda.synchronize()
-    n = max(5, min(a.steps, 50))
+    n = max(6, min(a.steps, 60))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(n):
-        one()
-    ev1.record()
+    ev0.record(s_in)
+    run(n)
+    s_out.synchronize()
+    ev1.record(s_out)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / n
     return {"value": D.flops_per_site() * Vh * world / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": ms,
             "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": n,
-            "note": "host spinor in/out (native order, pinned); gauge resident as after loadGaugeQuda"}
+            "note": "host spinor in/out (native order, pinned), 3-stream pipeline; gauge resident as after loadGaugeQuda"}
 
 
 def sweep(a, P, lib):

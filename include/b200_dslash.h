@@ -167,6 +167,58 @@ int b200_ipc_close_handle(void *peer_ptr);
 /* synchronous cudaMemcpy(dst, src, bytes, cudaMemcpyDefault) for the small control words living in comm memory */
 int b200_comm_copy(void *dst, const void *src, size_t bytes);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator + solver layer ("next" rows of the scope table): the C++ classes in quda_b200/csrc/host/dirac.h mirror
+ * DiracWilson[PC] / DiracClover[PC] (lib/dirac_wilson.cpp, lib/dirac_clover.cpp) and CG with reliable updates
+ * (lib/inv_cg_quda.cpp); these entry points expose them to non-C++ hosts the way MatQuda / invertQuda
+ * (include/quda.h:1206,1337) expose QUDA's. */
+typedef struct {
+  int comm_dim[4];
+  void *send_dst[2][4][2];    /* [buffer][dim][face] peer-mapped destination of our faces */
+  void *send_signal[2][4][2]; /* matching arrival flags in the receivers' memory */
+  void *recv[2][4][2];        /* [buffer][dim][dir] local ghost buffers */
+  void *recv_flag[2][4][2];
+  int *block_counter;
+  int *timeout_flag;
+  unsigned seq;               /* exchanges started so far (all ranks advance in lock step) */
+  void (*allreduce_sum)(double *data, int n, void *user); /* NULL on a single rank */
+  void *user;
+} b200_comm;
+
+typedef struct b200_dirac_s b200_dirac; /* opaque */
+
+typedef enum { B200_DIRAC_WILSON = 0, B200_DIRAC_WILSONPC = 1, B200_DIRAC_CLOVER = 2, B200_DIRAC_CLOVERPC = 3 } b200_dirac_type;
+typedef enum { B200_MATPC_EVEN_EVEN = 0, B200_MATPC_ODD_ODD = 1, B200_MATPC_EVEN_EVEN_ASYMMETRIC = 2,
+               B200_MATPC_ODD_ODD_ASYMMETRIC = 3 } b200_matpc_type;
+typedef enum { B200_APPLY_M = 0, B200_APPLY_MDAG = 1, B200_APPLY_MDAGM = 2, B200_APPLY_DSLASH = 3,
+               B200_APPLY_DSLASH_XPAY = 4 } b200_apply;
+
+/* Dirac::create (lib/dirac.cpp).  `A`/`Ainv` may be NULL for Wilson; `comm` may be NULL on a single rank.  The
+ * descriptors are copied; the fields they point to stay owned by the caller and must outlive the operator. */
+int b200_dirac_create(b200_dirac **op, int type, int precision, const int X[4], const b200_gauge *U, const b200_clover *A,
+                      const b200_clover *Ainv, double kappa, int matpc_type, b200_comm *comm, void *stream);
+int b200_dirac_destroy(b200_dirac *op);
+/* M / Mdag / MdagM act on full fields (unpreconditioned types) or single-parity fields (PC types);
+ * DSLASH / DSLASH_XPAY take the destination parity, x and k as Dirac::Dslash[Xpay] do. */
+int b200_dirac_apply(b200_dirac *op, int what, const b200_spinor *out, const b200_spinor *in, int parity,
+                     const b200_spinor *x, double k, int dagger);
+/* Dirac::prepare / Dirac::reconstruct for a full-system solve through the preconditioned operator: src_parity /
+ * sol_parity receive which parity block of x holds the preconditioned source / solution. */
+int b200_dirac_prepare(b200_dirac *op, const b200_spinor *x, const b200_spinor *b, int *src_parity, int *sol_parity);
+int b200_dirac_reconstruct(b200_dirac *op, const b200_spinor *x, const b200_spinor *b);
+
+typedef struct {
+  double tol;       /* relative residual target |r|/|b| */
+  int maxiter;
+  double delta;     /* reliable-update threshold */
+  int iter;         /* out */
+  int reliable_updates;
+  double true_res;  /* out: |b - A x| / |b| recomputed in the precise operator */
+  double secs, gflops;
+} b200_solver_param;
+/* CG on MdagM x = b (x, b in the precise operator's precision; sloppy may equal precise) */
+int b200_invert_cg(b200_dirac *precise, b200_dirac *sloppy, const b200_spinor *x, const b200_spinor *b, b200_solver_param *param);
+
 const char *b200_last_error(void);
 int b200_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches evidence) */

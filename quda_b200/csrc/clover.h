@@ -36,7 +36,6 @@ namespace b200
   {
     using real = typename P::real;
     using V = typename P::svec;
-    using store = typename P::store;
     constexpr int N = P::Ns;
     constexpr int M = (CB + N - 1) / N;
     constexpr int Moff = CB / N;
@@ -45,13 +44,10 @@ namespace b200
 #pragma unroll
     for (int i = 0; i < M; i++) {
       const V w = ld<Cache::STREAM>(base + (size_t)(chi * Moff + i) * A.volume_cb + x_cb);
-      const store *e = reinterpret_cast<const store *>(&w);
+      vec_to_real(tmp + i * N, w);
+      if constexpr (P::fixed) {
 #pragma unroll
-      for (int j = 0; j < N; j++) {
-        if constexpr (P::fixed)
-          tmp[i * N + j] = (real)e[j] * A.nrm;
-        else
-          tmp[i * N + j] = e[j];
+        for (int j = 0; j < N; j++) tmp[i * N + j] *= A.nrm;
       }
     }
     const int sh = (chi * CB) % N;

@@ -20,6 +20,8 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__ __forceinline__
@@ -139,11 +141,65 @@ namespace b200
   template <> struct GaugeVec<PrecH16, 12> { using vec = s4; static constexpr int N = 4; };
   template <> struct GaugeVec<PrecH16, 8> { using vec = s8; static constexpr int N = 8; };
 
+  // int16 pair -> two floats.  On the device this avoids the quarter-rate I2F conversion unit: PRMT sign-extends a half
+  // word, adding it to the bit pattern of 1.5*2^23 puts the integer into the mantissa, one FADD removes the bias
+  // (exact; the integer analogue of the reference's QUDA_ALTERNATIVE_I_TO_F path, convert.h:66-78).
+  B2_HD void s16x2_to_f32(unsigned w, float &lo, float &hi)
+  {
+#if defined(__CUDA_ARCH__)
+    unsigned a, b;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(a) : "r"(w));
+    asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(b) : "r"(w));
+    lo = __int_as_float((int)(a + 0x4B400000u)) - 12582912.0f;
+    hi = __int_as_float((int)(b + 0x4B400000u)) - 12582912.0f;
+#else
+    lo = (float)(short)(w & 0xffffu);
+    hi = (float)(short)(w >> 16);
+#endif
+  }
+
+  // generic "vector of storage elements -> reals" used by every accessor
+  template <typename real, typename V> B2_HD void vec_to_real(real *out, const V &v)
+  {
+    if constexpr (sizeof(V) == sizeof(short) * 8 && alignof(V) == 16 && std::is_same<V, struct s8>::value) {
+      unsigned w[4];
+      memcpy(w, &v, sizeof(w)); // (type punning through memcpy: folded to register moves, no aliasing UB on the host)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float lo, hi;
+        s16x2_to_f32(w[k], lo, hi);
+        out[2 * k] = lo;
+        out[2 * k + 1] = hi;
+      }
+    } else if constexpr (std::is_same<V, struct s4>::value) {
+      unsigned w[2];
+      memcpy(w, &v, sizeof(w));
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        float lo, hi;
+        s16x2_to_f32(w[k], lo, hi);
+        out[2 * k] = lo;
+        out[2 * k + 1] = hi;
+      }
+    } else if constexpr (std::is_same<V, struct s2>::value) {
+      float lo, hi;
+      unsigned w;
+      memcpy(&w, &v, sizeof(w));
+      s16x2_to_f32(w, lo, hi);
+      out[0] = lo;
+      out[1] = hi;
+    } else if constexpr (std::is_same<V, struct f4>::value) {
+      out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+      out[0] = v.x; out[1] = v.y;
+    }
+  }
+
   // round-to-nearest-even float -> int16 as the reference's device path does (convert.h:84-107)
   B2_HD short f2s(float f)
   {
 #if defined(__CUDA_ARCH__)
-    return (short)__float2int_rn(f);
+    return (short)__float_as_int(f + 12582912.0f); // magic-number round to nearest even: low 16 bits hold the integer
 #else
     return (short)std::nearbyintf(f);
 #endif
@@ -247,9 +303,7 @@ namespace b200
 #pragma unroll
       for (int i = 0; i < np; i++) {
         const V t = ld<c>(base + (size_t)(p0 + i) * stride + x_cb);
-        const store *e = reinterpret_cast<const store *>(&t);
-#pragma unroll
-        for (int j = 0; j < N; j++) out[i * N + j] = (typename P::real)e[j];
+        vec_to_real(out + i * N, t);
       }
     }
 
@@ -323,9 +377,7 @@ namespace b200
 #pragma unroll
       for (int i = 0; i < 12 / N; i++) {
         const V t = ld<Cache::STREAM>(base + (size_t)i * face_cb + idx);
-        const store *e = reinterpret_cast<const store *>(&t);
-#pragma unroll
-        for (int j = 0; j < N; j++) out[i * N + j] = (typename P::real)e[j];
+        vec_to_real(out + i * N, t);
       }
       if constexpr (P::fixed) {
         const float n = ld<Cache::STREAM>(norm + idx);
@@ -421,13 +473,10 @@ namespace b200
 #pragma unroll
       for (int i = 0; i < M; i++) {
         const V w = ld<Cache::STREAM>(base + (size_t)(dir * M + i) * stride + x_cb);
-        const store *e = reinterpret_cast<const store *>(&w);
+        vec_to_real(t + i * N, w);
+        if constexpr (P::fixed) {
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-          if constexpr (P::fixed)
-            t[i * N + j] = (real)e[j] * kFixedInvMax;
-          else
-            t[i * N + j] = e[j];
+          for (int j = 0; j < N; j++) t[i * N + j] *= kFixedInvMax;
         }
       }
       if constexpr (recon == 18) {
@@ -457,7 +506,7 @@ namespace b200
     // with the roles of rows 0 and 1 swapped and row 2 negated relative to the "textbook" parametrisation.
     B2_HD static void unpack8(real *u, const real *in, real u0v)
     {
-      const real u0_inv = (real)1 / u0v;
+      const real u0_inv = rcp_((real)u0v);
       cplx<real> o[9];
       o[1] = {in[2], in[3]};
       o[2] = {in[4], in[5]};
@@ -471,7 +520,7 @@ namespace b200
       row_sum += o[1].im * o[1].im;
       row_sum += o[2].re * o[2].re;
       row_sum += o[2].im * o[2].im;
-      const real row_sum_inv = (real)1 / row_sum;
+      const real row_sum_inv = rcp_(row_sum);
       real diff = u0_inv * u0_inv - row_sum;
       const real m00 = diff > 0 ? diff * rsqrt_(diff) : (real)0;
       o[0].re *= m00;
@@ -519,10 +568,20 @@ namespace b200
       }
     }
 
+    // single precision: hardware reciprocal / sin / cos (MUFU); |error| ~1e-6, far inside the 1e-4 gate
+    B2_HD static float rcp_(float x)
+    {
+#if defined(__CUDA_ARCH__)
+      return __frcp_rn(x);
+#else
+      return 1.0f / x;
+#endif
+    }
+    B2_HD static double rcp_(double x) { return 1.0 / x; }
     B2_HD static void sincospi_(float x, float *s, float *c)
     {
 #if defined(__CUDA_ARCH__)
-      ::sincospif(x, s, c);
+      __sincosf(x * 3.14159265358979323846f, s, c);
 #else
       *s = (float)std::sin(3.14159265358979323846 * (double)x);
       *c = (float)std::cos(3.14159265358979323846 * (double)x);

@@ -54,9 +54,13 @@ namespace b200
   }
 
   // Accumulate the hops of one output site.
-  //   kt == K_INTERIOR     : every hop whose source is local (periodic wrap inside non-partitioned dims)
+  //   kt == K_INTERIOR     : every hop whose source is local (periodic wrap inside non-partitioned dims).
+  //                          Written WITHOUT branches: all 16 loads of the 8 hops are unconditional so that the
+  //                          compiler can issue the loads of later hops while earlier ones are being multiplied
+  //                          (memory-level parallelism per warp); with partitioned dims (`part`) a hop that would
+  //                          cross a partitioned boundary still loads its periodic image but is masked to zero.
   //   kt == K_EXTERIOR_ALL : only hops that cross a partitioned boundary, sources read from the ghost buffers
-  template <class P, int recon, bool dagger, KernelType kt>
+  template <class P, int recon, bool dagger, KernelType kt, bool part = true>
   B2_HD void wilson_hops(typename P::real *acc, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
   {
     using real = typename P::real;
@@ -69,30 +73,36 @@ namespace b200
       {
         constexpr int sign = dagger ? +1 : -1;
         const bool boundary = (x[d] + 1 >= g.X[d]);
-        const bool ghost = boundary && arg.comm_dim[d];
-        if (kt == K_INTERIOR ? !ghost : ghost) {
+        if constexpr (kt == K_INTERIOR) {
           real u[18], h[12], r[12];
           arg.U.load(u, d, x_cb, parity);
-          if (kt == K_EXTERIOR_ALL) {
-            GhostView<P> gv = arg.ghost[d][1];
-            gv.v += (1 - parity) * arg.ghost_parity_stride[d];
-            if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
-            gv.load(h, face_index(x, g, d));
-          } else {
-            int y[4] = {x[0], x[1], x[2], x[3]};
-            y[d] = boundary ? 0 : x[d] + 1;
-            const int n_cb = cb_from_coords(y, g);
-            if (d == 3) {
-              real t[12];
-              load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+          int y[4] = {x[0], x[1], x[2], x[3]};
+          y[d] = boundary ? 0 : x[d] + 1;
+          const int n_cb = cb_from_coords(y, g);
+          if (d == 3) {
+            real t[12];
+            load_spin_pair<P, (sign > 0)>(t, in, n_cb);
 #pragma unroll
-              for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
-            } else {
-              real v[24];
-              in.load(v, n_cb);
-              project(h, v, d, sign);
-            }
+            for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+          } else {
+            real v[24];
+            in.load(v, n_cb);
+            project(h, v, d, sign);
           }
+          su3_mul<false>(r, u, h);
+          if constexpr (part) {
+            const real m = (boundary && arg.comm_dim[d]) ? (real)0 : (real)1;
+#pragma unroll
+            for (int i = 0; i < 12; i++) r[i] *= m;
+          }
+          reconstruct_add(acc, r, d, sign);
+        } else if (boundary && arg.comm_dim[d]) {
+          real u[18], h[12], r[12];
+          arg.U.load(u, d, x_cb, parity);
+          GhostView<P> gv = arg.ghost[d][1];
+          gv.v += (1 - parity) * arg.ghost_parity_stride[d];
+          if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
+          gv.load(h, face_index(x, g, d));
           su3_mul<false>(r, u, h);
           reconstruct_add(acc, r, d, sign);
         }
@@ -101,32 +111,37 @@ namespace b200
       {
         constexpr int sign = dagger ? -1 : +1;
         const bool boundary = (x[d] - 1 < 0);
-        const bool ghost = boundary && arg.comm_dim[d];
-        if (kt == K_INTERIOR ? !ghost : ghost) {
+        if constexpr (kt == K_INTERIOR) {
           real u[18], h[12], r[12];
-          if (kt == K_EXTERIOR_ALL) {
-            const int fidx = face_index(x, g, d);
-            arg.U.load(u, d, g.volume_cb + fidx, 1 - parity); // ghost link lives in the pad
-            GhostView<P> gv = arg.ghost[d][0];
-            gv.v += (1 - parity) * arg.ghost_parity_stride[d];
-            if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
-            gv.load(h, fidx);
-          } else {
-            int y[4] = {x[0], x[1], x[2], x[3]};
-            y[d] = boundary ? g.X[d] - 1 : x[d] - 1;
-            const int n_cb = cb_from_coords(y, g);
-            arg.U.load(u, d, n_cb, 1 - parity);
-            if (d == 3) {
-              real t[12];
-              load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+          int y[4] = {x[0], x[1], x[2], x[3]};
+          y[d] = boundary ? g.X[d] - 1 : x[d] - 1;
+          const int n_cb = cb_from_coords(y, g);
+          arg.U.load(u, d, n_cb, 1 - parity);
+          if (d == 3) {
+            real t[12];
+            load_spin_pair<P, (sign > 0)>(t, in, n_cb);
 #pragma unroll
-              for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
-            } else {
-              real v[24];
-              in.load(v, n_cb);
-              project(h, v, d, sign);
-            }
+            for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+          } else {
+            real v[24];
+            in.load(v, n_cb);
+            project(h, v, d, sign);
           }
+          su3_mul<true>(r, u, h);
+          if constexpr (part) {
+            const real m = (boundary && arg.comm_dim[d]) ? (real)0 : (real)1;
+#pragma unroll
+            for (int i = 0; i < 12; i++) r[i] *= m;
+          }
+          reconstruct_add(acc, r, d, sign);
+        } else if (boundary && arg.comm_dim[d]) {
+          real u[18], h[12], r[12];
+          const int fidx = face_index(x, g, d);
+          arg.U.load(u, d, g.volume_cb + fidx, 1 - parity); // ghost link lives in the pad
+          GhostView<P> gv = arg.ghost[d][0];
+          gv.v += (1 - parity) * arg.ghost_parity_stride[d];
+          if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
+          gv.load(h, fidx);
           su3_mul<true>(r, u, h);
           reconstruct_add(acc, r, d, sign);
         }
@@ -150,16 +165,16 @@ namespace b200
   //   OP_CLOVER    : (xpay only)                      out = A x + a D in
   //   OP_CLOVER_PC : out = A^{-1} D in              | xpay: out = x + a A^{-1} D in
   // With partitioned dims, boundary sites only store their partial sum (the exterior kernel finishes them).
-  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  template <class P, int recon, bool dagger, bool xpay, OpType op, bool part = true>
   B2_HD void dslash_site_interior(const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
   {
     using real = typename P::real;
     real acc[24];
 #pragma unroll
     for (int i = 0; i < 24; i++) acc[i] = 0;
-    wilson_hops<P, recon, dagger, K_INTERIOR>(acc, arg, x, x_cb, parity);
+    wilson_hops<P, recon, dagger, K_INTERIOR, part>(acc, arg, x, x_cb, parity);
 
-    const bool complete = site_is_interior(arg, x);
+    const bool complete = part ? site_is_interior(arg, x) : true;
     if constexpr (op == OP_CLOVER_PC) {
       if (complete) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
     }

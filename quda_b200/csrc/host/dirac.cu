@@ -1,0 +1,622 @@
+// Implementation of the host-side operator / blas / solver mirror (see dirac.h for the reference citations).
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "dirac.h"
+
+namespace b200
+{
+  namespace host
+  {
+
+    static void cuda_ok(cudaError_t e, const char *what)
+    {
+      if (e != cudaSuccess) throw Error(std::string(what) + ": " + cudaGetErrorString(e));
+    }
+    static void abi_ok(int rc)
+    {
+      if (rc != B200_SUCCESS) throw Error(b200_last_error());
+    }
+
+    // ------------------------------------------------------------------ fields
+    static size_t parity_bytes_of(const int *X, int precision)
+    {
+      const size_t vcb = (size_t)X[0] * X[1] * X[2] * X[3] / 2;
+      return vcb * 24 * precision + (precision == B200_HALF ? vcb * 4 : 0);
+    }
+
+    ColorSpinorField ColorSpinorField::wrap(void *v, const int *X, int precision, int n_parity)
+    {
+      ColorSpinorField f;
+      f.v = v;
+      for (int d = 0; d < 4; d++) f.X[d] = X[d];
+      f.precision = precision;
+      f.n_parity = n_parity;
+      f.parity_bytes = parity_bytes_of(X, precision);
+      return f;
+    }
+
+    ColorSpinorField ColorSpinorField::create(const int *X, int precision, int n_parity)
+    {
+      void *p = nullptr;
+      const size_t bytes = parity_bytes_of(X, precision) * n_parity;
+      cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(ColorSpinorField)");
+      cuda_ok(cudaMemset(p, 0, bytes), "cudaMemset(ColorSpinorField)");
+      ColorSpinorField f = wrap(p, X, precision, n_parity);
+      f.owned = std::shared_ptr<void>(p, [](void *q) { cudaFree(q); });
+      return f;
+    }
+
+    ColorSpinorField ColorSpinorField::parity_view(int p) const
+    {
+      if (n_parity != 2) throw Error("parity_view of a single-parity field");
+      ColorSpinorField f = wrap(static_cast<char *>(v) + p * parity_bytes, X, precision, 1);
+      f.owned = owned;
+      return f;
+    }
+
+    b200_spinor ColorSpinorField::desc() const
+    {
+      b200_spinor s;
+      s.v = v;
+      s.norm = nullptr;
+      s.parity_stride_bytes = n_parity == 2 ? parity_bytes : 0;
+      s.volume_cb = VolumeCB();
+      s.n_parity = n_parity;
+      return s;
+    }
+
+    // ------------------------------------------------------------------ Apply*
+    static void halo_fill(b200_halo &h, const int *comm_override, const CommContext *comm)
+    {
+      memset(&h, 0, sizeof(h));
+      if (!comm) return;
+      const int b = comm->seq & 1;
+      for (int d = 0; d < 4; d++) {
+        h.comm_dim[d] = comm->comm_dim[d] && (!comm_override || comm_override[d]);
+        for (int dir = 0; dir < 2; dir++) {
+          h.ghost[d][dir] = h.comm_dim[d] ? comm->recv[b][d][dir] : nullptr;
+          h.wait_flag[d][dir] = h.comm_dim[d] ? comm->recv_flag[b][d][dir] : nullptr;
+        }
+      }
+      h.seq = comm->seq;
+      h.timeout_flag = comm->timeout_flag;
+    }
+
+    // ship the faces of `in` (single-parity field holding parity `in_parity`) to the neighbours
+    static void exchange_start(const ColorSpinorField &in, int in_parity, bool dagger, const int *comm_override,
+                               CommContext *comm, void *stream)
+    {
+      comm->seq++;
+      const int b = comm->seq & 1;
+      b200_pack_args a;
+      memset(&a, 0, sizeof(a));
+      a.abi_version = B200_ABI_VERSION;
+      a.precision = in.precision;
+      for (int d = 0; d < 4; d++) {
+        a.X[d] = in.X[d];
+        a.comm_dim[d] = comm->comm_dim[d] && (!comm_override || comm_override[d]);
+        for (int f = 0; f < 2; f++) {
+          a.dst[d][f] = comm->send_dst[b][d][f];
+          a.signal[d][f] = comm->send_signal[b][d][f];
+        }
+      }
+      a.parity = in_parity;
+      a.dagger = dagger;
+      a.in = in.desc();
+      a.block_counter = comm->block_counter;
+      a.seq = comm->seq;
+      a.stream = stream;
+      abi_ok(b200_pack_ghost(&a));
+    }
+
+    static void apply(int op, ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, const CloverField *A,
+                      bool inverse_field, double a, const ColorSpinorField &x, int parity, bool dagger,
+                      const int *comm_override, CommContext *comm, void *stream)
+    {
+      b200_dslash_args args;
+      memset(&args, 0, sizeof(args));
+      args.abi_version = B200_ABI_VERSION;
+      args.op = op;
+      args.kernel = B200_KERNEL_AUTO;
+      args.precision = in.precision;
+      for (int d = 0; d < 4; d++) args.X[d] = U.X[d];
+      args.parity = parity == QUDA_INVALID_PARITY ? 0 : parity;
+      args.dagger = dagger;
+      args.a = a;
+      args.out = out.desc();
+      args.in = in.desc();
+      if (a != 0.0) args.x = x.desc();
+      args.U = U.g;
+      if (A) args.A = (inverse_field && A->has_inverse()) ? A->cinv : A->c;
+      bool part = false;
+      if (comm)
+        for (int d = 0; d < 4; d++) part |= (comm->comm_dim[d] && (!comm_override || comm_override[d]));
+      if (part) {
+        if (in.n_parity != 1) throw Error("partitioned full-field Dslash: apply per parity (Dirac::M does)");
+        exchange_start(in, 1 - parity, dagger, comm_override, comm, stream);
+      }
+      halo_fill(args.halo, comm_override, part ? comm : nullptr);
+      args.stream = stream;
+      abi_ok(b200_dslash_apply(&args));
+    }
+
+    void ApplyWilson(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a,
+                     const ColorSpinorField &x, int parity, bool dagger, const int *comm_override, CommContext *comm,
+                     void *stream)
+    {
+      apply(B200_OP_WILSON, out, in, U, nullptr, false, a, x, parity, dagger, comm_override, comm, stream);
+    }
+
+    void ApplyWilsonClover(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, const CloverField &A,
+                           double a, const ColorSpinorField &x, int parity, bool dagger, const int *comm_override,
+                           CommContext *comm, void *stream)
+    {
+      apply(B200_OP_CLOVER, out, in, U, &A, false, a, x, parity, dagger, comm_override, comm, stream);
+    }
+
+    void ApplyWilsonCloverPreconditioned(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U,
+                                         const CloverField &A, double a, const ColorSpinorField &x, int parity,
+                                         bool dagger, const int *comm_override, CommContext *comm, void *stream)
+    {
+      apply(B200_OP_CLOVER_PC, out, in, U, &A, true, a, x, parity, dagger, comm_override, comm, stream);
+    }
+
+    void ApplyClover(ColorSpinorField &out, const ColorSpinorField &in, const CloverField &A, bool inverse, int parity,
+                     void *stream)
+    {
+      b200_spinor o = out.desc(), i = in.desc();
+      b200_clover c = (inverse && A.has_inverse()) ? A.cinv : A.c;
+      abi_ok(b200_clover_apply(&o, &i, &c, in.precision, inverse, parity, stream));
+    }
+
+    // ------------------------------------------------------------------ blas
+    namespace blas
+    {
+      static long long g_flops = 0;
+      long long flops() { return g_flops; }
+
+      static double *reduce_buf()
+      {
+        static double *d = nullptr;
+        if (!d) cuda_ok(cudaMalloc(&d, 4 * sizeof(double)), "cudaMalloc(reduce)");
+        return d;
+      }
+
+      template <typename T> __device__ __forceinline__ double blk_sum(double v, double *out)
+      {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        __shared__ double s[32];
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) s[w] = v;
+        __syncthreads();
+        if (w == 0) {
+          v = l < (blockDim.x >> 5) ? s[l] : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+          if (l == 0) atomicAdd(out, v);
+        }
+        return v;
+      }
+
+      // y = a x + b y (+ optional z update), optional reduction of |y|^2 or <x,y>; one template keeps it compact
+      enum { R_NONE = 0, R_NORM_Y = 1, R_DOT_XY = 2 };
+      template <typename Tx, typename Ty, int R>
+      __global__ void axpby_kernel(double a, const Tx *__restrict__ x, double b, Ty *__restrict__ y, size_t n, double *red,
+                                   bool write)
+      {
+        double acc = 0;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+          const double xv = x[i], yv = y[i];
+          const double r = a * xv + b * yv;
+          if (write) y[i] = (Ty)r;
+          if (R == R_NORM_Y) acc += (write ? (double)(Ty)r * (double)(Ty)r : yv * yv);
+          if (R == R_DOT_XY) acc += xv * yv;
+        }
+        if (R != R_NONE) blk_sum<double>(acc, red);
+      }
+
+      template <typename T>
+      __global__ void axpyZpbx_kernel(double a, T *__restrict__ p, T *__restrict__ x, const T *__restrict__ r, double b, size_t n)
+      {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+          const double pv = p[i];
+          x[i] = (T)((double)x[i] + a * pv);
+          p[i] = (T)((double)r[i] + b * pv);
+        }
+      }
+
+      static void check_pair(const ColorSpinorField &x, const ColorSpinorField &y)
+      {
+        if (x.Length() != y.Length()) throw Error("blas: field length mismatch");
+        if (x.precision == B200_HALF || y.precision == B200_HALF) throw Error("blas: block-float half fields not supported");
+      }
+
+      template <int R>
+      static double run(double a, const ColorSpinorField &x, double b, ColorSpinorField &y, bool write, CommContext *comm)
+      {
+        check_pair(x, y);
+        const size_t n = x.Length();
+        double *red = reduce_buf();
+        if (R != R_NONE) cuda_ok(cudaMemsetAsync(red, 0, sizeof(double)), "memset");
+        const int threads = 256, blocks = 148 * 8;
+        if (x.precision == 8 && y.precision == 8)
+          axpby_kernel<double, double, R><<<blocks, threads>>>(a, (const double *)x.v, b, (double *)y.v, n, red, write);
+        else if (x.precision == 4 && y.precision == 4)
+          axpby_kernel<float, float, R><<<blocks, threads>>>(a, (const float *)x.v, b, (float *)y.v, n, red, write);
+        else if (x.precision == 8 && y.precision == 4)
+          axpby_kernel<double, float, R><<<blocks, threads>>>(a, (const double *)x.v, b, (float *)y.v, n, red, write);
+        else
+          axpby_kernel<float, double, R><<<blocks, threads>>>(a, (const float *)x.v, b, (double *)y.v, n, red, write);
+        cuda_ok(cudaGetLastError(), "blas launch");
+        g_flops += 3 * (long long)n;
+        if (R == R_NONE) return 0.0;
+        double h = 0;
+        cuda_ok(cudaMemcpy(&h, red, sizeof(double), cudaMemcpyDeviceToHost), "memcpy(reduce)");
+        if (comm && comm->allreduce_sum) comm->allreduce_sum(&h, 1, comm->user);
+        return h;
+      }
+
+      void copy(ColorSpinorField &dst, const ColorSpinorField &src) { run<R_NONE>(1.0, src, 0.0, dst, true, nullptr); }
+      void zero(ColorSpinorField &x) { cuda_ok(cudaMemsetAsync(x.v, 0, x.Bytes()), "memset"); }
+      void ax(double a, ColorSpinorField &x) { run<R_NONE>(0.0, x, a, x, true, nullptr); }
+      void axpy(double a, const ColorSpinorField &x, ColorSpinorField &y) { run<R_NONE>(a, x, 1.0, y, true, nullptr); }
+      void xpay(const ColorSpinorField &x, double a, ColorSpinorField &y) { run<R_NONE>(1.0, x, a, y, true, nullptr); }
+      void axpby(double a, const ColorSpinorField &x, double b, ColorSpinorField &y) { run<R_NONE>(a, x, b, y, true, nullptr); }
+      double norm2(const ColorSpinorField &x, CommContext *comm)
+      {
+        return run<R_NORM_Y>(0.0, x, 1.0, const_cast<ColorSpinorField &>(x), false, comm);
+      }
+      double reDotProduct(const ColorSpinorField &x, const ColorSpinorField &y, CommContext *comm)
+      {
+        return run<R_DOT_XY>(0.0, x, 1.0, const_cast<ColorSpinorField &>(y), false, comm);
+      }
+      double axpyNorm(double a, const ColorSpinorField &x, ColorSpinorField &y, CommContext *comm)
+      {
+        return run<R_NORM_Y>(a, x, 1.0, y, true, comm);
+      }
+      double xmyNorm(const ColorSpinorField &x, ColorSpinorField &y, CommContext *comm)
+      {
+        return run<R_NORM_Y>(1.0, x, -1.0, y, true, comm);
+      }
+      void axpyZpbx(double a, ColorSpinorField &p, ColorSpinorField &x, const ColorSpinorField &r, double b)
+      {
+        check_pair(p, x);
+        check_pair(p, r);
+        if (p.precision != x.precision || p.precision != r.precision) throw Error("axpyZpbx: mixed precision");
+        const size_t n = p.Length();
+        if (p.precision == 8)
+          axpyZpbx_kernel<double><<<148 * 8, 256>>>(a, (double *)p.v, (double *)x.v, (const double *)r.v, b, n);
+        else
+          axpyZpbx_kernel<float><<<148 * 8, 256>>>(a, (float *)p.v, (float *)x.v, (const float *)r.v, b, n);
+        cuda_ok(cudaGetLastError(), "blas launch");
+        g_flops += 4 * (long long)n;
+      }
+    } // namespace blas
+
+    // ------------------------------------------------------------------ Dirac
+    Dirac::Dirac(const DiracParam &p) :
+      gauge(p.gauge), kappa(p.kappa), matpcType(p.matpcType), dagger(p.dagger), comm(p.comm), stream(p.stream)
+    {
+      if (!gauge) throw Error("Dirac: gauge field missing");
+      for (int d = 0; d < 4; d++) commDim[d] = p.commDim[d];
+      symmetric = (matpcType == QUDA_MATPC_EVEN_EVEN || matpcType == QUDA_MATPC_ODD_ODD);
+      this_parity = (matpcType == QUDA_MATPC_EVEN_EVEN || matpcType == QUDA_MATPC_EVEN_EVEN_ASYMMETRIC) ? 0 : 1;
+      other_parity = 1 - this_parity;
+    }
+
+    void Dirac::Mdag(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      flipDagger();
+      try {
+        M(out, in);
+      } catch (...) {
+        flipDagger();
+        throw;
+      }
+      flipDagger();
+    }
+
+    Dirac *Dirac::create(const std::string &type, const DiracParam &p)
+    {
+      if (type == "wilson") return new DiracWilson(p);
+      if (type == "wilsonpc") return new DiracWilsonPC(p);
+      if (type == "clover") return new DiracClover(p);
+      if (type == "cloverpc") return new DiracCloverPC(p);
+      throw Error("Dirac::create: unsupported operator type '" + type + "'");
+    }
+
+    static void check_parity_spinor(const ColorSpinorField &a, const ColorSpinorField &b)
+    {
+      if (a.n_parity != 1 || b.n_parity != 1) throw Error("ColorSpinorFields are not single parity");
+      if (a.v == b.v) throw Error("Aliasing pointers");
+    }
+    static void check_full_spinor(const ColorSpinorField &a, const ColorSpinorField &b)
+    {
+      if (a.n_parity != 2 || b.n_parity != 2) throw Error("ColorSpinorFields are not full fields");
+    }
+
+    // --- Wilson (lib/dirac_wilson.cpp:21-104)
+    void DiracWilson::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
+    {
+      check_parity_spinor(in, out);
+      ApplyWilson(out, in, *gauge, 0.0, in, parity, dagger, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracWilson::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                                 double k) const
+    {
+      check_parity_spinor(in, out);
+      ApplyWilson(out, in, *gauge, k, x, parity, dagger, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracWilson::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      check_full_spinor(out, in);
+      if (comm && comm->partitioned()) { // halo exchange works per parity
+        auto oe = out.Even(), oo = out.Odd();
+        DiracWilson::DslashXpay(oe, in.Odd(), 0, in.Even(), -kappa);
+        DiracWilson::DslashXpay(oo, in.Even(), 1, in.Odd(), -kappa);
+      } else {
+        ApplyWilson(out, in, *gauge, -kappa, in, QUDA_INVALID_PARITY, dagger, commDim, comm, stream);
+        dslash_applications += 2;
+      }
+    }
+    void DiracWilson::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      auto tmp = ColorSpinorField::create(in.X, in.precision, in.n_parity);
+      M(tmp, in);
+      Mdag(out, tmp);
+    }
+    void DiracWilson::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
+                              QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION)
+        throw Error("Preconditioned solution requires a preconditioned solve_type");
+      src = b;
+      sol = x;
+    }
+    void DiracWilson::reconstruct(ColorSpinorField &, const ColorSpinorField &, QudaSolutionType) const { }
+
+    // --- WilsonPC (lib/dirac_wilson.cpp:106-163)
+    void DiracWilsonPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      const double kappa2 = -kappa * kappa;
+      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      if (!symmetric) throw Error("MatPCType not valid for DiracWilsonPC");
+      Dslash(tmp, in, other_parity);
+      DslashXpay(out, tmp, this_parity, in, kappa2);
+    }
+    void DiracWilsonPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      M(tmp, in);
+      Mdag(out, tmp);
+    }
+    void DiracWilsonPC::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
+                                QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) {
+        src = b;
+        sol = x;
+        return;
+      }
+      // src = b_e + k D_eo b_o (stored in x_o), solution in x_e
+      auto xo = x.parity_view(other_parity);
+      DslashXpay(xo, b.parity_view(other_parity), this_parity, b.parity_view(this_parity), kappa);
+      src = xo;
+      sol = x.parity_view(this_parity);
+    }
+    void DiracWilsonPC::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
+      check_full_spinor(x, b);
+      auto xo = x.parity_view(other_parity);
+      DslashXpay(xo, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
+    }
+
+    // --- Clover (lib/dirac_clover.cpp:36-100)
+    DiracClover::DiracClover(const DiracParam &p) : DiracWilson(p), clover(p.clover)
+    {
+      if (!clover) throw Error("DiracClover: clover field missing");
+    }
+    void DiracClover::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                                 double k) const
+    {
+      check_parity_spinor(in, out);
+      ApplyWilsonClover(out, in, *gauge, *clover, k, x, parity, dagger, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracClover::Clover(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
+    {
+      ApplyClover(out, in, *clover, false, parity, stream);
+    }
+    void DiracClover::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      check_full_spinor(out, in);
+      if (comm && comm->partitioned()) {
+        auto oe = out.Even(), oo = out.Odd();
+        DiracClover::DslashXpay(oe, in.Odd(), 0, in.Even(), -kappa);
+        DiracClover::DslashXpay(oo, in.Even(), 1, in.Odd(), -kappa);
+      } else {
+        ApplyWilsonClover(out, in, *gauge, *clover, -kappa, in, QUDA_INVALID_PARITY, dagger, commDim, comm, stream);
+        dslash_applications += 2;
+      }
+    }
+    void DiracClover::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      check_full_spinor(out, in);
+      auto tmp = ColorSpinorField::create(in.X, in.precision, 2);
+      M(tmp, in);
+      Mdag(out, tmp);
+    }
+
+    // --- CloverPC (lib/dirac_clover.cpp:118-258)
+    DiracCloverPC::DiracCloverPC(const DiracParam &p) : DiracClover(p)
+    {
+      if (!clover->has_inverse() && !clover->c.dynamic_inverse) throw Error("Clover inverse required for DiracCloverPC");
+    }
+    void DiracCloverPC::CloverInv(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
+    {
+      ApplyClover(out, in, *clover, true, parity, stream);
+    }
+    void DiracCloverPC::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
+    {
+      check_parity_spinor(in, out);
+      ApplyWilsonCloverPreconditioned(out, in, *gauge, *clover, 0.0, in, parity, dagger, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracCloverPC::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                                   double k) const
+    {
+      check_parity_spinor(in, out);
+      ApplyWilsonCloverPreconditioned(out, in, *gauge, *clover, k, x, parity, dagger, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracCloverPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      const double kappa2 = -kappa * kappa;
+      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      if (!symmetric) {
+        Dslash(tmp, in, other_parity);                                   // A^-1 D
+        DiracClover::DslashXpay(out, tmp, this_parity, in, kappa2);      // A x - k^2 D
+      } else if (!dagger) {
+        Dslash(tmp, in, other_parity);
+        DslashXpay(out, tmp, this_parity, in, kappa2);                   // x - k^2 A^-1 D (A^-1 D)
+      } else {
+        CloverInv(out, in, this_parity);                                 // 1 - D^+ A^-1 D^+ A^-1
+        Dslash(tmp, out, other_parity);
+        DiracWilson::DslashXpay(out, tmp, this_parity, in, kappa2);
+      }
+    }
+    void DiracCloverPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      M(tmp, in);
+      Mdag(out, tmp);
+    }
+    void DiracCloverPC::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
+                                QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) {
+        src = b;
+        sol = x;
+        return;
+      }
+      src = x.parity_view(other_parity);
+      sol = x.parity_view(this_parity);
+      auto tmp = ColorSpinorField::create(b.X, b.precision, 1);
+      if (symmetric) { // src = A_ee^-1 (b_e + k D_eo A_oo^-1 b_o)
+        CloverInv(src, b.parity_view(other_parity), other_parity);
+        DiracWilson::DslashXpay(tmp, src, this_parity, b.parity_view(this_parity), kappa);
+        CloverInv(src, tmp, this_parity);
+      } else { // src = b_e + k D_eo A_oo^-1 b_o
+        CloverInv(tmp, b.parity_view(other_parity), other_parity);
+        DiracWilson::DslashXpay(src, tmp, this_parity, b.parity_view(this_parity), kappa);
+      }
+    }
+    void DiracCloverPC::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
+      check_full_spinor(x, b);
+      auto tmp = ColorSpinorField::create(b.X, b.precision, 1);
+      // x_o = A_oo^-1 (b_o + k D_oe x_e)
+      DiracWilson::DslashXpay(tmp, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
+      auto xo = x.parity_view(other_parity);
+      CloverInv(xo, tmp, other_parity);
+    }
+
+    // ------------------------------------------------------------------ CG (normal equations) with reliable updates
+    void invertCG(const Dirac &mat, const Dirac &matSloppy, ColorSpinorField &x, const ColorSpinorField &b, SolverParam &param)
+    {
+      using namespace blas;
+      CommContext *comm = mat.Comm();
+      const auto t0 = std::chrono::steady_clock::now();
+      const long long flops0 = blas::flops();
+      const long long ds0 = mat.DslashApplications() + matSloppy.DslashApplications();
+      const bool mixed = (&mat != &matSloppy);
+      const int sp = mixed ? 4 : x.precision; // sloppy precision
+      if (mixed && x.precision != 8) throw Error("mixed-precision CG expects a double-precision solution field");
+
+      auto r = ColorSpinorField::create(x.X, x.precision, x.n_parity);  // high-precision residual
+      auto y = ColorSpinorField::create(x.X, x.precision, x.n_parity);  // high-precision accumulated solution
+      auto tmp = ColorSpinorField::create(x.X, x.precision, x.n_parity);
+      auto rS = mixed ? ColorSpinorField::create(x.X, sp, x.n_parity) : r;
+      auto xS = ColorSpinorField::create(x.X, sp, x.n_parity);
+      auto p = ColorSpinorField::create(x.X, sp, x.n_parity);
+      auto Ap = ColorSpinorField::create(x.X, sp, x.n_parity);
+
+      const double b2 = norm2(b, comm);
+      if (b2 == 0.0) {
+        zero(x);
+        param.iter = 0;
+        param.true_res = 0.0;
+        return;
+      }
+      // r = b - A x
+      mat.MdagM(tmp, x);
+      copy(r, b);
+      axpy(-1.0, tmp, r);
+      double r2 = norm2(r, comm);
+      copy(y, x);
+      if (mixed) copy(rS, r);
+      zero(xS);
+      copy(p, rS);
+      const double stop = param.tol * param.tol * b2;
+      double rNorm = std::sqrt(r2), r0Norm = rNorm, maxrx = rNorm, maxrr = rNorm;
+      int k = 0;
+      param.reliable_updates = 0;
+      while (r2 > stop && k < param.maxiter) {
+        matSloppy.MdagM(Ap, p);
+        const double pAp = reDotProduct(p, Ap, comm);
+        const double alpha = r2 / pAp;
+        const double r2_old = r2;
+        r2 = axpyNorm(-alpha, Ap, rS, comm);
+        rNorm = std::sqrt(r2);
+        if (rNorm > maxrx) maxrx = rNorm;
+        if (rNorm > maxrr) maxrr = rNorm;
+        const bool update = mixed && ((rNorm < param.delta * maxrx && r0Norm <= maxrx) || (rNorm < param.delta * r0Norm && r0Norm <= maxrr) || r2 <= stop);
+        if (!update) {
+          const double beta = r2 / r2_old;
+          axpyZpbx(alpha, p, xS, rS, beta); // xS += alpha p ; p = rS + beta p
+        } else {
+          axpy(alpha, p, xS);
+          // reliable update: fold the sloppy solution into y, recompute the true residual in high precision
+          copy(tmp, xS);
+          axpy(1.0, tmp, y);
+          mat.MdagM(tmp, y);
+          copy(r, b);
+          r2 = axpyNorm(-1.0, tmp, r, comm);
+          copy(rS, r);
+          zero(xS);
+          // keep the search direction conjugate as far as precision allows: p = r + beta p
+          const double beta = r2 / r2_old;
+          xpay(rS, beta, p);
+          rNorm = std::sqrt(r2);
+          maxrr = maxrx = r0Norm = rNorm;
+          param.reliable_updates++;
+        }
+        k++;
+      }
+      // x = y + xS
+      copy(tmp, xS);
+      axpy(1.0, tmp, y);
+      copy(x, y);
+      // true residual
+      mat.MdagM(tmp, x);
+      copy(r, b);
+      const double tr2 = axpyNorm(-1.0, tmp, r, comm);
+      cuda_ok(cudaDeviceSynchronize(), "sync");
+      param.iter = k;
+      param.true_res = std::sqrt(tr2 / b2);
+      param.secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const long long nds = mat.DslashApplications() + matSloppy.DslashApplications() - ds0;
+      const double fl = (double)(blas::flops() - flops0) + (double)nds * 1320.0 * x.VolumeCB();
+      param.gflops = fl / param.secs * 1e-9;
+    }
+
+  } // namespace host
+} // namespace b200

@@ -151,12 +151,21 @@ def gauge_pad(X):
     return max(V // X[d] for d in range(4)) // 2
 
 
-def gauge_to_native(host, X, prec, recon, link_max=None, ghost_from=None):
+def gauge_boundary_links(host, X, d):
+    """Links U_d on the x[d] = X[d]-1 slice, [2][face_cb][3][3][2] in face-index order: what the FORWARD neighbour
+    needs in its pad (its backward-hop links across the boundary)."""
+    Vh = volume_cb(X)
+    g = np.asarray(host).reshape(4, 2, Vh, 3, 3, 2)
+    return np.stack([g[d, p][face_sites(X, d, X[d] - 1, p)] for p in range(2)])
+
+
+def gauge_to_native(host, X, prec, recon, link_max=None, ghost_from=None, ghost_faces=None):
     """host QDP-order gauge [4][V][3][3][2] (parity-major sites) -> native uint8 buffer.
 
     Layout: [parity][dir*M + i][stride][N], stride = Vh + pad.  The pad of direction d holds, at
     x_cb = Vh + face_idx, the backward neighbour's links U_d on its x[d] = X[d]-1 slice (lib/gauge_field.cpp:453-575);
-    `ghost_from[d]` is the host gauge field of that neighbour (default: this field, i.e. periodic self-neighbour).
+    `ghost_from[d]` is the host gauge field of that neighbour (default: this field, i.e. periodic self-neighbour);
+    alternatively `ghost_faces[d]` gives just those links ([2][face_cb][3][3][2], see gauge_boundary_links).
     Returns (buffer, meta) with meta = dict(stride, parity_stride_bytes, link_max).
     """
     Vh = volume_cb(X)
@@ -173,8 +182,12 @@ def gauge_to_native(host, X, prec, recon, link_max=None, ghost_from=None):
             np.asarray(ghost_from[mu], dtype=np.float64).reshape(4, 2, Vh, 3, 3, 2)
         for p in range(2):
             packed[p, mu, :Vh] = _pack_links(g[mu, p], recon)
-            fs = face_sites(X, mu, X[mu] - 1, p)
-            packed[p, mu, Vh:Vh + len(fs)] = _pack_links(src[mu, p][fs], recon)
+            if ghost_faces is not None and ghost_faces[mu] is not None:
+                fl = np.asarray(ghost_faces[mu], dtype=np.float64)[p]
+                packed[p, mu, Vh:Vh + len(fl)] = _pack_links(fl, recon)
+            else:
+                fs = face_sites(X, mu, X[mu] - 1, p)
+                packed[p, mu, Vh:Vh + len(fs)] = _pack_links(src[mu, p][fs], recon)
     if prec == HALF:
         scaled = packed / link_max if recon == 18 else packed
         q = np.rint(scaled.astype(np.float32) * _FIXED_MAX).astype(np.int16)
@@ -238,3 +251,51 @@ def clover_is_compressible(host, tol=1e-12):
 def ghost_parity_bytes(X, prec, d):
     face_cb = volume_cb(X) * 2 // X[d] // 2
     return face_cb * (12 * prec + (4 if prec == HALF else 0))
+
+
+# ---------------------------------------------------------------------------------------------- device-side packing
+def gauge_to_native_torch(u, X, prec, recon, ghost_faces=None):
+    """Same result as gauge_to_native (fp64 / fp32 / half) but computed with torch ops on the device holding `u`
+    ([4][V][3][3][2], parity-major sites).  Used to set up the 32^4 benchmark fields in seconds."""
+    import torch
+    Vh = volume_cb(X)
+    pad = gauge_pad(X)
+    stride = Vh + pad
+    N = gauge_N(prec, recon)
+    M = recon // N
+    g = u.reshape(4, 2, Vh, 3, 3, 2).to(torch.float64)
+    link_max = float(g.abs().max().item())
+
+    def pack(w):
+        flat = w.reshape(w.shape[:-3] + (18,))
+        if recon == 18:
+            return flat
+        if recon == 12:
+            return flat[..., :12]
+        o = torch.empty(w.shape[:-3] + (8,), dtype=torch.float64, device=w.device)
+        o[..., 0] = torch.atan2(w[..., 1, 0, 1], w[..., 1, 0, 0]) / np.pi
+        o[..., 1] = torch.atan2(-w[..., 2, 0, 1], -w[..., 2, 0, 0]) / np.pi
+        o[..., 2:4] = w[..., 1, 1, :]
+        o[..., 4:6] = w[..., 1, 2, :]
+        o[..., 6:8] = w[..., 0, 0, :]
+        return o
+
+    packed = torch.zeros((2, 4, stride, recon), dtype=torch.float64, device=u.device)
+    for mu in range(4):
+        for p in range(2):
+            packed[p, mu, :Vh] = pack(g[mu, p])
+            if ghost_faces is not None and ghost_faces[mu] is not None:
+                fl = ghost_faces[mu][p].to(torch.float64)
+            else:
+                fs = torch.from_numpy(face_sites(X, mu, X[mu] - 1, p)).to(u.device)
+                fl = g[mu, p][fs]
+            packed[p, mu, Vh:Vh + fl.shape[0]] = pack(fl)
+    if prec == HALF:
+        scaled = packed / link_max if recon == 18 else packed
+        arr = torch.round(scaled.to(torch.float32) * float(_FIXED_MAX)).to(torch.int16)
+    else:
+        arr = packed.to(torch.float64 if prec == DOUBLE else torch.float32)
+    arr = arr.reshape(2, 4, stride, M, N).permute(0, 1, 3, 2, 4).contiguous()
+    buf = arr.view(torch.uint8).reshape(-1)
+    meta = dict(stride=stride, parity_stride_bytes=buf.numel() // 2, link_max=link_max, pad=pad)
+    return buf, meta

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libquda_b200.so")
+# B200_LIB lets the tuning tools load an alternative build of the same library (e.g. another occupancy target)
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libquda_b200.so")
 ABI_VERSION = 1
 
 DOUBLE, SINGLE, HALF = 8, 4, 2
@@ -53,6 +54,25 @@ class PackArgs(C.Structure):
                 ("seq", C.c_uint), ("stream", C.c_void_p)]
 
 
+class Comm(C.Structure):
+    _fields_ = [("comm_dim", C.c_int * 4), ("send_dst", ((C.c_void_p * 2) * 4) * 2),
+                ("send_signal", ((C.c_void_p * 2) * 4) * 2), ("recv", ((C.c_void_p * 2) * 4) * 2),
+                ("recv_flag", ((C.c_void_p * 2) * 4) * 2), ("block_counter", C.c_void_p),
+                ("timeout_flag", C.c_void_p), ("seq", C.c_uint), ("allreduce_sum", C.c_void_p), ("user", C.c_void_p)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+
+
+class SolverParam(C.Structure):
+    _fields_ = [("tol", C.c_double), ("maxiter", C.c_int), ("delta", C.c_double), ("iter", C.c_int),
+                ("reliable_updates", C.c_int), ("true_res", C.c_double), ("secs", C.c_double), ("gflops", C.c_double)]
+
+
+DIRAC_WILSON, DIRAC_WILSONPC, DIRAC_CLOVER, DIRAC_CLOVERPC = 0, 1, 2, 3
+APPLY_M, APPLY_MDAG, APPLY_MDAGM, APPLY_DSLASH, APPLY_DSLASH_XPAY = 0, 1, 2, 3, 4
+
+
 def declare(lib, prefix="b200"):
     """Attach argtypes/restypes for the entry points shared by the CUDA library and the test-only host twin."""
     f = getattr(lib, prefix + "_dslash_apply")
@@ -89,6 +109,21 @@ def load():
         lib.b200_ipc_open_handle.restype = C.c_int
         lib.b200_ipc_close_handle.argtypes, lib.b200_ipc_close_handle.restype = [C.c_void_p], C.c_int
         lib.b200_comm_copy.argtypes, lib.b200_comm_copy.restype = [C.c_void_p, C.c_void_p, C.c_size_t], C.c_int
+        lib.b200_dirac_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(Gauge),
+                                          C.POINTER(Clover), C.POINTER(Clover), C.c_double, C.c_int, C.POINTER(Comm),
+                                          C.c_void_p]
+        lib.b200_dirac_create.restype = C.c_int
+        lib.b200_dirac_destroy.argtypes, lib.b200_dirac_destroy.restype = [C.c_void_p], C.c_int
+        lib.b200_dirac_apply.argtypes = [C.c_void_p, C.c_int, C.POINTER(Spinor), C.POINTER(Spinor), C.c_int,
+                                         C.POINTER(Spinor), C.c_double, C.c_int]
+        lib.b200_dirac_apply.restype = C.c_int
+        lib.b200_dirac_prepare.argtypes = [C.c_void_p, C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int)]
+        lib.b200_dirac_prepare.restype = C.c_int
+        lib.b200_dirac_reconstruct.argtypes = [C.c_void_p, C.POINTER(Spinor), C.POINTER(Spinor)]
+        lib.b200_dirac_reconstruct.restype = C.c_int
+        lib.b200_invert_cg.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(SolverParam)]
+        lib.b200_invert_cg.restype = C.c_int
         if lib.b200_abi_version() != ABI_VERSION:
             raise B200Error("libquda_b200.so ABI version mismatch")
         _lib = lib
@@ -105,4 +140,6 @@ def check(rc, lib=None, prefix="b200"):
 EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
                     "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
+                    "b200_dirac_create", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",
+                    "b200_dirac_reconstruct", "b200_invert_cg",
                     "b200_last_error", "b200_abi_version", "b200_launch_count", "b200_reset_launch_count"]

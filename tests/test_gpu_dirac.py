@@ -1,0 +1,109 @@
+"""GPU tier: operator composition (DiracWilson[PC], DiracClover[PC]) and CG against the oracle's
+wil_mat / wil_matpc / clover_mat / clover_matpc (the reference's --test Mat / MatPC / MatPCDagMatPC cases,
+tests/dslash_test_utils.h:363-786) and a host-verified true residual as invert_test does
+(tests/invert_test_gtest.hpp:107-128)."""
+import numpy as np
+import pytest
+
+import oracle
+from common import CudaMem, Problem, assert_close
+from quda_b200 import dirac as DR
+
+pytestmark = pytest.mark.gpu
+KAPPA = 0.12195
+
+
+@pytest.mark.parametrize("prec", [8, 4])
+def test_wilson_mat_and_matpc(prec):
+    X = (4, 6, 4, 8)
+    P = Problem(X, prec, 12, CudaMem)
+    full = P.spinor(seed=3, nparity=2)
+    op = DR.Dirac("wilson", P.U, KAPPA)
+    for dagger in (0, 1):
+        out = P.empty(2)
+        op.M(out, P.to_dev(full, 2), dagger=dagger)
+        assert_close(oracle.wil_mat(P.gauge, full, X, KAPPA, dagger), P.to_host(out), prec, 12, "wilson M")
+    s = P.spinor(seed=4)
+    for matpc in (DR.MATPC_EVEN_EVEN, DR.MATPC_ODD_ODD):
+        pc = DR.Dirac("wilsonpc", P.U, KAPPA, matpc_type=matpc)
+        for dagger in (0, 1):
+            out = P.empty()
+            pc.M(out, P.to_dev(s), dagger=dagger)
+            assert_close(oracle.wil_matpc(P.gauge, s, X, KAPPA, matpc, dagger), P.to_host(out), prec, 12, "wilson Mpc")
+        out = P.empty()
+        pc.MdagM(out, P.to_dev(s))
+        ref = oracle.wil_matpc(P.gauge, oracle.wil_matpc(P.gauge, s, X, KAPPA, matpc, 0), X, KAPPA, matpc, 1)
+        assert_close(ref, P.to_host(out), prec, 12, "wilson MpcdagMpc")
+
+
+@pytest.mark.parametrize("prec", [8, 4])
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_clover_mat_and_matpc(prec, dynamic):
+    X = (4, 4, 6, 4)
+    P = Problem(X, prec, 12, CudaMem, clover=True, compressed=dynamic, dynamic=dynamic)
+    full = P.spinor(seed=3, nparity=2)
+    op = DR.Dirac("clover", P.U, KAPPA, clover=P.A, clover_inv=P.Ainv)
+    for dagger in (0, 1):
+        out = P.empty(2)
+        op.M(out, P.to_dev(full, 2), dagger=dagger)
+        assert_close(oracle.clover_mat(P.gauge, P.clover, full, X, KAPPA, dagger), P.to_host(out), prec, 12, "clover M")
+    s = P.spinor(seed=4)
+    for matpc in range(4):
+        pc = DR.Dirac("cloverpc", P.U, KAPPA, clover=P.A, clover_inv=P.Ainv, matpc_type=matpc)
+        for dagger in (0, 1):
+            out = P.empty()
+            pc.M(out, P.to_dev(s), dagger=dagger)
+            ref = oracle.clover_matpc(P.gauge, P.clover, P.clover_inv, s, X, KAPPA, matpc, dagger)
+            assert_close(ref, P.to_host(out), prec, 12, f"clover Mpc type={matpc} dag={dagger}")
+
+
+def _solve_full_system(P, kind_pc, X, tol, mixed, matpc=DR.MATPC_EVEN_EVEN):
+    """invertQuda-style: prepare -> CG on MpcdagMpc -> reconstruct, then verify M x = b on the host."""
+    import torch
+    kw = dict(clover=P.A, clover_inv=P.Ainv) if "clover" in kind_pc else {}
+    pc = DR.Dirac(kind_pc, P.U, KAPPA, matpc_type=matpc, **kw)
+    b = P.spinor(seed=77, nparity=2)
+    bdev, xdev = P.to_dev(b, 2), P.empty(2)
+    src_p, sol_p = pc.prepare(xdev, bdev)
+    Vh = P.Vh
+    pb = xdev.parity_bytes
+    from quda_b200 import dslash as D
+    src = D.ColorSpinorField(xdev.buf[src_p * pb:(src_p + 1) * pb], X, P.prec)
+    sol = D.ColorSpinorField(xdev.buf[sol_p * pb:(sol_p + 1) * pb], X, P.prec)
+    # normal equations: MdagM sol = Mdag src
+    rhs = P.empty()
+    pc.Mdag(rhs, src)
+    sol.buf.zero_()
+    sloppy = None
+    if mixed:
+        Ps = Problem(X, 4, 12, CudaMem, clover=P.clover is not None, compressed=True, dynamic=True)
+        kws = dict(clover=Ps.A, clover_inv=Ps.Ainv) if "clover" in kind_pc else {}
+        sloppy = DR.Dirac(kind_pc, Ps.U, KAPPA, matpc_type=matpc, **kws)
+        sloppy._keep = Ps
+    res = DR.invert_cg(pc, sloppy, sol, rhs, tol=tol, maxiter=2000)
+    pc.reconstruct(xdev, bdev)
+    x = P.to_host(xdev)
+    if "clover" in kind_pc:
+        Mx = oracle.clover_mat(P.gauge, P.clover, x.astype(b.dtype), X, KAPPA, 0)
+    else:
+        Mx = oracle.wil_mat(P.gauge, x.astype(b.dtype), X, KAPPA, 0)
+    true_res = np.linalg.norm(Mx.astype(np.float64).ravel() - b.astype(np.float64).ravel()) / np.linalg.norm(b.ravel())
+    return res, true_res
+
+
+def test_cg_wilson_double():
+    X = (8, 8, 8, 8)
+    P = Problem(X, 8, 18, CudaMem)
+    res, true_res = _solve_full_system(P, "wilsonpc", X, 1e-10, mixed=False)
+    assert res.iter < 2000 and res.true_res < 5e-10
+    assert true_res < 1e-8, true_res  # host-verified residual of the FULL system (normal-equation solve squares the condition)
+
+
+def test_cg_clover_mixed_precision():
+    """config 5 in miniature: clover, CG on MdagM, double precise / single sloppy with reliable updates"""
+    X = (8, 8, 8, 8)
+    P = Problem(X, 8, 18, CudaMem, clover=True, compressed=True, dynamic=True)
+    res, true_res = _solve_full_system(P, "cloverpc", X, 1e-10, mixed=True)
+    assert res.reliable_updates >= 1
+    assert res.true_res < 5e-10, res.true_res
+    assert true_res < 1e-8, true_res

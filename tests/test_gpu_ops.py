@@ -1,0 +1,57 @@
+"""GPU tier: the operator-level cases of tests/ops.py through libquda_b200.so -- xpay / dagger / full fields,
+clover variants, and the self-partitioned halo path (pack kernel -> ghost buffers + arrival flags -> interior +
+fused exterior kernel) for the partition masks dslash_ctest uses (tests/dslash_ctest.cpp:40-42,174-186)."""
+import numpy as np
+import pytest
+
+import oracle
+import ops
+from common import CudaMem, Problem, assert_close
+from quda_b200 import comm, dslash as D
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("prec", [8, 4, 2])
+@pytest.mark.parametrize("recon", [18, 12, 8])
+def test_xpay_dagger_fullfield(prec, recon):
+    ops.check_xpay_fullfield(CudaMem, None, prec, recon)
+
+
+@pytest.mark.parametrize("prec", [8, 4, 2])
+@pytest.mark.parametrize("compressed,dynamic", [(True, True), (False, False)])
+def test_clover(prec, compressed, dynamic):
+    ops.check_clover(CudaMem, None, prec, 12, compressed, dynamic)
+
+
+def test_clover_half_recon8_config3():
+    """BASELINE config 3: clover-preconditioned Dslash, half precision, recon-8 (tolerance 1e-3 x 10)"""
+    ops.check_clover(CudaMem, None, 2, 8, True, True, X=(8, 8, 8, 8))
+
+
+@pytest.mark.parametrize("comm_dim", [(1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1), (1, 1, 0, 0), (0, 0, 1, 1), (1, 1, 1, 1)])
+@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (2, 8)])
+def test_partitioned_wilson(prec, recon, comm_dim):
+    ops.check_partitioned(CudaMem, None, prec, recon, comm_dim, X=(4, 6, 4, 8), xpay=True, dagger=1)
+
+
+@pytest.mark.parametrize("op", ["clover_pc", "clover"])
+def test_partitioned_clover(op):
+    ops.check_partitioned(CudaMem, None, 4, 12, (1, 1, 1, 1), op=op, xpay=True, clover_kw=dict(compressed=True, dynamic=True))
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (2, 12)])
+def test_self_exchange_with_arrival_flags(prec, recon):
+    """The NVLink remote-write protocol on one GPU: the pack kernel raises sequence-numbered flags, the exterior
+    kernel spins on them; ten back-to-back applications exercise the double-buffered ghost zones."""
+    X = (8, 4, 4, 8)
+    P = Problem(X, prec, recon, CudaMem)
+    grid = comm.ProcessGrid((1, 1, 1, 1), 0)
+    ex = comm.HaloExchange(grid, X, prec, mode="self")
+    s = P.spinor(seed=1)
+    ref = oracle.wil_dslash(P.gauge, s, X, 0, 0)
+    din, out = P.to_dev(s), P.empty()
+    for _ in range(10):
+        comm.apply_wilson_distributed(ex, out, din, P.U, 0.0, None, 0, 0)
+    assert_close(ref, P.to_host(out), prec, recon, "self exchange")
+    assert not ex.timed_out()

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Lean single-GPU call: parity tests, variant/tile tuning in one process per library build, bench, ncu evidence.
+mkdir -p gpurun_out
+T0=$(date +%s)
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.txt
+echo "[t=$(( $(date +%s)-T0 ))s]"
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.txt
+for v in "" _v2 _v4; do
+  echo "== tune lib$v"; B200_LIB=$PWD/quda_b200/libquda_b200$v.so timeout 400 python tools/tune.py "lib$v" 2>&1 | grep tune
+done
+echo "[t=$(( $(date +%s)-T0 ))s]"
+echo "== bench"; timeout 600 python bench.py 2> gpurun_out/bench_err.txt | tee gpurun_out/bench_single_r12.json
+echo "[t=$(( $(date +%s)-T0 ))s]"
+echo "== ncu launch list"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dslash --csv \
+   --log-file gpurun_out/launches_single_r12.csv python tools/prof_target.py single 12 8 > gpurun_out/ncu_list.log 2>&1
+echo "== ncu full (single r12, double r18, half r8)"
+for cfg in "single 12" "double 18" "half 8"; do
+  set -- $cfg
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:dslash_interior -s 3 -c 1 \
+     -o gpurun_out/prof_$1_r$2 -f python tools/prof_target.py $1 $2 5 > gpurun_out/ncu_full_$1_r$2.log 2>&1
+  tail -2 gpurun_out/ncu_full_$1_r$2.log
+done
+echo "[t=$(( $(date +%s)-T0 ))s]"
+echo "== done"

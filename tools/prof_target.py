@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Lean ncu target: one 32^4 problem, a handful of Dslash launches (no solver, no linalg set-up kernels)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from quda_b200 import dslash as D  # noqa: E402
+
+pname, recon = (sys.argv[1], int(sys.argv[2])) if len(sys.argv) > 2 else ("single", 12)
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+P = bench.make_device_problem([32, 32, 32, 32], bench.PREC_BYTES[pname], recon)
+st = torch.cuda.current_stream().cuda_stream
+for _ in range(n):
+    D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, stream=st)
+torch.cuda.synchronize()
+print("prof_target done", pname, recon)
