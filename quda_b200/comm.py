@@ -259,6 +259,46 @@ class HaloExchange:
         h.timeout_flag = (self.base + self.timeout_off) if self.mode in ("p2p", "self") else None
         return h
 
+    def comm_struct(self):
+        """b200_comm block for the C++ operator / solver layer (quda_b200/csrc/host/dirac.h::CommContext): peer
+        destinations + signals for both ghost buffers, local receive slots + flags, and an allreduce callback for the
+        solver's scalars.  The returned object must be kept alive as long as operators created with it exist."""
+        assert self.mode in ("p2p", "self")
+        c = L.Comm()
+        g = self.grid
+        for d in range(4):
+            c.comm_dim[d] = self.comm_dim[d]
+            if not self.comm_dim[d]:
+                continue
+            back = self.peer[g.neighbor(d, -1)] if self.mode == "p2p" else self.base
+            fwd = self.peer[g.neighbor(d, +1)] if self.mode == "p2p" else self.base
+            for b in range(2):
+                c.send_dst[b][d][0] = back + self.off[(b, d, 1)]
+                c.send_dst[b][d][1] = fwd + self.off[(b, d, 0)]
+                c.send_signal[b][d][0] = back + self.flag_off + ((b * 4 + d) * 2 + 1) * 4
+                c.send_signal[b][d][1] = fwd + self.flag_off + ((b * 4 + d) * 2 + 0) * 4
+                for dr in range(2):
+                    c.recv[b][d][dr] = self.base + self.off[(b, d, dr)]
+                    c.recv_flag[b][d][dr] = self.base + self.flag_off + ((b * 4 + d) * 2 + dr) * 4
+        c.block_counter = self.base + self.counter_off
+        c.timeout_flag = self.base + self.timeout_off
+        c.seq = self.seq
+        if self.mode == "p2p" and g.size > 1:
+            import torch
+            dist = self.dist
+
+            def _allreduce(ptr, n, _user):
+                t = torch.tensor([ptr[i] for i in range(n)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t)
+                v = t.cpu().tolist()
+                for i in range(n):
+                    ptr[i] = v[i]
+
+            self._allreduce_cb = L.ALLREDUCE_FN(_allreduce)  # keep the callback object alive
+            c.allreduce_sum = C.cast(self._allreduce_cb, C.c_void_p)
+        self._comm_struct = c
+        return c
+
     def timed_out(self):
         """True if an exterior kernel gave up waiting for a neighbour (device flag set by wait_for_halo)."""
         if self.mode not in ("p2p", "self"):

@@ -37,6 +37,51 @@ namespace b200
     int *timeout_flag;        // set to 1 if a wait gives up
   };
 
+  // CTA -> 4-d tile of checkerboard sites, thread -> site inside the tile (x fastest so that a warp's 16-byte plane
+  // loads cover contiguous 256..512-byte runs).  grid = (nt0*nt1, nt2, nt3 * n_parity); the thread index decomposes by
+  // shifts (tile extents are powers of two) and the only division is a multiply-high: no runtime integer division.
+  struct TileMap {
+    int sh[4];          // log2 of the tile extents: [0] in checkerboard sites (x/2), [1..3] in sites
+    int nt[4];          // tiles per dimension
+    unsigned nt0_magic; // floor(2^32 / nt[0]) + 1 (nt[0] >= 2); blockIdx.x / nt[0] == umulhi(blockIdx.x, magic)
+  };
+
+  B2_HD unsigned mulhi_u32(unsigned a, unsigned b)
+  {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (unsigned)(((unsigned long long)a * b) >> 32);
+#endif
+  }
+
+  B2_HD bool tile_site(int *x, int &x_cb, int &parity, const Geom &g, const TileMap &tm, int n_parity, int arg_parity,
+                       unsigned bx, unsigned by, unsigned bz, unsigned tid)
+  {
+    const int b1 = tm.nt[0] == 1 ? (int)bx : (int)mulhi_u32(bx, tm.nt0_magic);
+    const int b0 = (int)bx - b1 * tm.nt[0];
+    const int b2 = (int)by;
+    int b3 = (int)bz;
+    parity = arg_parity;
+    if (n_parity == 2) {
+      parity = b3 >= tm.nt[3] ? 1 : 0;
+      b3 -= parity * tm.nt[3];
+    }
+    const int l = (int)tid;
+    const int l0 = l & ((1 << tm.sh[0]) - 1);
+    const int l1 = (l >> tm.sh[0]) & ((1 << tm.sh[1]) - 1);
+    const int l2 = (l >> (tm.sh[0] + tm.sh[1])) & ((1 << tm.sh[2]) - 1);
+    const int l3 = l >> (tm.sh[0] + tm.sh[1] + tm.sh[2]);
+    const int xh = (b0 << tm.sh[0]) + l0;
+    x[1] = (b1 << tm.sh[1]) + l1;
+    x[2] = (b2 << tm.sh[2]) + l2;
+    x[3] = (b3 << tm.sh[3]) + l3;
+    if (xh >= g.Xh0 || x[1] >= g.X[1] || x[2] >= g.X[2] || x[3] >= g.X[3]) return false;
+    x[0] = 2 * xh + ((x[1] + x[2] + x[3] + parity) & 1);
+    x_cb = ((x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.Xh0 + xh;
+    return true;
+  }
+
   // which spin pair the t-direction projector keeps: P(3,+1) -> upper (spins 0,1), P(3,-1) -> lower
   template <class P, bool upper, Cache c = Cache::REUSE>
   B2_HD void load_spin_pair(typename P::real *h, const SpinorView<P> &f, int x_cb)

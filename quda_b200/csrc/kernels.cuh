@@ -11,44 +11,6 @@
 namespace b200
 {
 
-  // CTA -> 4-d tile of checkerboard sites, thread -> site inside the tile (x fastest so that a warp's 16-byte
-  // plane loads cover contiguous 128..512-byte runs).  A 4-d tile (instead of the reference's linear
-  // checkerboard index) keeps most +-y/z/t neighbours of a CTA's sites inside the CTA's own working set,
-  // so they are served by the SM's L1 instead of L2.
-  struct TileMap {
-    int sh[4];     // log2 of the tile extents: t[0] in checkerboard sites (x/2), t[1..3] in sites (powers of two)
-    int nt[4];     // tiles per dimension
-    unsigned nt0_magic; // floor(2^32 / nt[0]) + 1 : blockIdx.x / nt[0] == __umulhi(blockIdx.x, magic) for our ranges
-  };
-
-  // grid = (nt0*nt1, nt2, nt3 * n_parity); thread index decomposes by shifts; no runtime integer division
-  __device__ __forceinline__ bool tile_site(int *x, int &x_cb, int &parity, const Geom &g, const TileMap &tm, int n_parity,
-                                            int arg_parity)
-  {
-    const int b1 = __umulhi(blockIdx.x, tm.nt0_magic);
-    const int b0 = blockIdx.x - b1 * tm.nt[0];
-    const int b2 = blockIdx.y;
-    int b3 = blockIdx.z;
-    parity = arg_parity;
-    if (n_parity == 2) {
-      parity = b3 >= tm.nt[3] ? 1 : 0;
-      b3 -= parity * tm.nt[3];
-    }
-    const int l = threadIdx.x;
-    const int l0 = l & ((1 << tm.sh[0]) - 1);
-    const int l1 = (l >> tm.sh[0]) & ((1 << tm.sh[1]) - 1);
-    const int l2 = (l >> (tm.sh[0] + tm.sh[1])) & ((1 << tm.sh[2]) - 1);
-    const int l3 = l >> (tm.sh[0] + tm.sh[1] + tm.sh[2]);
-    const int xh = (b0 << tm.sh[0]) + l0;
-    x[1] = (b1 << tm.sh[1]) + l1;
-    x[2] = (b2 << tm.sh[2]) + l2;
-    x[3] = (b3 << tm.sh[3]) + l3;
-    if (xh >= g.Xh0 || x[1] >= g.X[1] || x[2] >= g.X[2] || x[3] >= g.X[3]) return false;
-    x[0] = 2 * xh + ((x[1] + x[2] + x[3] + parity) & 1);
-    x_cb = ((x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.Xh0 + xh;
-    return true;
-  }
-
   // Occupancy targets (CTAs of <= kMaxTile threads per SM) per storage precision; set from the B200 sweeps in
   // profiles/ (fp64 needs ~128 registers for the 24 double accumulators + a link + a half spinor).
 #ifndef B2_MINBLOCKS_F64
@@ -71,7 +33,8 @@ namespace b200
     dslash_interior_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TileMap tm)
   {
     int x[4], x_cb, parity;
-    if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity)) return;
+    if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x))
+      return;
     dslash_site_interior<P, recon, dagger, xpay, op, part>(arg, x, x_cb, parity);
   }
 
@@ -202,20 +165,9 @@ namespace b200
     cudaStream_t s = (cudaStream_t)rq.stream;
     if (rq.kernel != B200_KERNEL_EXTERIOR) {
       TileMap tm;
-      int threads = 1;
-      for (int d = 0; d < 4; d++) {
-        int sh = 0;
-        while ((2 << sh) <= rq.tile[d]) sh++; // round the requested extent down to a power of two
-        tm.sh[d] = sh;
-        const int ext = d == 0 ? arg.geom.Xh0 : arg.geom.X[d];
-        tm.nt[d] = (ext + (1 << sh) - 1) >> sh;
-        threads <<= sh;
-      }
-      if (threads > kMaxTile) return set_error(B200_ERR_INVALID, "tile volume %d exceeds %d threads", threads, kMaxTile);
-      tm.nt0_magic = (unsigned)(0x100000000ull / (unsigned)tm.nt[0]) + 1u;
-      if ((long long)tm.nt[0] * tm.nt[1] >= (1ll << 31) / tm.nt[0] || tm.nt[2] > 65535 || tm.nt[3] * arg.n_parity > 65535)
-        return set_error(B200_ERR_INVALID, "lattice too large for the tile grid");
-      dim3 grid(tm.nt[0] * tm.nt[1], tm.nt[2], tm.nt[3] * arg.n_parity);
+      int threads, gx, gy, gz;
+      if (int rc = make_tile_map(tm, threads, gx, gy, gz, rq.tile, arg.geom, arg.n_parity, kMaxTile)) return rc;
+      dim3 grid(gx, gy, gz);
       if (arg.threads_ext[4] > 0)
         dslash_interior_kernel<P, recon, dagger, xpay, op, true><<<grid, threads, 0, s>>>(arg, tm);
       else

@@ -205,6 +205,31 @@ namespace b200
     return 0;
   }
 
+  // launch geometry of the interior kernel for a requested tile (extents rounded down to powers of two)
+  inline int make_tile_map(TileMap &tm, int &threads, int &gx, int &gy, int &gz, const int *tile, const Geom &g,
+                           int n_parity, int max_threads)
+  {
+    threads = 1;
+    for (int d = 0; d < 4; d++) {
+      int sh = 0;
+      while ((2 << sh) <= tile[d]) sh++;
+      const int ext = d == 0 ? g.Xh0 : g.X[d];
+      while (sh > 0 && (1 << sh) > 2 * ext) sh--; // no point in tiles more than twice the extent
+      tm.sh[d] = sh;
+      tm.nt[d] = (ext + (1 << sh) - 1) >> sh;
+      threads <<= sh;
+    }
+    if (threads > max_threads) return set_error(B200_ERR_INVALID, "tile volume %d exceeds %d threads", threads, max_threads);
+    tm.nt0_magic = tm.nt[0] >= 2 ? (unsigned)(0x100000000ull / (unsigned)tm.nt[0]) + 1u : 0u;
+    // umulhi(b, magic) == b / nt0 needs b * nt0 < 2^32
+    if ((long long)tm.nt[0] * tm.nt[0] * tm.nt[1] >= (1ll << 32) || tm.nt[2] > 65535 || tm.nt[3] * n_parity > 65535)
+      return set_error(B200_ERR_INVALID, "lattice too large for the tile grid");
+    gx = tm.nt[0] * tm.nt[1];
+    gy = tm.nt[2];
+    gz = tm.nt[3] * n_parity;
+    return 0;
+  }
+
   template <class P> int launch_precision(const LaunchRequest &rq);
   template <class P> int launch_clover_precision(const CloverRequest &rq);
   template <class P> int launch_pack_precision(const PackRequest &rq);

@@ -27,17 +27,28 @@ namespace b200
   template <class P, int recon, bool dagger, bool xpay, OpType op> int run_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
   {
     const Geom &g = arg.geom;
-    for (int pp = 0; pp < arg.n_parity; pp++) {
-      const int parity = arg.n_parity == 2 ? pp : arg.parity;
-      if (rq.kernel != B200_KERNEL_EXTERIOR) {
-#pragma omp parallel for
-        for (int x_cb = 0; x_cb < g.volume_cb; x_cb++) {
-          int x[4];
-          coords_from_cb(x, g, x_cb, parity);
-          dslash_site_interior<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
-        }
-      }
-      if (rq.kernel != B200_KERNEL_INTERIOR) {
+    if (rq.kernel != B200_KERNEL_EXTERIOR) {
+      // walk the SAME launch grid as kernels.cuh::launch_config (tile map, block and thread decomposition, parity in z)
+      TileMap tm;
+      int threads, gx, gy, gz;
+      if (int rc = make_tile_map(tm, threads, gx, gy, gz, rq.tile, g, arg.n_parity, 256)) return rc;
+      long visited = 0;
+#pragma omp parallel for collapse(2) reduction(+ : visited)
+      for (int bz = 0; bz < gz; bz++)
+        for (int by = 0; by < gy; by++)
+          for (int bx = 0; bx < gx; bx++)
+            for (int tid = 0; tid < threads; tid++) {
+              int x[4], x_cb, par;
+              if (!tile_site(x, x_cb, par, g, tm, arg.n_parity, arg.parity, bx, by, bz, tid)) continue;
+              dslash_site_interior<P, recon, dagger, xpay, op>(arg, x, x_cb, par);
+              visited++;
+            }
+      if (visited != (long)g.volume_cb * arg.n_parity)
+        return set_error(B200_ERR_INVALID, "tile map visited %ld of %ld sites", visited, (long)g.volume_cb * arg.n_parity);
+    }
+    if (rq.kernel != B200_KERNEL_INTERIOR) {
+      for (int pp = 0; pp < arg.n_parity; pp++) {
+        const int parity = arg.n_parity == 2 ? pp : arg.parity;
 #pragma omp parallel for
         for (int tid = 0; tid < arg.threads_ext[4]; tid++) {
           int x[4], x_cb;

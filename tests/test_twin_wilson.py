@@ -24,3 +24,21 @@ def test_wilson_dslash(prec, recon, X):
             D.ApplyWilson(out, P.to_dev(s), P.U, 0.0, None, parity, dagger, backend=be)
             ref = oracle.wil_dslash(P.gauge, s, X, parity, dagger)
             assert_close(ref, P.to_host(out), prec, recon, f"dslash parity={parity} dagger={dagger}")
+
+
+@pytest.mark.parametrize("tile", [(16, 2, 2, 1), (2, 2, 2, 2), (1, 4, 1, 2), (4, 1, 1, 1), (2, 8, 4, 4), (3, 4, 4, 4)])
+def test_launch_tilings_cover_the_lattice(tile):
+    """The host twin walks the same (grid, block) decomposition the CUDA launcher builds (launch.h::make_tile_map,
+    dslash_site.h::tile_site): every tiling, including ragged ones and nt0 == 1, must visit each site exactly once."""
+    be = twin_backend()
+    X = (8, 6, 4, 6)
+    P = Problem(X, 4, 12, HostMem)
+    s = P.spinor(seed=2)
+    out = P.empty()
+    D.ApplyWilson(out, P.to_dev(s), P.U, 0.0, None, 1, 0, tile=tile, backend=be)
+    assert_close(oracle.wil_dslash(P.gauge, s, X, 1, 0), P.to_host(out), 4, 12, f"tile {tile}")
+    full = P.spinor(seed=3, nparity=2)
+    out2 = P.empty(2)
+    D.ApplyWilson(out2, P.to_dev(full, 2), P.U, 0.0, None, D.QUDA_INVALID_PARITY, 0, tile=tile, backend=be)
+    ref = np.concatenate([oracle.wil_dslash(P.gauge, full[P.Vh:], X, 0, 0), oracle.wil_dslash(P.gauge, full[:P.Vh], X, 1, 0)])
+    assert_close(ref, P.to_host(out2), 4, 12, f"full-field tile {tile}")

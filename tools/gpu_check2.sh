@@ -14,12 +14,19 @@ echo "[t=$(( $(date +%s)-T0 ))s]"
 echo "== ncu launch list"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dslash --csv \
    --log-file gpurun_out/launches_single_r12.csv python tools/prof_target.py single 12 8 > gpurun_out/ncu_list.log 2>&1
-echo "== ncu full (single r12, double r18, half r8)"
+echo "== ncu full (single r12 with source, double r18, half r8)"
 for cfg in "single 12" "double 18" "half 8"; do
   set -- $cfg
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:dslash_interior -s 3 -c 1 \
+  SRC=""; [ "$1" = "single" ] && SRC="--import-source on"
+  timeout 400 ncu --set full --clock-control none $SRC -k regex:dslash_interior -s 3 -c 1 \
      -o gpurun_out/prof_$1_r$2 -f python tools/prof_target.py $1 $2 5 > gpurun_out/ncu_full_$1_r$2.log 2>&1
-  tail -2 gpurun_out/ncu_full_$1_r$2.log
+  tail -1 gpurun_out/ncu_full_$1_r$2.log
+  ncu -i gpurun_out/prof_$1_r$2.ncu-rep --page raw --csv > gpurun_out/prof_$1_r$2.raw.csv 2>/dev/null
+  [ "$1" = "single" ] && ncu -i gpurun_out/prof_$1_r$2.ncu-rep --page source --csv > gpurun_out/prof_$1_r$2.source.csv 2>/dev/null
+  ls -la gpurun_out/prof_$1_r$2.ncu-rep
+  # the merge-back limit is 64 MiB in total: keep the report only if it is small
+  [ $(stat -c %s gpurun_out/prof_$1_r$2.ncu-rep) -gt 15000000 ] && rm -f gpurun_out/prof_$1_r$2.ncu-rep
 done
+du -sh gpurun_out
 echo "[t=$(( $(date +%s)-T0 ))s]"
 echo "== done"
