@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="(N>1) also time pack / interior / exterior separately")
     return ap.parse_args()
 
 
@@ -260,6 +261,29 @@ def run_b200(a):
                         "traffic": ncu_traffic(a), "peak_source": peak_src,
                         "kernel": "dslash_interior_kernel", "algorithmic_bytes_per_launch": bmin * Vh},
            "clocks": cs.summary()}
+    if world > 1 and a.breakdown:
+        from quda_b200 import lib as LL
+        def timed(fn, n=50):
+            for _ in range(5):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / n * 1e3], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        halo_now = comm._RawHalo(ex.halo())
+        out["breakdown_us"] = {
+            "pack_and_send": timed(lambda: ex.start(src, 1, 0, stream=stream)),
+            "interior": timed(lambda: D._apply(LL.OP_WILSON, dst, src, P["U"], 0.0, None, 0, 0, None, halo=comm._RawHalo(ex.halo()),
+                                               kernel=LL.KERNEL_INTERIOR, stream=stream, tile=a.tile)),
+            "exterior": timed(lambda: D._apply(LL.OP_WILSON, dst, src, P["U"], 0.0, None, 0, 0, None, halo=comm._RawHalo(ex.halo()),
+                                               kernel=LL.KERNEL_EXTERIOR, stream=stream, tile=a.tile)),
+        }
     if world > 1:
         out["halo"] = {"mode": halo_mode, "grid": grid.dims, "bytes_per_step_per_gpu": int(sum(
             2 * ex.face_bytes[d] for d in range(4) if ex.comm_dim[d])), "timed_out": bool(ex.timed_out()) if halo_mode.startswith("p2p") else False}

@@ -53,11 +53,20 @@ namespace b200
     static_assert(sizeof(V) == 16 || sizeof(V) == 8 || sizeof(V) == 4, "vector width");
     if constexpr (sizeof(V) == 16) {
       uint4 r;
-      if constexpr (c == Cache::STREAM)
+      if constexpr (c == Cache::STREAM) {
+#ifdef B2_L2_HINTS
+        // read-once data: additionally ask L2 to evict these lines first so they do not displace neighbour spinors
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                     : "l"(p), "l"(pol));
+#else
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                      : "l"(p));
-      else
+#endif
+      } else
         asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
       return *reinterpret_cast<V *>(&r);
     } else if constexpr (sizeof(V) == 8) {

@@ -1,6 +1,8 @@
 // Implementation of the host-side operator / blas / solver mirror (see dirac.h for the reference citations).
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 
@@ -569,6 +571,8 @@ namespace b200
       double rNorm = std::sqrt(r2), r0Norm = rNorm, maxrx = rNorm, maxrr = rNorm;
       int k = 0;
       param.reliable_updates = 0;
+      const bool verbose = getenv("B200_CG_VERBOSE") != nullptr;
+      if (verbose) fprintf(stderr, "[cg] b2=%g r2=%g stop=%g mixed=%d\n", b2, r2, stop, (int)mixed);
       while (r2 > stop && k < param.maxiter) {
         matSloppy.MdagM(Ap, p);
         const double pAp = reDotProduct(p, Ap, comm);
@@ -600,6 +604,8 @@ namespace b200
           param.reliable_updates++;
         }
         k++;
+        if (verbose && (k < 10 || k % 20 == 0 || update))
+          fprintf(stderr, "[cg] k=%d r2=%g pAp=%g alpha=%g update=%d\n", k, r2, pAp, alpha, (int)update);
       }
       // x = y + xS
       copy(tmp, xS);

@@ -11,18 +11,24 @@
 namespace b200
 {
 
-  // Occupancy targets (CTAs of <= kMaxTile threads per SM) per storage precision; set from the B200 sweeps in
-  // profiles/ (fp64 needs ~128 registers for the 24 double accumulators + a link + a half spinor).
+  // Occupancy targets per storage precision: CTAs hold at most B2_MAXTILE threads (the fastest tiles on B200 are
+  // 64..128 threads: full x rows x a few y/z rows) and ptxas may use 65536 / (B2_MAXTILE * minBlocks) registers per
+  // thread.  The stencil is latency bound (ncu: long-scoreboard stalls dominate), so registers spent on keeping the
+  // loads of several hops in flight pay better than extra resident warps: fp64 255 regs, fp32 128, half 128
+  // (sweeps in profiles/r01_*tune*).
+#ifndef B2_MAXTILE
+#define B2_MAXTILE 128
+#endif
 #ifndef B2_MINBLOCKS_F64
 #define B2_MINBLOCKS_F64 2
 #endif
 #ifndef B2_MINBLOCKS_F32
-#define B2_MINBLOCKS_F32 3
+#define B2_MINBLOCKS_F32 4
 #endif
 #ifndef B2_MINBLOCKS_H16
-#define B2_MINBLOCKS_H16 3
+#define B2_MINBLOCKS_H16 4
 #endif
-  constexpr int kMaxTile = 256;
+  constexpr int kMaxTile = B2_MAXTILE;
   template <class P> struct MinBlocks { static constexpr int value = B2_MINBLOCKS_F32; };
   template <> struct MinBlocks<PrecF64> { static constexpr int value = B2_MINBLOCKS_F64; };
   template <> struct MinBlocks<PrecH16> { static constexpr int value = B2_MINBLOCKS_H16; };

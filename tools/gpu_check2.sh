@@ -2,10 +2,11 @@
 # Lean single-GPU call: parity tests, variant/tile tuning in one process per library build, bench, ncu evidence.
 mkdir -p gpurun_out
 T0=$(date +%s)
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.txt
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.txt
 echo "[t=$(( $(date +%s)-T0 ))s]"
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.txt
-for v in "" _v2 _v4; do
+B200_CG_VERBOSE=1 timeout 300 python -m pytest tests/test_gpu_dirac.py -m gpu -q -k mixed 2>&1 | grep "\[cg\]" | head -40
+for v in "" _r255 _r170 _r102 _r85 _l2; do
   echo "== tune lib$v"; B200_LIB=$PWD/quda_b200/libquda_b200$v.so timeout 400 python tools/tune.py "lib$v" 2>&1 | grep tune
 done
 echo "[t=$(( $(date +%s)-T0 ))s]"

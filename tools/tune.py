@@ -21,7 +21,7 @@ if len(sys.argv) > 2:
     cfgs = [(p, int(r)) for p, r in cfgs]
 X = [32, 32, 32, 32]
 TILES = [(16, 1, 1, 1), (16, 2, 1, 1), (16, 2, 2, 1), (16, 2, 1, 2), (16, 4, 1, 1), (16, 4, 2, 1), (16, 4, 1, 2),
-         (16, 8, 1, 1), (16, 8, 2, 1), (16, 4, 4, 1), (16, 16, 1, 1), (8, 8, 1, 1), (8, 4, 2, 1), (16, 2, 2, 2)]
+         (16, 8, 1, 1), (16, 2, 2, 2), (16, 1, 2, 1), (16, 1, 1, 2), (8, 8, 1, 1), (8, 4, 2, 1)]
 stream = torch.cuda.current_stream().cuda_stream
 res = {}
 t_all = time.time()
