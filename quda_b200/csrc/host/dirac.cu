@@ -241,6 +241,7 @@ namespace b200
       static double run(double a, const ColorSpinorField &x, double b, ColorSpinorField &y, bool write, CommContext *comm)
       {
         check_pair(x, y);
+        if (x.precision != y.precision) throw Error("blas: mixed-precision operands (use blas::copy to convert)");
         const size_t n = x.Length();
         double *red = reduce_buf();
         if (R != R_NONE) cuda_ok(cudaMemsetAsync(red, 0, sizeof(double)), "memset");
@@ -262,7 +263,41 @@ namespace b200
         return h;
       }
 
-      void copy(ColorSpinorField &dst, const ColorSpinorField &src) { run<R_NONE>(1.0, src, 0.0, dst, true, nullptr); }
+      // Precision conversion has to go through the site/component map: the native order of fp64 fields is planes of 2
+      // reals, that of fp32 fields planes of 4 (color_spinor_field_order.h FloatNOrder), so an element-wise cast
+      // would permute components.  One thread per site moves its 24 reals.
+      template <typename Ts, int Ns, typename Td, int Nd>
+      __global__ void convert_kernel(const Ts *__restrict__ src, Td *__restrict__ dst, int volume_cb, size_t src_parity_elems,
+                                     size_t dst_parity_elems)
+      {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= volume_cb) return;
+        const Ts *s = src + blockIdx.y * src_parity_elems;
+        Td *d = dst + blockIdx.y * dst_parity_elems;
+        double v[24];
+#pragma unroll
+        for (int r = 0; r < 24; r++) v[r] = s[((size_t)(r / Ns) * volume_cb + x) * Ns + r % Ns];
+#pragma unroll
+        for (int r = 0; r < 24; r++) d[((size_t)(r / Nd) * volume_cb + x) * Nd + r % Nd] = (Td)v[r];
+      }
+
+      void copy(ColorSpinorField &dst, const ColorSpinorField &src)
+      {
+        check_pair(src, dst);
+        if (dst.n_parity != src.n_parity) throw Error("copy: site subsets differ");
+        if (src.precision == dst.precision) {
+          cuda_ok(cudaMemcpyAsync(dst.v, src.v, src.Bytes(), cudaMemcpyDeviceToDevice), "copy");
+          return;
+        }
+        const int vcb = src.VolumeCB();
+        dim3 grid((vcb + 127) / 128, src.n_parity);
+        const size_t se = (size_t)24 * vcb, de = (size_t)24 * vcb;
+        if (src.precision == 8)
+          convert_kernel<double, 2, float, 4><<<grid, 128>>>((const double *)src.v, (float *)dst.v, vcb, se, de);
+        else
+          convert_kernel<float, 4, double, 2><<<grid, 128>>>((const float *)src.v, (double *)dst.v, vcb, se, de);
+        cuda_ok(cudaGetLastError(), "convert launch");
+      }
       void zero(ColorSpinorField &x) { cuda_ok(cudaMemsetAsync(x.v, 0, x.Bytes()), "memset"); }
       void ax(double a, ColorSpinorField &x) { run<R_NONE>(0.0, x, a, x, true, nullptr); }
       void axpy(double a, const ColorSpinorField &x, ColorSpinorField &y) { run<R_NONE>(a, x, 1.0, y, true, nullptr); }
