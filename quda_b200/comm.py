@@ -169,6 +169,13 @@ class HaloExchange:
         self.send = torch.zeros(self.slab_bytes, dtype=torch.uint8, device="cuda")
         self.base = self.slab.data_ptr()
 
+    def pack_stream(self, stream=None):
+        """side stream on which the pack kernel runs concurrently with the interior kernel"""
+        if getattr(self, "_pack_stream", None) is None:
+            import torch
+            self._pack_stream = torch.cuda.Stream()
+        return self._pack_stream
+
     # ------------------------------------------------------------------ per-application calls
     def start(self, in_field, in_parity, dagger, stream=None, parity_slot=0):
         """Pack the faces of `in_field` (sites of parity `in_parity`) and ship them to the neighbours."""
@@ -324,11 +331,23 @@ class _RawHalo:
 
 def apply_wilson_distributed(ex, out, in_, U, a, x, parity, dagger, op=L.OP_WILSON, A=None, stream=None, tile=None):
     """One partitioned Dslash: exchange faces of `in_` (parity 1-parity) and apply the operator.
-    The pack kernel is enqueued first so that its NVLink stores overlap the interior kernel."""
-    in_parity = 1 - parity if in_.n_parity == 1 else None
-    if in_.n_parity == 1:
-        ex.start(in_, in_parity, dagger, stream=stream)
-    else:
+
+    Schedule (device side only, nothing is polled on the host):
+      pack stream : pack_kernel -> faces + arrival flags into the neighbours' ghost slabs over NVLink
+      main stream : interior tiles (no dependence on the halo)  ->  boundary tiles (acquire the flags, finish the sites)
+    The pack stream forks from the main stream (so `in_` is complete) and joins it again afterwards (so nothing that
+    follows can overwrite `in_` while it is still being packed)."""
+    if in_.n_parity != 1:
         raise NotImplementedError("full-field halo exchange: pack each parity into its slot")
+    side = ex.pack_stream(stream) if ex.mode == "p2p" else None
+    if side is not None:
+        import torch
+        main = torch.cuda.current_stream() if stream is None else torch.cuda.ExternalStream(stream)
+        side.wait_stream(main)
+        ex.start(in_, 1 - parity, dagger, stream=side.cuda_stream)
+    else:
+        ex.start(in_, 1 - parity, dagger, stream=stream)
     D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(ex.halo()), stream=stream, tile=tile,
              backend=ex.backend)
+    if side is not None:
+        main.wait_stream(side)

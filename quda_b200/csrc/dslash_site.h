@@ -12,7 +12,7 @@
 namespace b200
 {
 
-  enum KernelType { K_INTERIOR = 0, K_EXTERIOR_ALL = 1 };
+  enum KernelType { K_INTERIOR = 0, K_EXTERIOR_ALL = 1, K_FULL = 2 };
   enum OpType { OP_WILSON = 0, OP_CLOVER = 1, OP_CLOVER_PC = 2 };
 
   constexpr int kMaxParity = 2;
@@ -42,8 +42,16 @@ namespace b200
   // shifts (tile extents are powers of two) and the only division is a multiply-high: no runtime integer division.
   struct TileMap {
     int sh[4];          // log2 of the tile extents: [0] in checkerboard sites (x/2), [1..3] in sites
-    int nt[4];          // tiles per dimension
-    unsigned nt0_magic; // floor(2^32 / nt[0]) + 1 (nt[0] >= 2); blockIdx.x / nt[0] == umulhi(blockIdx.x, magic)
+    int nt[4];          // tiles per dimension (whole lattice)
+    int org[4], cnt[4]; // the launch covers the box of tiles [org, org + cnt)
+    unsigned cnt0_magic; // floor(2^32 / cnt[0]) + 1 (cnt[0] >= 2); blockIdx.x / cnt[0] == umulhi(blockIdx.x, magic)
+  };
+
+  // Up to 8 boxes of boundary tiles (two per partitioned dimension) enumerated by one 1-d grid
+  struct SlabTable {
+    int n;
+    int cta_start[9];
+    int org[8][4], cnt[8][4];
   };
 
   B2_HD unsigned mulhi_u32(unsigned a, unsigned b)
@@ -55,18 +63,10 @@ namespace b200
 #endif
   }
 
-  B2_HD bool tile_site(int *x, int &x_cb, int &parity, const Geom &g, const TileMap &tm, int n_parity, int arg_parity,
-                       unsigned bx, unsigned by, unsigned bz, unsigned tid)
+  // thread `tid` of the CTA that owns tile (b0,b1,b2,b3) -> its site; false if the (ragged) tile sticks out of the lattice
+  B2_HD bool tile_thread_site(int *x, int &x_cb, const Geom &g, const TileMap &tm, int parity, int b0, int b1, int b2, int b3,
+                              unsigned tid)
   {
-    const int b1 = tm.nt[0] == 1 ? (int)bx : (int)mulhi_u32(bx, tm.nt0_magic);
-    const int b0 = (int)bx - b1 * tm.nt[0];
-    const int b2 = (int)by;
-    int b3 = (int)bz;
-    parity = arg_parity;
-    if (n_parity == 2) {
-      parity = b3 >= tm.nt[3] ? 1 : 0;
-      b3 -= parity * tm.nt[3];
-    }
     const int l = (int)tid;
     const int l0 = l & ((1 << tm.sh[0]) - 1);
     const int l1 = (l >> tm.sh[0]) & ((1 << tm.sh[1]) - 1);
@@ -80,6 +80,40 @@ namespace b200
     x[0] = 2 * xh + ((x[1] + x[2] + x[3] + parity) & 1);
     x_cb = ((x[3] * g.X[2] + x[2]) * g.X[1] + x[1]) * g.Xh0 + xh;
     return true;
+  }
+
+  // box launch: grid = (cnt0*cnt1, cnt2, cnt3 * n_parity)
+  B2_HD bool tile_site(int *x, int &x_cb, int &parity, const Geom &g, const TileMap &tm, int n_parity, int arg_parity,
+                       unsigned bx, unsigned by, unsigned bz, unsigned tid)
+  {
+    const int b1 = tm.cnt[0] == 1 ? (int)bx : (int)mulhi_u32(bx, tm.cnt0_magic);
+    const int b0 = (int)bx - b1 * tm.cnt[0];
+    const int b2 = (int)by;
+    int b3 = (int)bz;
+    parity = arg_parity;
+    if (n_parity == 2) {
+      parity = b3 >= tm.cnt[3] ? 1 : 0;
+      b3 -= parity * tm.cnt[3];
+    }
+    return tile_thread_site(x, x_cb, g, tm, parity, tm.org[0] + b0, tm.org[1] + b1, tm.org[2] + b2, tm.org[3] + b3, tid);
+  }
+
+  // slab launch: grid = (total CTAs of all slabs, n_parity)
+  B2_HD bool slab_site(int *x, int &x_cb, const Geom &g, const TileMap &tm, const SlabTable &st, int parity, unsigned bx,
+                       unsigned tid)
+  {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < 8; k++)
+      if (k < st.n && (int)bx >= st.cta_start[k]) s = k;
+    int l = (int)bx - st.cta_start[s];
+    const int b0 = l % st.cnt[s][0];
+    l /= st.cnt[s][0];
+    const int b1 = l % st.cnt[s][1];
+    l /= st.cnt[s][1];
+    const int b2 = l % st.cnt[s][2];
+    const int b3 = l / st.cnt[s][2];
+    return tile_thread_site(x, x_cb, g, tm, parity, st.org[s][0] + b0, st.org[s][1] + b1, st.org[s][2] + b2, st.org[s][3] + b3, tid);
   }
 
   // which spin pair the t-direction projector keeps: P(3,+1) -> upper (spins 0,1), P(3,-1) -> lower
@@ -98,6 +132,57 @@ namespace b200
     }
   }
 
+  // ---- one hop, source on this rank (periodic wrap inside the local lattice)
+  template <class P, int recon, bool dagger, bool fwd>
+  B2_HD void hop_local(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    const SpinorView<P> &in = arg.in[1 - parity];
+    constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
+    real u[18], h[12];
+    int y[4] = {x[0], x[1], x[2], x[3]};
+    if (fwd)
+      y[d] = (x[d] + 1 >= g.X[d]) ? 0 : x[d] + 1;
+    else
+      y[d] = (x[d] - 1 < 0) ? g.X[d] - 1 : x[d] - 1;
+    const int n_cb = cb_from_coords(y, g);
+    if (fwd)
+      arg.U.load(u, d, x_cb, parity);
+    else
+      arg.U.load(u, d, n_cb, 1 - parity);
+    if (d == 3) {
+      real t[12];
+      load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+#pragma unroll
+      for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+    } else {
+      real v[24];
+      in.load(v, n_cb);
+      project(h, v, d, sign);
+    }
+    su3_mul<!fwd>(r, u, h);
+  }
+
+  // ---- one hop across a partitioned face: pre-projected half spinor from the ghost buffer, backward link from the pad
+  template <class P, int recon, bool fwd>
+  B2_HD void hop_ghost(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    real u[18], h[12];
+    const int fidx = face_index(x, g, d);
+    if (fwd)
+      arg.U.load(u, d, x_cb, parity);
+    else
+      arg.U.load(u, d, g.volume_cb + fidx, 1 - parity); // ghost link lives in the pad
+    GhostView<P> gv = arg.ghost[d][fwd ? 1 : 0];
+    gv.v += (1 - parity) * arg.ghost_parity_stride[d];
+    if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
+    gv.load(h, fidx);
+    su3_mul<!fwd>(r, u, h);
+  }
+
   // Accumulate the hops of one output site.
   //   kt == K_INTERIOR     : every hop whose source is local (periodic wrap inside non-partitioned dims).
   //                          Written WITHOUT branches: all 16 loads of the 8 hops are unconditional so that the
@@ -105,89 +190,62 @@ namespace b200
   //                          (memory-level parallelism per warp); with partitioned dims (`part`) a hop that would
   //                          cross a partitioned boundary still loads its periodic image but is masked to zero.
   //   kt == K_EXTERIOR_ALL : only hops that cross a partitioned boundary, sources read from the ghost buffers
+  //   kt == K_FULL         : all 8 hops, each from the ghost buffer if it crosses a partitioned face, else local --
+  //                          used for the boundary tiles once the halo has arrived (no read-modify-write pass)
   template <class P, int recon, bool dagger, KernelType kt, bool part = true>
   B2_HD void wilson_hops(typename P::real *acc, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
-    const SpinorView<P> &in = arg.in[1 - parity];
-
 #pragma unroll
     for (int d = 0; d < 4; d++) {
-      // ---------------- forward hop: U_d(x) P(d, dagger ? + : -) in(x + d)
-      {
+      { // forward hop: U_d(x) P(d, dagger ? + : -) in(x + d)
         constexpr int sign = dagger ? +1 : -1;
-        const bool boundary = (x[d] + 1 >= g.X[d]);
+        const bool ghost = (x[d] + 1 >= g.X[d]) && arg.comm_dim[d];
+        real r[12];
         if constexpr (kt == K_INTERIOR) {
-          real u[18], h[12], r[12];
-          arg.U.load(u, d, x_cb, parity);
-          int y[4] = {x[0], x[1], x[2], x[3]};
-          y[d] = boundary ? 0 : x[d] + 1;
-          const int n_cb = cb_from_coords(y, g);
-          if (d == 3) {
-            real t[12];
-            load_spin_pair<P, (sign > 0)>(t, in, n_cb);
-#pragma unroll
-            for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
-          } else {
-            real v[24];
-            in.load(v, n_cb);
-            project(h, v, d, sign);
-          }
-          su3_mul<false>(r, u, h);
+          hop_local<P, recon, dagger, true>(r, arg, x, x_cb, parity, d);
           if constexpr (part) {
-            const real m = (boundary && arg.comm_dim[d]) ? (real)0 : (real)1;
+            const real m = ghost ? (real)0 : (real)1;
 #pragma unroll
             for (int i = 0; i < 12; i++) r[i] *= m;
           }
           reconstruct_add(acc, r, d, sign);
-        } else if (boundary && arg.comm_dim[d]) {
-          real u[18], h[12], r[12];
-          arg.U.load(u, d, x_cb, parity);
-          GhostView<P> gv = arg.ghost[d][1];
-          gv.v += (1 - parity) * arg.ghost_parity_stride[d];
-          if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
-          gv.load(h, face_index(x, g, d));
-          su3_mul<false>(r, u, h);
+        } else if constexpr (kt == K_EXTERIOR_ALL) {
+          if (ghost) {
+            hop_ghost<P, recon, true>(r, arg, x, x_cb, parity, d);
+            reconstruct_add(acc, r, d, sign);
+          }
+        } else {
+          if (ghost)
+            hop_ghost<P, recon, true>(r, arg, x, x_cb, parity, d);
+          else
+            hop_local<P, recon, dagger, true>(r, arg, x, x_cb, parity, d);
           reconstruct_add(acc, r, d, sign);
         }
       }
-      // ---------------- backward hop: U_d(x - d)^dagger P(d, dagger ? - : +) in(x - d)
-      {
+      { // backward hop: U_d(x - d)^dagger P(d, dagger ? - : +) in(x - d)
         constexpr int sign = dagger ? -1 : +1;
-        const bool boundary = (x[d] - 1 < 0);
+        const bool ghost = (x[d] - 1 < 0) && arg.comm_dim[d];
+        real r[12];
         if constexpr (kt == K_INTERIOR) {
-          real u[18], h[12], r[12];
-          int y[4] = {x[0], x[1], x[2], x[3]};
-          y[d] = boundary ? g.X[d] - 1 : x[d] - 1;
-          const int n_cb = cb_from_coords(y, g);
-          arg.U.load(u, d, n_cb, 1 - parity);
-          if (d == 3) {
-            real t[12];
-            load_spin_pair<P, (sign > 0)>(t, in, n_cb);
-#pragma unroll
-            for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
-          } else {
-            real v[24];
-            in.load(v, n_cb);
-            project(h, v, d, sign);
-          }
-          su3_mul<true>(r, u, h);
+          hop_local<P, recon, dagger, false>(r, arg, x, x_cb, parity, d);
           if constexpr (part) {
-            const real m = (boundary && arg.comm_dim[d]) ? (real)0 : (real)1;
+            const real m = ghost ? (real)0 : (real)1;
 #pragma unroll
             for (int i = 0; i < 12; i++) r[i] *= m;
           }
           reconstruct_add(acc, r, d, sign);
-        } else if (boundary && arg.comm_dim[d]) {
-          real u[18], h[12], r[12];
-          const int fidx = face_index(x, g, d);
-          arg.U.load(u, d, g.volume_cb + fidx, 1 - parity); // ghost link lives in the pad
-          GhostView<P> gv = arg.ghost[d][0];
-          gv.v += (1 - parity) * arg.ghost_parity_stride[d];
-          if constexpr (P::fixed) gv.norm += (1 - parity) * arg.ghost_norm_parity_stride[d];
-          gv.load(h, fidx);
-          su3_mul<true>(r, u, h);
+        } else if constexpr (kt == K_EXTERIOR_ALL) {
+          if (ghost) {
+            hop_ghost<P, recon, false>(r, arg, x, x_cb, parity, d);
+            reconstruct_add(acc, r, d, sign);
+          }
+        } else {
+          if (ghost)
+            hop_ghost<P, recon, false>(r, arg, x, x_cb, parity, d);
+          else
+            hop_local<P, recon, dagger, false>(r, arg, x, x_cb, parity, d);
           reconstruct_add(acc, r, d, sign);
         }
       }
@@ -233,6 +291,28 @@ namespace b200
       }
       // OP_CLOVER_PC on an incomplete site: store the bare partial sum; x and a are applied by the exterior kernel
       // after A^{-1} (dslash_wilson_clover_preconditioned.cuh:74-101)
+    }
+    arg.out[parity].save(acc, x_cb);
+  }
+
+  // Complete update of a boundary site once the halo is there: all hops (local or ghost), then clover / xpay exactly as
+  // for an unpartitioned lattice.  Together with the interior launch over the non-boundary tiles this replaces the
+  // reference's "interior partial sums + exterior read-modify-write" split (include/kernels/dslash_wilson.cuh:186-195).
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  B2_HD void dslash_site_full(const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
+  {
+    using real = typename P::real;
+    real acc[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) acc[i] = 0;
+    wilson_hops<P, recon, dagger, K_FULL>(acc, arg, x, x_cb, parity);
+    if constexpr (op == OP_CLOVER_PC) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+    if constexpr (xpay) {
+      real xv[24];
+      arg.x[parity].template load<Cache::STREAM>(xv, x_cb);
+      if constexpr (op == OP_CLOVER) clover_apply_site<P, false>(xv, arg.A, x_cb, parity);
+#pragma unroll
+      for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
     }
     arg.out[parity].save(acc, x_cb);
   }

@@ -44,7 +44,7 @@ namespace b200
     dslash_site_interior<P, recon, dagger, xpay, op, part>(arg, x, x_cb, parity);
   }
 
-  // ---- system-scope flag helpers for the NVLink remote-write halo path
+  // ---- system-scope flag helpers for the NVLink remote-write halo path (used by the kernels below)
   __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
   {
     unsigned v;
@@ -79,6 +79,19 @@ namespace b200
       }
     }
     __syncthreads();
+  }
+
+  // Boundary tiles: wait for the neighbours' faces, then update the sites completely (local + ghost hops, clover, xpay)
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  __global__ void __launch_bounds__(kMaxTile, MinBlocks<P>::value)
+    dslash_boundary_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TileMap tm,
+                           const __grid_constant__ SlabTable st)
+  {
+    wait_for_halo(arg);
+    const int parity = arg.n_parity == 2 ? blockIdx.y : arg.parity;
+    int x[4], x_cb;
+    if (!slab_site(x, x_cb, arg.geom, tm, st, parity, blockIdx.x, threadIdx.x)) return;
+    dslash_site_full<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
   }
 
   template <class P, int recon, bool dagger, bool xpay, OpType op>
@@ -169,18 +182,38 @@ namespace b200
   int launch_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
   {
     cudaStream_t s = (cudaStream_t)rq.stream;
+    TileMap tm;
+    int threads, gx, gy, gz, rc;
+    if (int e = make_tile_map(tm, threads, rq.tile, arg.geom, kMaxTile)) return e;
+    const bool partitioned = arg.threads_ext[4] > 0;
+    if (rq.kernel == B200_KERNEL_AUTO && partitioned) {
+      // B200 schedule: tiles that touch no partitioned face run now (branch-free kernel, overlapping the halo that is
+      // in flight over NVLink); the boundary tiles follow in ONE launch that acquires the arrival flags and updates
+      // its sites completely -- no partial sums, no read-modify-write pass.
+      SlabTable st;
+      const int nb = split_boundary(tm, st, arg.comm_dim);
+      if (box_grid(tm, arg.n_parity, gx, gy, gz, rc)) {
+        dslash_interior_kernel<P, recon, dagger, xpay, op, false><<<dim3(gx, gy, gz), threads, 0, s>>>(arg, tm);
+        count_launch();
+      } else if (rc) {
+        return rc;
+      }
+      if (nb > 0) {
+        dslash_boundary_kernel<P, recon, dagger, xpay, op><<<dim3(nb, arg.n_parity, 1), threads, 0, s>>>(arg, tm, st);
+        count_launch();
+      }
+      return check_cuda(cudaGetLastError(), "dslash launch");
+    }
     if (rq.kernel != B200_KERNEL_EXTERIOR) {
-      TileMap tm;
-      int threads, gx, gy, gz;
-      if (int rc = make_tile_map(tm, threads, gx, gy, gz, rq.tile, arg.geom, arg.n_parity, kMaxTile)) return rc;
+      if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
       dim3 grid(gx, gy, gz);
-      if (arg.threads_ext[4] > 0)
+      if (partitioned)
         dslash_interior_kernel<P, recon, dagger, xpay, op, true><<<grid, threads, 0, s>>>(arg, tm);
       else
         dslash_interior_kernel<P, recon, dagger, xpay, op, false><<<grid, threads, 0, s>>>(arg, tm);
       count_launch();
     }
-    if (rq.kernel != B200_KERNEL_INTERIOR && arg.threads_ext[4] > 0) {
+    if (rq.kernel != B200_KERNEL_INTERIOR && partitioned) {
       dim3 grid((arg.threads_ext[4] + 127) / 128, arg.n_parity, 1);
       dslash_exterior_kernel<P, recon, dagger, xpay, op><<<grid, 128, 0, s>>>(arg);
       count_launch();

@@ -206,9 +206,9 @@ namespace b200
     return 0;
   }
 
-  // launch geometry of the interior kernel for a requested tile (extents rounded down to powers of two)
-  inline int make_tile_map(TileMap &tm, int &threads, int &gx, int &gy, int &gz, const int *tile, const Geom &g,
-                           int n_parity, int max_threads)
+  // launch geometry of the interior kernel for a requested tile (extents rounded down to powers of two); the box
+  // initially covers all tiles
+  inline int make_tile_map(TileMap &tm, int &threads, const int *tile, const Geom &g, int max_threads)
   {
     threads = 1;
     for (int d = 0; d < 4; d++) {
@@ -218,17 +218,73 @@ namespace b200
       while (sh > 0 && (1 << sh) > 2 * ext) sh--; // no point in tiles more than twice the extent
       tm.sh[d] = sh;
       tm.nt[d] = (ext + (1 << sh) - 1) >> sh;
+      tm.org[d] = 0;
+      tm.cnt[d] = tm.nt[d];
       threads <<= sh;
     }
     if (threads > max_threads) return set_error(B200_ERR_INVALID, "tile volume %d exceeds %d threads", threads, max_threads);
-    tm.nt0_magic = tm.nt[0] >= 2 ? (unsigned)(0x100000000ull / (unsigned)tm.nt[0]) + 1u : 0u;
-    // umulhi(b, magic) == b / nt0 needs b * nt0 < 2^32
-    if ((long long)tm.nt[0] * tm.nt[0] * tm.nt[1] >= (1ll << 32) || tm.nt[2] > 65535 || tm.nt[3] * n_parity > 65535)
-      return set_error(B200_ERR_INVALID, "lattice too large for the tile grid");
-    gx = tm.nt[0] * tm.nt[1];
-    gy = tm.nt[2];
-    gz = tm.nt[3] * n_parity;
     return 0;
+  }
+
+  // grid of a box launch; returns false if the box is empty
+  inline bool box_grid(TileMap &tm, int n_parity, int &gx, int &gy, int &gz, int &rc)
+  {
+    rc = 0;
+    for (int d = 0; d < 4; d++)
+      if (tm.cnt[d] <= 0) return false;
+    tm.cnt0_magic = tm.cnt[0] >= 2 ? (unsigned)(0x100000000ull / (unsigned)tm.cnt[0]) + 1u : 0u;
+    // umulhi(b, magic) == b / cnt0 needs b * cnt0 < 2^32
+    if ((long long)tm.cnt[0] * tm.cnt[0] * tm.cnt[1] >= (1ll << 32) || tm.cnt[2] > 65535 || tm.cnt[3] * n_parity > 65535) {
+      rc = set_error(B200_ERR_INVALID, "lattice too large for the tile grid");
+      return false;
+    }
+    gx = tm.cnt[0] * tm.cnt[1];
+    gy = tm.cnt[2];
+    gz = tm.cnt[3] * n_parity;
+    return true;
+  }
+
+  // Split the tiles of a partitioned lattice into the box that touches no partitioned face (tm.org / tm.cnt) and a
+  // disjoint set of boundary slabs: going from the highest partitioned dimension down, the slab(s) of dimension D fix
+  // the tile index of D to its first / last value, take the interior range in the partitioned dimensions above D and
+  // the full range everywhere else.  Returns the number of boundary CTAs.
+  inline int split_boundary(TileMap &tm, SlabTable &st, const int *comm_dim)
+  {
+    st.n = 0;
+    st.cta_start[0] = 0;
+    for (int d = 0; d < 4; d++) {
+      tm.org[d] = comm_dim[d] ? 1 : 0;
+      tm.cnt[d] = tm.nt[d] - (comm_dim[d] ? 2 : 0); // <= 0: no interior tile at all in that dimension
+    }
+    for (int D = 3; D >= 0; D--) {
+      if (!comm_dim[D]) continue;
+      const int nb = tm.nt[D] >= 2 ? 2 : 1;
+      for (int k = 0; k < nb; k++) {
+        int org[4], cnt[4];
+        long ctas = 1;
+        for (int e = 0; e < 4; e++) {
+          if (e == D) {
+            org[e] = k == 0 ? 0 : tm.nt[D] - 1;
+            cnt[e] = 1;
+          } else if (e > D && comm_dim[e]) {
+            org[e] = 1;
+            cnt[e] = tm.nt[e] - 2;
+          } else {
+            org[e] = 0;
+            cnt[e] = tm.nt[e];
+          }
+          ctas *= cnt[e] > 0 ? cnt[e] : 0;
+        }
+        if (ctas <= 0) continue;
+        for (int e = 0; e < 4; e++) {
+          st.org[st.n][e] = org[e];
+          st.cnt[st.n][e] = cnt[e];
+        }
+        st.cta_start[st.n + 1] = st.cta_start[st.n] + (int)ctas;
+        st.n++;
+      }
+    }
+    return st.cta_start[st.n];
   }
 
   template <class P> int launch_precision(const LaunchRequest &rq);

@@ -27,12 +27,13 @@ namespace b200
   template <class P, int recon, bool dagger, bool xpay, OpType op> int run_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
   {
     const Geom &g = arg.geom;
-    if (rq.kernel != B200_KERNEL_EXTERIOR) {
-      // walk the SAME launch grid as kernels.cuh::launch_config (tile map, block and thread decomposition, parity in z)
-      TileMap tm;
-      int threads, gx, gy, gz;
-      if (int rc = make_tile_map(tm, threads, gx, gy, gz, rq.tile, g, arg.n_parity, 256)) return rc;
-      long visited = 0;
+    TileMap tm;
+    int threads, gx, gy, gz, rc;
+    if (int e = make_tile_map(tm, threads, rq.tile, g, 128)) return e;
+    const bool partitioned = arg.threads_ext[4] > 0;
+    long visited = 0;
+    // walk the SAME launch grids as kernels.cuh::launch_config (tile boxes, slab table, block / thread decomposition)
+    auto walk_box = [&](auto site_fn) {
 #pragma omp parallel for collapse(2) reduction(+ : visited)
       for (int bz = 0; bz < gz; bz++)
         for (int by = 0; by < gy; by++)
@@ -40,9 +41,39 @@ namespace b200
             for (int tid = 0; tid < threads; tid++) {
               int x[4], x_cb, par;
               if (!tile_site(x, x_cb, par, g, tm, arg.n_parity, arg.parity, bx, by, bz, tid)) continue;
-              dslash_site_interior<P, recon, dagger, xpay, op>(arg, x, x_cb, par);
+              site_fn(x, x_cb, par);
               visited++;
             }
+    };
+    if (rq.kernel == B200_KERNEL_AUTO && partitioned) {
+      SlabTable st;
+      const int nb = split_boundary(tm, st, arg.comm_dim);
+      if (box_grid(tm, arg.n_parity, gx, gy, gz, rc))
+        walk_box([&](const int *x, int x_cb, int par) { dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par); });
+      else if (rc)
+        return rc;
+      for (int pp = 0; pp < arg.n_parity; pp++) {
+        const int parity = arg.n_parity == 2 ? pp : arg.parity;
+#pragma omp parallel for reduction(+ : visited)
+        for (int bx = 0; bx < nb; bx++)
+          for (int tid = 0; tid < threads; tid++) {
+            int x[4], x_cb;
+            if (!slab_site(x, x_cb, g, tm, st, parity, bx, tid)) continue;
+            dslash_site_full<P, recon, dagger, xpay, op>(arg, x, x_cb, parity);
+            visited++;
+          }
+      }
+      if (visited != (long)g.volume_cb * arg.n_parity)
+        return set_error(B200_ERR_INVALID, "interior box + boundary slabs visited %ld of %ld sites", visited,
+                         (long)g.volume_cb * arg.n_parity);
+      return 0;
+    }
+    if (rq.kernel != B200_KERNEL_EXTERIOR) {
+      if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+      if (partitioned)
+        walk_box([&](const int *x, int x_cb, int par) { dslash_site_interior<P, recon, dagger, xpay, op, true>(arg, x, x_cb, par); });
+      else
+        walk_box([&](const int *x, int x_cb, int par) { dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par); });
       if (visited != (long)g.volume_cb * arg.n_parity)
         return set_error(B200_ERR_INVALID, "tile map visited %ld of %ld sites", visited, (long)g.volume_cb * arg.n_parity);
     }

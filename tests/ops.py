@@ -85,7 +85,8 @@ def self_exchange(P, halo, in_field, in_parity, dagger, be, parity_slot=0):
     D.PackGhost(dst, in_field, in_parity, dagger, halo.comm_dim, backend=be)
 
 
-def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4), xpay=False, dagger=0, clover_kw=None):
+def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4), xpay=False, dagger=0, clover_kw=None,
+                      split=False, tile=None):
     """Self-partitioned run (the reference's --partition trick, tests/utils/host_utils.cpp:425): pack -> ghost buffers
     -> interior + fused exterior must reproduce the plain periodic operator."""
     P = Problem(X, prec, recon, mem, clover=(op != "wilson"), **(clover_kw or {}))
@@ -98,19 +99,23 @@ def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4
         out = P.empty()
         a = -kappa if xpay else 0.0
         xdev = P.to_dev(xs) if xpay else None
+        kws = [dict(tile=tile)] if not split else [dict(kernel=1, tile=tile), dict(kernel=2, tile=tile)]  # AUTO | INTERIOR, EXTERIOR
         if op == "wilson":
-            D.ApplyWilson(out, din, P.U, a, xdev, parity, dagger, halo=halo, backend=be)
+            for kw in kws:
+                D.ApplyWilson(out, din, P.U, a, xdev, parity, dagger, halo=halo, backend=be, **kw)
             ref = oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
             if xpay:
                 ref = xs.astype(np.float64) - kappa * ref
         elif op == "clover_pc":
-            D.ApplyWilsonCloverPreconditioned(out, din, P.U, P.A if P.A.dynamic else P.Ainv, a, xdev, parity, dagger,
-                                              halo=halo, backend=be)
+            for kw in kws:
+                D.ApplyWilsonCloverPreconditioned(out, din, P.U, P.A if P.A.dynamic else P.Ainv, a, xdev, parity, dagger,
+                                                  halo=halo, backend=be, **kw)
             ref = oracle.clover_dslash(P.gauge, P.clover_inv, s, X, parity, dagger).astype(np.float64)
             if xpay:
                 ref = xs.astype(np.float64) - kappa * ref
         else:
-            D.ApplyWilsonClover(out, din, P.U, P.A, -kappa, P.to_dev(xs), parity, dagger, halo=halo, backend=be)
+            for kw in kws:
+                D.ApplyWilsonClover(out, din, P.U, P.A, -kappa, P.to_dev(xs), parity, dagger, halo=halo, backend=be, **kw)
             ref = oracle.apply_clover(P.clover, xs, X, parity).astype(np.float64) \
                 - kappa * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
         assert_close(ref, P.to_host(out), prec, recon, f"partitioned {comm_dim} op={op} p={parity}")

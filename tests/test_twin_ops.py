@@ -41,3 +41,19 @@ def test_partitioned_wilson_precisions(prec, recon, comm_dim):
 def test_partitioned_clover(op, prec, comm_dim):
     ops.check_partitioned(HostMem, twin_backend(), prec, 12, comm_dim, op=op, xpay=True,
                           clover_kw=dict(compressed=True, dynamic=True))
+
+
+@pytest.mark.parametrize("comm_dim", MASKS)
+def test_partitioned_reference_style_split(comm_dim):
+    """explicit INTERIOR (masked partial sums) + EXTERIOR (read-modify-write) kernels, the reference's decomposition"""
+    ops.check_partitioned(HostMem, twin_backend(), 8, 12, comm_dim, X=(4, 6, 4, 8), xpay=True, split=True)
+
+
+@pytest.mark.parametrize("op", ["wilson", "clover_pc", "clover"])
+@pytest.mark.parametrize("tile", [(16, 2, 2, 1), (2, 2, 2, 2), (1, 4, 1, 2), (2, 8, 4, 2)])
+@pytest.mark.parametrize("comm_dim", [(0, 0, 0, 1), (0, 1, 1, 1), (1, 1, 1, 1), (1, 0, 1, 0)])
+def test_boundary_slab_schedule(op, tile, comm_dim):
+    """interior tile box + boundary slabs must cover every site exactly once for any tiling / partition mask
+    (including tilings with 1 or 2 tiles along a partitioned dimension)"""
+    ops.check_partitioned(HostMem, twin_backend(), 8, 18, comm_dim, op=op, X=(8, 6, 4, 8), xpay=True, tile=tile,
+                          clover_kw=dict(compressed=True, dynamic=True))

@@ -26,7 +26,7 @@ def test_wilson_dslash(prec, recon, X):
             assert_close(ref, P.to_host(out), prec, recon, f"dslash parity={parity} dagger={dagger}")
 
 
-@pytest.mark.parametrize("tile", [(16, 2, 2, 1), (2, 2, 2, 2), (1, 4, 1, 2), (4, 1, 1, 1), (2, 8, 4, 4), (3, 4, 4, 4)])
+@pytest.mark.parametrize("tile", [(16, 2, 2, 1), (2, 2, 2, 2), (1, 4, 1, 2), (4, 1, 1, 1), (2, 8, 4, 2), (3, 4, 4, 2)])
 def test_launch_tilings_cover_the_lattice(tile):
     """The host twin walks the same (grid, block) decomposition the CUDA launcher builds (launch.h::make_tile_map,
     dslash_site.h::tile_site): every tiling, including ragged ones and nt0 == 1, must visit each site exactly once."""
