@@ -154,6 +154,14 @@ int b200_pack_ghost(const b200_pack_args *args);
 /* bytes of one face buffer holding BOTH parities (what b200_halo.ghost[d][dir] must point to), and of one parity */
 size_t b200_ghost_face_bytes(int precision, const int X[4], int dim);
 
+/* Device-side spinor marshaling (the spinor slice of QUDA's copy kernels, lib/copy_color_spinor.cu,
+ * include/kernels/copy_color_spinor.cuh:4-89): converts between the host interface order
+ * (QUDA_SPACE_SPIN_COLOR_FIELD_ORDER: [site][spin 4][colour 3][re,im], DeGrand-Rossi basis, fp64 or fp32, one parity)
+ * and the native FloatN order in the UKQCD basis at `native.` precision.  Both buffers are device memory.
+ * to_native != 0: host order -> native;  to_native == 0: native -> host order. */
+int b200_copy_spinor(const b200_spinor *native, int native_precision, void *host_order, int host_precision, int to_native,
+                     void *stream);
+
 /* Halo buffers that peer GPUs must be able to map: plain cudaMalloc allocations (zero-filled) plus CUDA-IPC
  * export / import.  Replaces the reference's static ghost buffers + IPC handle exchange
  * (lib/lattice_field.cpp:252-470, lib/targets/cuda/comm_target.cpp:37-167); the 64-byte handles travel between
@@ -181,6 +189,7 @@ typedef struct {
   int *block_counter;
   int *timeout_flag;
   unsigned seq;               /* exchanges started so far (all ranks advance in lock step) */
+  void *pack_stream;          /* optional cudaStream_t: pack kernels run there, concurrently with the interior tiles */
   void (*allreduce_sum)(double *data, int n, void *user); /* NULL on a single rank */
   void *user;
 } b200_comm;

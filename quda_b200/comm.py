@@ -173,7 +173,7 @@ class HaloExchange:
         """side stream on which the pack kernel runs concurrently with the interior kernel"""
         if getattr(self, "_pack_stream", None) is None:
             import torch
-            self._pack_stream = torch.cuda.Stream()
+            self._pack_stream = torch.cuda.Stream(priority=-1)  # high priority: never starved by spinning boundary CTAs
         return self._pack_stream
 
     # ------------------------------------------------------------------ per-application calls
@@ -290,6 +290,8 @@ class HaloExchange:
         c.block_counter = self.base + self.counter_off
         c.timeout_flag = self.base + self.timeout_off
         c.seq = self.seq
+        if self.mode == "p2p":
+            c.pack_stream = self.pack_stream().cuda_stream
         if self.mode == "p2p" and g.size > 1:
             import torch
             dist = self.dist

@@ -98,6 +98,30 @@ int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", precision);
 }
 
+int b200_copy_spinor(const b200_spinor *native, int native_precision, void *host_order, int host_precision, int to_native,
+                     void *stream)
+{
+  if (!native || !native->v || !host_order) return set_error(B200_ERR_INVALID, "b200_copy_spinor: null argument");
+  if (int rc = require_device()) return rc;
+  if (native->n_parity != 1) return set_error(B200_ERR_INVALID, "b200_copy_spinor converts one parity block per call");
+  if (host_precision != B200_DOUBLE && host_precision != B200_SINGLE)
+    return set_error(B200_ERR_INVALID, "host order precision must be 8 or 4 (got %d)", host_precision);
+  CopyRequest rq;
+  rq.native = native->v;
+  rq.native_norm = native->norm;
+  rq.host = host_order;
+  rq.volume_cb = native->volume_cb;
+  rq.host_precision = host_precision;
+  rq.to_native = to_native ? 1 : 0;
+  rq.stream = stream;
+  switch (native_precision) {
+  case B200_DOUBLE: return launch_copy_precision<PrecF64>(rq);
+  case B200_SINGLE: return launch_copy_precision<PrecF32>(rq);
+  case B200_HALF: return launch_copy_precision<PrecH16>(rq);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", native_precision);
+}
+
 int b200_comm_alloc(void **ptr, size_t bytes)
 {
   if (!ptr || bytes == 0) return set_error(B200_ERR_INVALID, "b200_comm_alloc: null pointer or zero size");

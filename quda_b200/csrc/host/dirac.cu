@@ -110,7 +110,16 @@ namespace b200
       a.in = in.desc();
       a.block_counter = comm->block_counter;
       a.seq = comm->seq;
-      a.stream = stream;
+      if (comm->pack_stream && comm->pack_stream != stream) {
+        // fork: the pack kernel runs on its own stream, concurrently with the interior tiles (joined in apply())
+        static cudaEvent_t fork_ev = nullptr;
+        if (!fork_ev) cuda_ok(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming), "event");
+        cuda_ok(cudaEventRecord(fork_ev, (cudaStream_t)stream), "record");
+        cuda_ok(cudaStreamWaitEvent((cudaStream_t)comm->pack_stream, fork_ev, 0), "wait");
+        a.stream = comm->pack_stream;
+      } else {
+        a.stream = stream;
+      }
       abi_ok(b200_pack_ghost(&a));
     }
 
@@ -143,6 +152,13 @@ namespace b200
       halo_fill(args.halo, comm_override, part ? comm : nullptr);
       args.stream = stream;
       abi_ok(b200_dslash_apply(&args));
+      if (part && comm->pack_stream && comm->pack_stream != stream) {
+        // join: nothing enqueued later may overwrite `in` while its faces are still being packed
+        static cudaEvent_t join_ev = nullptr;
+        if (!join_ev) cuda_ok(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming), "event");
+        cuda_ok(cudaEventRecord(join_ev, (cudaStream_t)comm->pack_stream), "record");
+        cuda_ok(cudaStreamWaitEvent((cudaStream_t)stream, join_ev, 0), "wait");
+      }
     }
 
     void ApplyWilson(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a,

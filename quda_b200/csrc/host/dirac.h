@@ -48,6 +48,7 @@ namespace b200
       int *block_counter = nullptr;
       int *timeout_flag = nullptr;
       unsigned seq = 0;
+      void *pack_stream = nullptr; // cudaStream_t for the pack kernels (nullptr: same stream as the Dslash)
       void (*allreduce_sum)(double *data, int n, void *user) = nullptr; // nullptr: single rank
       void *user = nullptr;
       bool partitioned() const { return comm_dim[0] || comm_dim[1] || comm_dim[2] || comm_dim[3]; }

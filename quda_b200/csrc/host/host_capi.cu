@@ -36,6 +36,7 @@ static void pull_comm(b200_dirac_s *h)
   k.block_counter = c->block_counter;
   k.timeout_flag = c->timeout_flag;
   k.seq = c->seq;
+  k.pack_stream = c->pack_stream;
   k.allreduce_sum = c->allreduce_sum;
   k.user = c->user;
 }

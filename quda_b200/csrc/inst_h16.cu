@@ -6,4 +6,5 @@ namespace b200
   template int launch_precision<PrecH16>(const LaunchRequest &);
   template int launch_clover_precision<PrecH16>(const CloverRequest &);
   template int launch_pack_precision<PrecH16>(const PackRequest &);
+  template int launch_copy_precision<PrecH16>(const CopyRequest &);
 } // namespace b200

@@ -177,6 +177,58 @@ namespace b200
     }
   }
 
+  // Host interface order <-> native order, with the DeGrand-Rossi <-> UKQCD rotation
+  // out[s] = K1[s] in[s1[s]] + K2[s] in[s2[s]], s1 = {1,2,3,0}, s2 = {3,0,1,2} (copy_color_spinor.cuh:51-89)
+  template <class P, typename H, bool to_native>
+  __global__ void __launch_bounds__(128) copy_spinor_kernel(SpinorView<P> nat, H *host, int volume_cb)
+  {
+    using real = typename P::real;
+    const int x_cb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x_cb >= volume_cb) return;
+    constexpr double k = 0.70710678118654752440;
+    constexpr int s1[4] = {1, 2, 3, 0}, s2[4] = {3, 0, 1, 2};
+    if constexpr (to_native) {
+      constexpr double K1[4] = {k, -k, -k, -k}, K2[4] = {k, -k, k, k};
+      real v[24];
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+          v[s * 6 + c] = (real)(K1[s] * (double)host[(size_t)x_cb * 24 + s1[s] * 6 + c] + K2[s] * (double)host[(size_t)x_cb * 24 + s2[s] * 6 + c]);
+      nat.save(v, x_cb);
+    } else {
+      constexpr double K1[4] = {-k, k, k, k}, K2[4] = {-k, k, -k, -k};
+      real v[24];
+      nat.template load<Cache::STREAM>(v, x_cb);
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+          host[(size_t)x_cb * 24 + s * 6 + c] = (H)(K1[s] * (double)v[s1[s] * 6 + c] + K2[s] * (double)v[s2[s] * 6 + c]);
+    }
+  }
+
+  template <class P> int launch_copy_precision(const CopyRequest &rq)
+  {
+    SpinorView<P> nat;
+    fill_spinor(nat, rq.native, rq.native_norm, rq.volume_cb);
+    const int blocks = (rq.volume_cb + 127) / 128;
+    cudaStream_t s = (cudaStream_t)rq.stream;
+    if (rq.host_precision == 8) {
+      if (rq.to_native)
+        copy_spinor_kernel<P, double, true><<<blocks, 128, 0, s>>>(nat, (double *)rq.host, rq.volume_cb);
+      else
+        copy_spinor_kernel<P, double, false><<<blocks, 128, 0, s>>>(nat, (double *)rq.host, rq.volume_cb);
+    } else {
+      if (rq.to_native)
+        copy_spinor_kernel<P, float, true><<<blocks, 128, 0, s>>>(nat, (float *)rq.host, rq.volume_cb);
+      else
+        copy_spinor_kernel<P, float, false><<<blocks, 128, 0, s>>>(nat, (float *)rq.host, rq.volume_cb);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "copy_spinor launch");
+  }
+
   // ------------------------------------------------------------------ host-side dispatch for one precision
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   int launch_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)

@@ -33,6 +33,12 @@ namespace b200
     void *stream;
   };
 
+  struct CopyRequest {
+    void *native, *native_norm, *host;
+    int volume_cb, host_precision, to_native;
+    void *stream;
+  };
+
   struct PackRequest {
     int X[4], parity, dagger, comm_dim[4];
     void *in, *in_norm;
@@ -290,5 +296,6 @@ namespace b200
   template <class P> int launch_precision(const LaunchRequest &rq);
   template <class P> int launch_clover_precision(const CloverRequest &rq);
   template <class P> int launch_pack_precision(const PackRequest &rq);
+  template <class P> int launch_copy_precision(const CopyRequest &rq);
 
 } // namespace b200

@@ -161,6 +161,15 @@ def PackGhost(dst, in_, parity, dagger, comm_dim, stream=None, backend=None):
     be.call("pack_ghost", C.byref(a))
 
 
+def copy_spinor(native, host_order, to_native, stream=None):
+    """Device-side marshaling between the host interface order ([site][4][3][2], DeGrand-Rossi; a torch tensor of
+    float32/float64 on the device) and a native ColorSpinorField.  Reference: lib/copy_color_spinor.cu."""
+    lib = L.load()
+    d = native.desc()
+    hp = host_order.element_size()
+    L.check(lib.b200_copy_spinor(C.byref(d), native.prec, host_order.data_ptr(), hp, int(bool(to_native)), stream))
+
+
 def flops_per_site(op=L.OP_WILSON, xpay=False):
     """Reference flop model: include/dslash.h:475-528, lib/dslash_wilson_clover_preconditioned.hpp:52-57."""
     f = 1320 + (48 if xpay else 0)

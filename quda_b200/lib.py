@@ -58,7 +58,8 @@ class Comm(C.Structure):
     _fields_ = [("comm_dim", C.c_int * 4), ("send_dst", ((C.c_void_p * 2) * 4) * 2),
                 ("send_signal", ((C.c_void_p * 2) * 4) * 2), ("recv", ((C.c_void_p * 2) * 4) * 2),
                 ("recv_flag", ((C.c_void_p * 2) * 4) * 2), ("block_counter", C.c_void_p),
-                ("timeout_flag", C.c_void_p), ("seq", C.c_uint), ("allreduce_sum", C.c_void_p), ("user", C.c_void_p)]
+                ("timeout_flag", C.c_void_p), ("seq", C.c_uint), ("pack_stream", C.c_void_p),
+                ("allreduce_sum", C.c_void_p), ("user", C.c_void_p)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_void_p)
@@ -102,6 +103,8 @@ def load():
         lib.b200_launch_count.restype = C.c_long
         lib.b200_ghost_face_bytes.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
         lib.b200_ghost_face_bytes.restype = C.c_size_t
+        lib.b200_copy_spinor.argtypes = [C.POINTER(Spinor), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.b200_copy_spinor.restype = C.c_int
         lib.b200_comm_alloc.argtypes, lib.b200_comm_alloc.restype = [C.POINTER(C.c_void_p), C.c_size_t], C.c_int
         lib.b200_comm_free.argtypes, lib.b200_comm_free.restype = [C.c_void_p], C.c_int
         lib.b200_ipc_get_handle.argtypes, lib.b200_ipc_get_handle.restype = [C.c_void_p, C.c_char_p], C.c_int
@@ -138,7 +141,7 @@ def check(rc, lib=None, prefix="b200"):
 
 
 EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
-                    "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
+                    "b200_copy_spinor", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
                     "b200_dirac_create", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",
                     "b200_dirac_reconstruct", "b200_invert_cg",

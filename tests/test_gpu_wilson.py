@@ -81,3 +81,23 @@ def test_argument_errors():
     with pytest.raises(L.B200Error, match="clover"):
         D.ApplyWilsonClover(P.empty(), s, P.U, D.CloverField(None, X, 4, dict(parity_stride_bytes=0, compressed=0,
                             diagonal=0.0, max_element=1.0)), 0.5, s, 0, 0)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("host_dtype", ["float32", "float64"])
+def test_device_side_spinor_marshaling(prec, host_dtype):
+    """b200_copy_spinor (host interface order <-> native UKQCD order, on the device) against the numpy marshaling"""
+    import torch
+    from quda_b200 import fields as F
+    X = (4, 6, 4, 8)
+    P = Problem(X, prec, 12, CudaMem)
+    s = P.spinor(seed=8).astype(host_dtype)
+    dev_host_order = torch.from_numpy(s).cuda()
+    nat = P.empty()
+    D.copy_spinor(nat, dev_host_order, True)
+    got = P.to_host(nat)                      # numpy: native -> host order
+    assert_close(s, got, prec, 18, "to native")
+    back = torch.zeros_like(dev_host_order)
+    D.copy_spinor(P.to_dev(s), back, False)
+    torch.cuda.synchronize()
+    assert_close(s, back.cpu().numpy(), prec, 18, "from native")
