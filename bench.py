@@ -211,8 +211,8 @@ def run_b200(a):
         # drive the partitioned Dslash through the C++ operator layer (one native call per step: pack on the side
         # stream, interior tiles, boundary tiles) -- the Python-level schedule costs more host time than the GPU needs
         from quda_b200 import dirac as DR
-        cs = ex.comm_struct()
-        dirac = DR.Dirac("wilson", P["U"], 0.0, comm=cs, stream=stream)
+        comm_cs = ex.comm_struct()
+        dirac = DR.Dirac("wilson", P["U"], 0.0, comm=comm_cs, stream=stream)
 
     def step(tile=None):
         if ex is None:
@@ -284,7 +284,7 @@ def run_b200(a):
     if world > 1 and a.breakdown:
         from quda_b200 import lib as LL
         if dirac is not None:
-            ex.seq = cs.seq
+            ex.seq = comm_cs.seq
         def timed(fn, n=50):
             for _ in range(5):
                 fn()

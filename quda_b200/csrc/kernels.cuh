@@ -33,11 +33,52 @@ namespace b200
   template <> struct MinBlocks<PrecF64> { static constexpr int value = B2_MINBLOCKS_F64; };
   template <> struct MinBlocks<PrecH16> { static constexpr int value = B2_MINBLOCKS_H16; };
 
+  // Optional L2 look-ahead: the first thread of every 128-byte line segment asks L2 for the links (and the input
+  // spinor) of the tile that a CTA B2_L2_PREFETCH launch slots further on will work on, so that by the time those
+  // CTAs run their link loads are L2 hits instead of full DRAM round trips.  The links are 2/3 of the traffic and a
+  // pure stream, i.e. perfectly predictable.
+#ifndef B2_L2_PREFETCH
+#define B2_L2_PREFETCH 0
+#endif
+  __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+  template <class P, int recon>
+  __device__ __forceinline__ void prefetch_future_tile(const DslashArgs<P, recon> &arg, const TileMap &tm)
+  {
+    using GV = GaugeView<P, recon>;
+    constexpr int lanes_per_line = 128 / sizeof(typename GV::V);
+    if ((threadIdx.x & ((1 << tm.sh[0]) - 1)) % lanes_per_line != 0) return;
+    const unsigned gx = gridDim.x, gy = gridDim.y, gz = gridDim.z;
+    unsigned lin = blockIdx.x + gx * (blockIdx.y + gy * blockIdx.z) + B2_L2_PREFETCH;
+    if (lin >= gx * gy * gz) return;
+    const unsigned bz = lin / (gx * gy);
+    lin -= bz * gx * gy;
+    const unsigned by = lin / gx;
+    const unsigned bx = lin - by * gx;
+    int x[4], x_cb, parity;
+    if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, bx, by, bz, threadIdx.x)) return;
+    const Geom &g = arg.geom;
+    const typename GV::V *gf = reinterpret_cast<const typename GV::V *>(arg.U.g[parity]);
+    const typename GV::V *gb = reinterpret_cast<const typename GV::V *>(arg.U.g[1 - parity]);
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      int y[4] = {x[0], x[1], x[2], x[3]};
+      y[d] = (x[d] - 1 < 0) ? g.X[d] - 1 : x[d] - 1;
+      const int n_cb = cb_from_coords(y, g);
+#pragma unroll
+      for (int i = 0; i < GV::M; i++) {
+        prefetch_l2(gf + (size_t)(d * GV::M + i) * arg.U.stride + x_cb);
+        prefetch_l2(gb + (size_t)(d * GV::M + i) * arg.U.stride + n_cb);
+      }
+    }
+  }
+
   // `part` == false: no dimension is partitioned -> the stencil is completely branch free
   template <class P, int recon, bool dagger, bool xpay, OpType op, bool part>
   __global__ void __launch_bounds__(kMaxTile, MinBlocks<P>::value)
     dslash_interior_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TileMap tm)
   {
+    if constexpr (B2_L2_PREFETCH > 0) prefetch_future_tile(arg, tm);
     int x[4], x_cb, parity;
     if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x))
       return;
