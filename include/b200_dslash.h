@@ -46,7 +46,10 @@ typedef enum {
 typedef enum {
   B200_KERNEL_AUTO = 0,     /* interior, then (if any comm_dim set) wait for halos and run the exterior update */
   B200_KERNEL_INTERIOR = 1, /* interior kernel only (hops across partitioned boundaries are skipped)           */
-  B200_KERNEL_EXTERIOR = 2  /* fused exterior kernel only (adds ghost hops to the partial result in `out`)      */
+  B200_KERNEL_EXTERIOR = 2, /* fused exterior kernel only (adds ghost hops to the partial result in `out`)      */
+  /* the two halves of B200_KERNEL_AUTO on a partitioned lattice, for callers that put them on different streams:  */
+  B200_KERNEL_INTERIOR_TILES = 3, /* tiles that touch no partitioned face (independent of the halo)               */
+  B200_KERNEL_BOUNDARY_TILES = 4  /* boundary tiles: waits for the arrival flags, then complete site updates      */
 } b200_kernel;
 
 /* One ColorSpinorField in native order.  n_parity == 1: a single-parity field (QUDA_PARITY_SITE_SUBSET);

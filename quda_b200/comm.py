@@ -335,21 +335,27 @@ def apply_wilson_distributed(ex, out, in_, U, a, x, parity, dagger, op=L.OP_WILS
     """One partitioned Dslash: exchange faces of `in_` (parity 1-parity) and apply the operator.
 
     Schedule (device side only, nothing is polled on the host):
-      pack stream : pack_kernel -> faces + arrival flags into the neighbours' ghost slabs over NVLink
-      main stream : interior tiles (no dependence on the halo)  ->  boundary tiles (acquire the flags, finish the sites)
-    The pack stream forks from the main stream (so `in_` is complete) and joins it again afterwards (so nothing that
-    follows can overwrite `in_` while it is still being packed)."""
+      side stream : pack_kernel (faces + arrival flags into the neighbours' ghost slabs over NVLink)
+                    -> boundary tiles (acquire the neighbours' flags, then complete site updates)
+      main stream : interior tiles (no dependence on the halo), concurrently
+    The side stream forks from the main stream (so `in_` is complete) and joins it again afterwards (so `out` is
+    complete and nothing that follows can overwrite `in_` while it is still being packed)."""
     if in_.n_parity != 1:
         raise NotImplementedError("full-field halo exchange: pack each parity into its slot")
     side = ex.pack_stream(stream) if ex.mode == "p2p" else None
-    if side is not None:
-        import torch
-        main = torch.cuda.current_stream() if stream is None else torch.cuda.ExternalStream(stream)
-        side.wait_stream(main)
-        ex.start(in_, 1 - parity, dagger, stream=side.cuda_stream)
-    else:
+    if side is None:
         ex.start(in_, 1 - parity, dagger, stream=stream)
-    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(ex.halo()), stream=stream, tile=tile,
-             backend=ex.backend)
-    if side is not None:
-        main.wait_stream(side)
+        D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(ex.halo()), stream=stream, tile=tile,
+                 backend=ex.backend)
+        return
+    import torch
+    main = torch.cuda.current_stream() if stream is None else torch.cuda.ExternalStream(stream)
+    side.wait_stream(main)
+    ex.start(in_, 1 - parity, dagger, stream=side.cuda_stream)
+    halo = ex.halo()
+    # side stream: pack -> boundary tiles (wait for the neighbours' flags, complete updates); main stream: interior tiles
+    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(halo), stream=side.cuda_stream, tile=tile,
+             kernel=L.KERNEL_BOUNDARY_TILES, backend=ex.backend)
+    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(halo), stream=main.cuda_stream, tile=tile,
+             kernel=L.KERNEL_INTERIOR_TILES, backend=ex.backend)
+    main.wait_stream(side)

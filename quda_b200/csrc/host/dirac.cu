@@ -150,14 +150,24 @@ namespace b200
         exchange_start(in, 1 - parity, dagger, comm_override, comm, stream);
       }
       halo_fill(args.halo, comm_override, part ? comm : nullptr);
-      args.stream = stream;
-      abi_ok(b200_dslash_apply(&args));
-      if (part && comm->pack_stream && comm->pack_stream != stream) {
-        // join: nothing enqueued later may overwrite `in` while its faces are still being packed
+      const bool two_streams = part && comm->pack_stream && comm->pack_stream != stream;
+      if (two_streams) {
+        // side stream (behind the pack kernel): boundary tiles -- they depend only on the halo, not on the interior
+        // launch; main stream: the interior tiles.  Both halves write disjoint sites.
+        args.kernel = B200_KERNEL_BOUNDARY_TILES;
+        args.stream = comm->pack_stream;
+        abi_ok(b200_dslash_apply(&args));
+        args.kernel = B200_KERNEL_INTERIOR_TILES;
+        args.stream = stream;
+        abi_ok(b200_dslash_apply(&args));
+        // join: `out` is complete, and `in` may be overwritten, only after the side stream has drained
         static cudaEvent_t join_ev = nullptr;
         if (!join_ev) cuda_ok(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming), "event");
         cuda_ok(cudaEventRecord(join_ev, (cudaStream_t)comm->pack_stream), "record");
         cuda_ok(cudaStreamWaitEvent((cudaStream_t)stream, join_ev, 0), "wait");
+      } else {
+        args.stream = stream;
+        abi_ok(b200_dslash_apply(&args));
       }
     }
 

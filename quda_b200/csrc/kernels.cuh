@@ -279,25 +279,30 @@ namespace b200
     int threads, gx, gy, gz, rc;
     if (int e = make_tile_map(tm, threads, rq.tile, arg.geom, kMaxTile)) return e;
     const bool partitioned = arg.threads_ext[4] > 0;
-    if (rq.kernel == B200_KERNEL_AUTO && partitioned) {
+    const bool tiles_path
+      = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES;
+    if (tiles_path && !partitioned && rq.kernel == B200_KERNEL_BOUNDARY_TILES) return B200_SUCCESS;
+    if (tiles_path && partitioned) {
       // B200 schedule: tiles that touch no partitioned face run now (branch-free kernel, overlapping the halo that is
       // in flight over NVLink); the boundary tiles follow in ONE launch that acquires the arrival flags and updates
       // its sites completely -- no partial sums, no read-modify-write pass.
       SlabTable st;
       const int nb = split_boundary(tm, st, arg.comm_dim);
-      if (box_grid(tm, arg.n_parity, gx, gy, gz, rc)) {
-        dslash_interior_kernel<P, recon, dagger, xpay, op, false><<<dim3(gx, gy, gz), threads, 0, s>>>(arg, tm);
-        count_launch();
-      } else if (rc) {
-        return rc;
+      if (rq.kernel != B200_KERNEL_BOUNDARY_TILES) {
+        if (box_grid(tm, arg.n_parity, gx, gy, gz, rc)) {
+          dslash_interior_kernel<P, recon, dagger, xpay, op, false><<<dim3(gx, gy, gz), threads, 0, s>>>(arg, tm);
+          count_launch();
+        } else if (rc) {
+          return rc;
+        }
       }
-      if (nb > 0) {
+      if (nb > 0 && rq.kernel != B200_KERNEL_INTERIOR_TILES) {
         dslash_boundary_kernel<P, recon, dagger, xpay, op><<<dim3(nb, arg.n_parity, 1), threads, 0, s>>>(arg, tm, st);
         count_launch();
       }
       return check_cuda(cudaGetLastError(), "dslash launch");
     }
-    if (rq.kernel != B200_KERNEL_EXTERIOR) {
+    if (rq.kernel != B200_KERNEL_EXTERIOR) { // AUTO / INTERIOR_TILES on an unpartitioned lattice, or reference-style INTERIOR
       if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
       dim3 grid(gx, gy, gz);
       if (partitioned)
@@ -306,7 +311,7 @@ namespace b200
         dslash_interior_kernel<P, recon, dagger, xpay, op, false><<<grid, threads, 0, s>>>(arg, tm);
       count_launch();
     }
-    if (rq.kernel != B200_KERNEL_INTERIOR && partitioned) {
+    if (rq.kernel == B200_KERNEL_EXTERIOR && partitioned) {
       dim3 grid((arg.threads_ext[4] + 127) / 128, arg.n_parity, 1);
       dslash_exterior_kernel<P, recon, dagger, xpay, op><<<grid, 128, 0, s>>>(arg);
       count_launch();

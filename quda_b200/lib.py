@@ -12,7 +12,7 @@ ABI_VERSION = 1
 
 DOUBLE, SINGLE, HALF = 8, 4, 2
 OP_WILSON, OP_CLOVER, OP_CLOVER_PC = 0, 1, 2
-KERNEL_AUTO, KERNEL_INTERIOR, KERNEL_EXTERIOR = 0, 1, 2
+KERNEL_AUTO, KERNEL_INTERIOR, KERNEL_EXTERIOR, KERNEL_INTERIOR_TILES, KERNEL_BOUNDARY_TILES = 0, 1, 2, 3, 4
 
 
 class B200Error(RuntimeError):

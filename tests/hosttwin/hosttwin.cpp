@@ -45,13 +45,18 @@ namespace b200
               visited++;
             }
     };
-    if (rq.kernel == B200_KERNEL_AUTO && partitioned) {
+    const bool tiles_path
+      = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES;
+    if (tiles_path && partitioned) {
       SlabTable st;
       const int nb = split_boundary(tm, st, arg.comm_dim);
-      if (box_grid(tm, arg.n_parity, gx, gy, gz, rc))
-        walk_box([&](const int *x, int x_cb, int par) { dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par); });
-      else if (rc)
-        return rc;
+      if (rq.kernel != B200_KERNEL_BOUNDARY_TILES) {
+        if (box_grid(tm, arg.n_parity, gx, gy, gz, rc))
+          walk_box([&](const int *x, int x_cb, int par) { dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par); });
+        else if (rc)
+          return rc;
+      }
+      if (rq.kernel != B200_KERNEL_INTERIOR_TILES)
       for (int pp = 0; pp < arg.n_parity; pp++) {
         const int parity = arg.n_parity == 2 ? pp : arg.parity;
 #pragma omp parallel for reduction(+ : visited)
@@ -63,7 +68,7 @@ namespace b200
             visited++;
           }
       }
-      if (visited != (long)g.volume_cb * arg.n_parity)
+      if (rq.kernel == B200_KERNEL_AUTO && visited != (long)g.volume_cb * arg.n_parity)
         return set_error(B200_ERR_INVALID, "interior box + boundary slabs visited %ld of %ld sites", visited,
                          (long)g.volume_cb * arg.n_parity);
       return 0;
@@ -77,7 +82,7 @@ namespace b200
       if (visited != (long)g.volume_cb * arg.n_parity)
         return set_error(B200_ERR_INVALID, "tile map visited %ld of %ld sites", visited, (long)g.volume_cb * arg.n_parity);
     }
-    if (rq.kernel != B200_KERNEL_INTERIOR) {
+    if (rq.kernel == B200_KERNEL_EXTERIOR) {
       for (int pp = 0; pp < arg.n_parity; pp++) {
         const int parity = arg.n_parity == 2 ? pp : arg.parity;
 #pragma omp parallel for

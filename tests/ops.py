@@ -99,7 +99,12 @@ def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4
         out = P.empty()
         a = -kappa if xpay else 0.0
         xdev = P.to_dev(xs) if xpay else None
-        kws = [dict(tile=tile)] if not split else [dict(kernel=1, tile=tile), dict(kernel=2, tile=tile)]  # AUTO | INTERIOR, EXTERIOR
+        if split == "tiles":      # the two halves of AUTO issued separately (boundary first: they are independent)
+            kws = [dict(kernel=4, tile=tile), dict(kernel=3, tile=tile)]
+        elif split:               # reference-style: masked INTERIOR then EXTERIOR read-modify-write
+            kws = [dict(kernel=1, tile=tile), dict(kernel=2, tile=tile)]
+        else:
+            kws = [dict(tile=tile)]
         if op == "wilson":
             for kw in kws:
                 D.ApplyWilson(out, din, P.U, a, xdev, parity, dagger, halo=halo, backend=be, **kw)

@@ -57,3 +57,11 @@ def test_boundary_slab_schedule(op, tile, comm_dim):
     (including tilings with 1 or 2 tiles along a partitioned dimension)"""
     ops.check_partitioned(HostMem, twin_backend(), 8, 18, comm_dim, op=op, X=(8, 6, 4, 8), xpay=True, tile=tile,
                           clover_kw=dict(compressed=True, dynamic=True))
+
+
+@pytest.mark.parametrize("comm_dim", [(0, 0, 0, 1), (0, 1, 1, 1), (1, 1, 1, 1)])
+@pytest.mark.parametrize("op", ["wilson", "clover_pc"])
+def test_boundary_and_interior_tiles_are_independent(op, comm_dim):
+    """BOUNDARY_TILES and INTERIOR_TILES launches write disjoint sites, in any order (they run on different streams)"""
+    ops.check_partitioned(HostMem, twin_backend(), 4, 12, comm_dim, op=op, X=(8, 6, 4, 8), xpay=True, split="tiles",
+                          clover_kw=dict(compressed=True, dynamic=True))
