@@ -474,15 +474,25 @@ namespace b200
       return (real)1;
     }
 
-    // load link (dir, x_cb, parity) into row-major u[18] = U[row][col] (re, im)
-    B2_HD void load(real *u, int dir, int x_cb, int parity) const
+    // raw (still packed) link: M vectors straight from memory -- lets a kernel issue the loads of all its links first
+    // and unpack each one only when its hop is computed
+    struct Raw {
+      V w[M];
+    };
+
+    B2_HD void load_raw(Raw &r, int dir, int x_cb, int parity) const
     {
-      real t[recon];
       const V *base = reinterpret_cast<const V *>(g[parity]);
 #pragma unroll
+      for (int i = 0; i < M; i++) r.w[i] = ld<Cache::STREAM>(base + (size_t)(dir * M + i) * stride + x_cb);
+    }
+
+    B2_HD void unpack(real *u, const Raw &r, int dir, int x_cb) const
+    {
+      real t[recon];
+#pragma unroll
       for (int i = 0; i < M; i++) {
-        const V w = ld<Cache::STREAM>(base + (size_t)(dir * M + i) * stride + x_cb);
-        vec_to_real(t + i * N, w);
+        vec_to_real(t + i * N, r.w[i]);
         if constexpr (P::fixed) {
 #pragma unroll
           for (int j = 0; j < N; j++) t[i * N + j] *= kFixedInvMax;
@@ -509,6 +519,14 @@ namespace b200
       } else {
         unpack8(u, t, u0(dir, x_cb));
       }
+    }
+
+    // load link (dir, x_cb, parity) into row-major u[18] = U[row][col] (re, im)
+    B2_HD void load(real *u, int dir, int x_cb, int parity) const
+    {
+      Raw r;
+      load_raw(r, dir, x_cb, parity);
+      unpack(u, r, dir, x_cb);
     }
 
     // 8-parameter reconstruction (gauge_field_order.h:1303-1390); packed = [arg(U10)/pi, arg(-U20)/pi, U11, U12, U00]

@@ -133,21 +133,40 @@ namespace b200
   }
 
   // ---- one hop, source on this rank (periodic wrap inside the local lattice)
+  // checkerboard index of the neighbour of x in direction +-d (periodic wrap)
+  template <bool fwd> B2_HD int neighbor_cb(const int *x, const Geom &g, int d)
+  {
+    int y[4] = {x[0], x[1], x[2], x[3]};
+    if (fwd)
+      y[d] = (x[d] + 1 >= g.X[d]) ? 0 : x[d] + 1;
+    else
+      y[d] = (x[d] - 1 < 0) ? g.X[d] - 1 : x[d] - 1;
+    return cb_from_coords(y, g);
+  }
+
+  // Links whose packed form is small enough (<= 48 B: fp32 recon-12/8, every half format) are fetched for all 8 hops
+  // before the first hop is computed (<= 96 registers of raw vectors): one exposed DRAM round trip per site for the
+  // link stream instead of one per hop.  Wider links (fp64, fp32 recon-18) would not fit the register file.
+#ifndef B2_PRELOAD_LINKS
+#define B2_PRELOAD_LINKS 1
+#endif
+  template <class P, int recon> struct PreloadLinks {
+    static constexpr bool value = B2_PRELOAD_LINKS && (sizeof(typename GaugeView<P, recon>::Raw) <= 48);
+  };
+
   template <class P, int recon, bool dagger, bool fwd>
-  B2_HD void hop_local(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d)
+  B2_HD void hop_local(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d,
+                       const typename GaugeView<P, recon>::Raw *raw = nullptr)
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
     const SpinorView<P> &in = arg.in[1 - parity];
     constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
     real u[18], h[12];
-    int y[4] = {x[0], x[1], x[2], x[3]};
-    if (fwd)
-      y[d] = (x[d] + 1 >= g.X[d]) ? 0 : x[d] + 1;
-    else
-      y[d] = (x[d] - 1 < 0) ? g.X[d] - 1 : x[d] - 1;
-    const int n_cb = cb_from_coords(y, g);
-    if (fwd)
+    const int n_cb = neighbor_cb<fwd>(x, g, d);
+    if (raw)
+      arg.U.unpack(u, *raw, d, fwd ? x_cb : n_cb);
+    else if (fwd)
       arg.U.load(u, d, x_cb, parity);
     else
       arg.U.load(u, d, n_cb, 1 - parity);
@@ -197,6 +216,15 @@ namespace b200
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
+    constexpr bool preload = (kt == K_INTERIOR) && PreloadLinks<P, recon>::value;
+    typename GaugeView<P, recon>::Raw raw[preload ? 8 : 1];
+    if constexpr (preload) {
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        arg.U.load_raw(raw[2 * d], d, x_cb, parity);
+        arg.U.load_raw(raw[2 * d + 1], d, neighbor_cb<false>(x, g, d), 1 - parity);
+      }
+    }
 #pragma unroll
     for (int d = 0; d < 4; d++) {
       { // forward hop: U_d(x) P(d, dagger ? + : -) in(x + d)
@@ -204,7 +232,7 @@ namespace b200
         const bool ghost = (x[d] + 1 >= g.X[d]) && arg.comm_dim[d];
         real r[12];
         if constexpr (kt == K_INTERIOR) {
-          hop_local<P, recon, dagger, true>(r, arg, x, x_cb, parity, d);
+          hop_local<P, recon, dagger, true>(r, arg, x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr);
           if constexpr (part) {
             const real m = ghost ? (real)0 : (real)1;
 #pragma unroll
@@ -229,7 +257,7 @@ namespace b200
         const bool ghost = (x[d] - 1 < 0) && arg.comm_dim[d];
         real r[12];
         if constexpr (kt == K_INTERIOR) {
-          hop_local<P, recon, dagger, false>(r, arg, x, x_cb, parity, d);
+          hop_local<P, recon, dagger, false>(r, arg, x, x_cb, parity, d, preload ? &raw[2 * d + 1] : nullptr);
           if constexpr (part) {
             const real m = ghost ? (real)0 : (real)1;
 #pragma unroll
