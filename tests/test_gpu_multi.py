@@ -38,3 +38,9 @@ def test_two_gpus_match_global_oracle(grid_dims, Xl, prec, recon, mode):
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs >= 4 GPUs")
 def test_four_gpus_two_partitioned_dims():
     _run(4, (1, 1, 2, 2), (8, 8, 4, 4), 4, 12, "p2p")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 8, reason="needs 8 GPUs")
+def test_eight_gpus_three_partitioned_dims():
+    """the 8-GPU benchmark grid (1,2,2,2): y, z and t partitioned, every rank has 3 distinct NVLink peers"""
+    _run(8, (1, 2, 2, 2), (4, 4, 4, 4), 4, 12, "p2p")

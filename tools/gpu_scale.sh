@@ -4,7 +4,7 @@ N=${1:-8}
 mkdir -p gpurun_out
 T0=$(date +%s)
 nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
-echo "== pytest multi (2- and 4-GPU cases)"; timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "four or (p2p and 1-1-1-2)" 2>&1 | tail -5 | tee gpurun_out/pytest_multi_$N.txt
+echo "== pytest multi (2- and 4-GPU cases)"; timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "four or eight or (p2p and grid_dims0)" 2>&1 | tail -5 | tee gpurun_out/pytest_multi_$N.txt
 echo "[t=$(( $(date +%s)-T0 ))s]"
 for n in 1 2 4 8; do
   [ $n -gt $N ] && continue
