@@ -70,6 +70,40 @@ namespace b200
       return s;
     }
 
+    // Field temporaries (reference: getFieldTmp / lib/field_cache.cpp): operators need a scratch field per application;
+    // cudaMalloc per call would serialise the stream, so released temporaries are parked in a free list and reused.
+    namespace
+    {
+      struct TmpPool {
+        std::vector<ColorSpinorField> free_list;
+        ColorSpinorField get(const int *X, int precision, int n_parity)
+        {
+          for (size_t i = 0; i < free_list.size(); i++) {
+            auto &f = free_list[i];
+            if (f.precision == precision && f.n_parity == n_parity && f.X[0] == X[0] && f.X[1] == X[1] && f.X[2] == X[2]
+                && f.X[3] == X[3]) {
+              ColorSpinorField r = f;
+              free_list.erase(free_list.begin() + i);
+              return r;
+            }
+          }
+          return ColorSpinorField::create(X, precision, n_parity);
+        }
+        void put(const ColorSpinorField &f) { free_list.push_back(f); }
+      };
+      TmpPool &pool()
+      {
+        static TmpPool p;
+        return p;
+      }
+      struct FieldTmp {
+        ColorSpinorField f;
+        FieldTmp(const ColorSpinorField &like, int n_parity) : f(pool().get(like.X, like.precision, n_parity)) { }
+        ~FieldTmp() { pool().put(f); }
+        operator ColorSpinorField &() { return f; }
+      };
+    } // namespace
+
     // ------------------------------------------------------------------ Apply*
     static void halo_fill(b200_halo &h, const int *comm_override, const CommContext *comm)
     {
@@ -430,7 +464,7 @@ namespace b200
     }
     void DiracWilson::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
     {
-      auto tmp = ColorSpinorField::create(in.X, in.precision, in.n_parity);
+      FieldTmp tmp(in, in.n_parity);
       M(tmp, in);
       Mdag(out, tmp);
     }
@@ -448,14 +482,14 @@ namespace b200
     void DiracWilsonPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
     {
       const double kappa2 = -kappa * kappa;
-      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      FieldTmp tmp(in, 1);
       if (!symmetric) throw Error("MatPCType not valid for DiracWilsonPC");
       Dslash(tmp, in, other_parity);
       DslashXpay(out, tmp, this_parity, in, kappa2);
     }
     void DiracWilsonPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
     {
-      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      FieldTmp tmp(in, 1);
       M(tmp, in);
       Mdag(out, tmp);
     }
@@ -512,7 +546,7 @@ namespace b200
     void DiracClover::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
     {
       check_full_spinor(out, in);
-      auto tmp = ColorSpinorField::create(in.X, in.precision, 2);
+      FieldTmp tmp(in, 2);
       M(tmp, in);
       Mdag(out, tmp);
     }
@@ -542,7 +576,7 @@ namespace b200
     void DiracCloverPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
     {
       const double kappa2 = -kappa * kappa;
-      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      FieldTmp tmp(in, 1);
       if (!symmetric) {
         Dslash(tmp, in, other_parity);                                   // A^-1 D
         DiracClover::DslashXpay(out, tmp, this_parity, in, kappa2);      // A x - k^2 D
@@ -557,7 +591,7 @@ namespace b200
     }
     void DiracCloverPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
     {
-      auto tmp = ColorSpinorField::create(in.X, in.precision, 1);
+      FieldTmp tmp(in, 1);
       M(tmp, in);
       Mdag(out, tmp);
     }
@@ -571,7 +605,7 @@ namespace b200
       }
       src = x.parity_view(other_parity);
       sol = x.parity_view(this_parity);
-      auto tmp = ColorSpinorField::create(b.X, b.precision, 1);
+      FieldTmp tmp(b, 1);
       if (symmetric) { // src = A_ee^-1 (b_e + k D_eo A_oo^-1 b_o)
         CloverInv(src, b.parity_view(other_parity), other_parity);
         DiracWilson::DslashXpay(tmp, src, this_parity, b.parity_view(this_parity), kappa);
@@ -585,7 +619,7 @@ namespace b200
     {
       if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
       check_full_spinor(x, b);
-      auto tmp = ColorSpinorField::create(b.X, b.precision, 1);
+      FieldTmp tmp(b, 1);
       // x_o = A_oo^-1 (b_o + k D_oe x_e)
       DiracWilson::DslashXpay(tmp, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
       auto xo = x.parity_view(other_parity);

@@ -167,18 +167,16 @@ int b200_invert_cg(b200_dirac *precise, b200_dirac *sloppy, const b200_spinor *x
     if (!sloppy) sloppy = precise;
     pull_comm(precise);
     if (sloppy != precise) {
-      // both operators must walk the same sequence of halo exchanges: share one context
+      // a partitioned mixed-precision solve needs one halo context per precision (the ghost buffers differ in size);
+      // both advance in lock step on every rank because all ranks execute the same operator sequence
       if (precise->has_comm != sloppy->has_comm) throw Error("precise / sloppy operators disagree on partitioning");
+      pull_comm(sloppy);
     }
     auto xf = wrap(precise, x), bf = wrap(precise, b);
     SolverParam sp;
     sp.tol = param->tol;
     sp.maxiter = param->maxiter;
     sp.delta = param->delta > 0 ? param->delta : 0.1;
-    if (sloppy != precise && precise->has_comm) {
-      // route the sloppy operator's exchanges through the precise operator's context object
-      throw Error("mixed-precision partitioned solve: create both operators with the same b200_comm and precision-specific buffers (next round)");
-    }
     invertCG(*precise->op, *sloppy->op, xf, bf, sp);
     param->iter = sp.iter;
     param->reliable_updates = sp.reliable_updates;
@@ -186,6 +184,7 @@ int b200_invert_cg(b200_dirac *precise, b200_dirac *sloppy, const b200_spinor *x
     param->secs = sp.secs;
     param->gflops = sp.gflops;
     push_comm(precise);
+    if (sloppy != precise) push_comm(sloppy);
   });
 }
 }

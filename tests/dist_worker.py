@@ -60,3 +60,88 @@ def worker(rank, world, port, grid_dims, Xl, prec, recon, q, mode="host", reps=3
     q.put((rank, dev, timed_out))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def cg_worker(rank, world, port, grid_dims, Xl, q, mixed=True, kind="wilsonpc"):
+    """Distributed CG (normal equations on the even-odd preconditioned operator) through the C++ operator / solver layer:
+    every Dslash inside the solver exchanges its halo over NVLink, scalars go through an all-reduce.  The gathered
+    solution is verified on the host against the oracle's full operator on the GLOBAL lattice (invert_test's criterion)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import oracle
+    from common import CudaMem
+    from quda_b200 import comm, dirac as DR, dslash as D, fields as F
+    grid = comm.ProcessGrid(grid_dims, rank)
+    Xg = [Xl[d] * grid_dims[d] for d in range(4)]
+    kappa = 0.12195
+    gauge = oracle.random_gauge(Xg, 8, seed=137)
+    clover = oracle.random_clover(Xg, 8, seed=138) if "clover" in kind else None
+    b = oracle.random_spinor(Xg, 8, seed=77, nparity=2)
+    Vhl = F.volume_cb(Xl)
+
+    def local_gauge(prec):
+        gl = comm.local_slice(gauge, Xg, Xl, grid.coords, "gauge")
+        ghost_from = []
+        for d in range(4):
+            c = list(grid.coords)
+            c[d] = (c[d] - 1) % grid_dims[d]
+            ghost_from.append(comm.local_slice(gauge, Xg, Xl, c, "gauge") if grid_dims[d] > 1 else None)
+        gbuf, gmeta = F.gauge_to_native(gl, Xl, prec, 12, ghost_from=ghost_from)
+        return D.GaugeField(CudaMem.put(gbuf), Xl, prec, 12, gmeta, t_boundary=-1,
+                            first_time_slice=grid.first_time_slice(), last_time_slice=grid.last_time_slice())
+
+    def local_clover(prec):
+        if clover is None:
+            return None
+        cl = comm.local_slice(clover, Xg, Xl, grid.coords, "clover")
+        cbuf, cmeta = F.clover_to_native(cl, Xl, prec, compressed=True)
+        return D.CloverField(CudaMem.put(cbuf), Xl, prec, cmeta, dynamic=True)
+
+    ops, keep = {}, []
+    for prec in ((8, 4) if mixed else (8,)):
+        ex = comm.HaloExchange(grid, Xl, prec, mode="p2p", dist=dist)
+        cs = ex.comm_struct()
+        U, A = local_gauge(prec), local_clover(prec)
+        ops[prec] = DR.Dirac(kind, U, kappa, clover=A, comm=cs)
+        keep += [ex, cs, U, A]
+    pc = ops[8]
+    # local pieces of b: parity blocks [even | odd]
+    bl = np.concatenate([comm.local_slice(b[p * (len(b) // 2):(p + 1) * (len(b) // 2)], Xg, Xl, grid.coords, ("spinor1", p))
+                         for p in range(2)])
+    pb = F.spinor_bytes(Xl, 8)
+    bdev = D.ColorSpinorField(CudaMem.put(np.concatenate([F.spinor_to_native(bl[p * Vhl:(p + 1) * Vhl], 8) for p in range(2)])), Xl, 8, 2)
+    xdev = D.ColorSpinorField(CudaMem.empty(2 * pb), Xl, 8, 2)
+    src_p, sol_p = pc.prepare(xdev, bdev)
+    src = D.ColorSpinorField(xdev.buf[src_p * pb:(src_p + 1) * pb], Xl, 8)
+    sol = D.ColorSpinorField(xdev.buf[sol_p * pb:(sol_p + 1) * pb], Xl, 8)
+    rhs = D.ColorSpinorField(CudaMem.empty(pb), Xl, 8)
+    pc.Mdag(rhs, src)
+    sol.buf.zero_()
+    res = DR.invert_cg(pc, ops.get(4), sol, rhs, tol=1e-10, maxiter=3000)
+    pc.reconstruct(xdev, bdev)
+    torch.cuda.synchronize()
+    raw = CudaMem.get(xdev.buf)
+    xl = np.concatenate([F.spinor_from_native(raw[p * pb:(p + 1) * pb], Vhl, 8) for p in range(2)])
+    # gather the solution: every rank contributes its block to the global field
+    xg = np.zeros_like(b, dtype=np.float64)
+    Vhg = F.volume_cb(Xg)
+    blocks = [None] * world
+    dist.all_gather_object(blocks, (grid.coords, xl))
+    for coords, blk in blocks:
+        off = np.array([coords[d] * Xl[d] for d in range(4)])
+        for p in range(2):
+            idx = F.cb_index(F.cb_coords(Xl, p) + off, Xg)
+            xg[p * Vhg + idx] = blk[p * Vhl:(p + 1) * Vhl]
+    if clover is None:
+        Mx = oracle.wil_mat(gauge, xg, Xg, kappa, 0)
+    else:
+        Mx = oracle.clover_mat(gauge, clover, xg, Xg, kappa, 0)
+    true_res = float(np.linalg.norm(Mx.ravel() - b.ravel()) / np.linalg.norm(b.ravel()))
+    q.put((rank, res.iter, res.reliable_updates, res.true_res, true_res, any(e.timed_out() for e in keep if hasattr(e, "timed_out"))))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -44,3 +44,26 @@ def test_four_gpus_two_partitioned_dims():
 def test_eight_gpus_three_partitioned_dims():
     """the 8-GPU benchmark grid (1,2,2,2): y, z and t partitioned, every rank has 3 distinct NVLink peers"""
     _run(8, (1, 2, 2, 2), (4, 4, 4, 4), 4, 12, "p2p")
+
+
+@pytest.mark.parametrize("kind,mixed", [("wilsonpc", False), ("cloverpc", True)])
+def test_two_gpu_cg_host_verified(kind, mixed):
+    """config 5 in miniature: CG to 1e-10 on a lattice split over 2 GPUs (clover: double/single mixed precision with
+    reliable updates); the gathered solution must satisfy M x = b on the GLOBAL lattice according to the CPU oracle."""
+    from dist_worker import cg_worker
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=cg_worker, args=(r, 2, port, (1, 1, 1, 2), (8, 8, 8, 8), q, mixed, kind)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, iters, rel_updates, solver_res, true_res, timed_out in res:
+        assert not timed_out
+        assert iters < 3000 and solver_res < 5e-10, (iters, solver_res)
+        assert true_res < 1e-8, true_res
+        if mixed:
+            assert rel_updates >= 1
