@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--recon", type=int, default=12, choices=[18, 12, 8])
     ap.add_argument("--dim", type=int, nargs=4, default=[32, 32, 32, 32])
     ap.add_argument("--tile", type=int, nargs=4, default=None)
+    ap.add_argument("--op", default="wilson", choices=["wilson", "clover_pc"],
+                    help="clover_pc: ApplyWilsonCloverPreconditioned (BASELINE config 3), compressed clover, dynamic inverse")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -101,7 +103,9 @@ def cpu_reference(X, prec, budget_s=20.0, min_reps=2):
     s = oracle.random_spinor(X, hp, seed=137)
     Vh = oracle.volume(X) // 2
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host cores, so set it explicitly
+    # (before the OpenMP runtime of the oracle library is loaded)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     if oracle.have_ref():
         R = oracle.Reference(X)
         fn, kind = (lambda: R.wil_dslash(g, s, 0, 0)), "reference"
@@ -178,6 +182,8 @@ def run_b200(a):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
+        if not os.environ.get("NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (an empty value makes NCCL print its banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = L.load()
     X = a.dim
@@ -214,8 +220,16 @@ def run_b200(a):
         comm_cs = ex.comm_struct()
         dirac = DR.Dirac("wilson", P["U"], 0.0, comm=comm_cs, stream=stream)
 
+    clover_bytes = 0
+    if a.op == "clover_pc":
+        assert world == 1, "--op clover_pc is a single-GPU measurement"
+        P["A"] = make_device_clover(X, prec)
+        clover_bytes = 56 * prec
+
     def step(tile=None):
-        if ex is None:
+        if a.op == "clover_pc":
+            D.ApplyWilsonCloverPreconditioned(dst, src, P["U"], P["A"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
+        elif ex is None:
             D.ApplyWilson(dst, src, P["U"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
         elif dirac is not None:
             dirac.Dslash(dst, src, 0)
@@ -263,9 +277,9 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms = ms_total / a.steps
-    flops = D.flops_per_site() * Vh * world
+    flops = D.flops_per_site(L.OP_CLOVER_PC if a.op == "clover_pc" else L.OP_WILSON) * Vh * world
     gflops = flops / (ms * 1e-3) * 1e-9
-    bmin = D.min_bytes_per_site(prec, a.recon)
+    bmin = D.min_bytes_per_site(prec, a.recon, clover_bytes=clover_bytes)
     S = 24 * prec + (4 if prec == 2 else 0)
     bquda = 8 * a.recon * prec + 8 * S
     peak, peak_src = measured_peaks()
@@ -311,7 +325,10 @@ def run_b200(a):
             2 * ex.face_bytes[d] for d in range(4) if ex.comm_dim[d])), "timed_out": bool(ex.timed_out()) if halo_mode.startswith("p2p") else False}
         out["halo"]["gbs_per_gpu"] = out["halo"]["bytes_per_step_per_gpu"] / (ms * 1e-3) * 1e-9
 
-    if rank == 0 and not a.no_e2e:
+    if a.op != "wilson":
+        out["metric"] = "wilson_clover_pc_dslash_gflops"
+        out["config"]["workload"] = out["config"]["workload"].replace("Wilson Dslash", "Wilson-clover preconditioned Dslash (A^-1 D, compressed clover, per-site Cholesky)")
+    if rank == 0 and not a.no_e2e and a.op == "wilson":
         out["e2e"] = e2e(a, P, lib, Vh, prec, world)
     if rank == 0 and not a.no_cpu_baseline:
         try:
@@ -382,6 +399,23 @@ def make_device_problem(X, prec, recon, grid=None):
     inp = D.ColorSpinorField(torch.from_numpy(sbuf).cuda(), X, prec, 1)
     out = D.ColorSpinorField(torch.zeros(len(sbuf), dtype=torch.uint8, device="cuda"), X, prec, 1)
     return {"U": U, "in": inp, "out": out, "host_in": sbuf}
+
+
+def make_device_clover(X, prec):
+    """Synthetic clover term in the native compressed layout: 1 + small Hermitian noise with the symmetry the 28-real
+    format assumes (the construction of tests/utils/host_utils.cpp:1162-1188 with numpy's generator)."""
+    import numpy as np
+    import torch
+    from quda_b200 import dslash as D
+    from quda_b200 import fields as F
+    V = 2 * F.volume_cb(X)
+    rng = np.random.default_rng(5)
+    c = (rng.random((V, 2, 36)) * 0.02 - 0.01)
+    for dst, src in zip((3, 4, 5, 30, 31, 32, 33, 34, 35), (0, 1, 2, 6, 7, 8, 9, 16, 17)):
+        c[:, :, dst] = -c[:, :, src]
+    c[:, :, :6] += 1.0
+    buf, meta = F.clover_to_native(c, X, prec, compressed=True)
+    return D.CloverField(torch.from_numpy(buf).cuda(), X, prec, meta, dynamic=True)
 
 
 def e2e(a, P, lib, Vh, prec, world):

@@ -150,12 +150,29 @@ namespace b200
   template <> struct GaugeVec<PrecH16, 12> { using vec = s4; static constexpr int N = 4; };
   template <> struct GaugeVec<PrecH16, 8> { using vec = s8; static constexpr int N = 8; };
 
+#ifndef B2_I2F_NATIVE
+#define B2_I2F_NATIVE 0
+#endif
   // int16 pair -> two floats.  On the device this avoids the quarter-rate I2F conversion unit: PRMT sign-extends a half
   // word, adding it to the bit pattern of 1.5*2^23 puts the integer into the mantissa, one FADD removes the bias
   // (exact; the integer analogue of the reference's QUDA_ALTERNATIVE_I_TO_F path, convert.h:66-78).
   B2_HD void s16x2_to_f32(unsigned w, float &lo, float &hi)
   {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && (B2_I2F_NATIVE == 2)
+    // both halves through the conversion unit (I2F.S16 reads either half of a register directly: one issue slot each)
+    short s0, s1;
+    asm("mov.b32 {%0, %1}, %2;" : "=h"(s0), "=h"(s1) : "r"(w));
+    lo = (float)s0;
+    hi = (float)s1;
+#elif defined(__CUDA_ARCH__) && (B2_I2F_NATIVE == 1)
+    // split the work between the conversion unit (low half) and the integer/FP32 pipes (high half)
+    short s0, s1;
+    asm("mov.b32 {%0, %1}, %2;" : "=h"(s0), "=h"(s1) : "r"(w));
+    lo = (float)s0;
+    unsigned b;
+    asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(b) : "r"(w));
+    hi = __int_as_float((int)(b + 0x4B400000u)) - 12582912.0f;
+#elif defined(__CUDA_ARCH__)
     unsigned a, b;
     asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(a) : "r"(w));
     asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(b) : "r"(w));
