@@ -96,16 +96,21 @@ class ClockSampler:
 def cpu_reference(X, prec, budget_s=20.0, min_reps=2):
     """Time the reference's own host Dslash (oracle/_ref, kind 'reference'; our restatement 'port' otherwise)
     on all host cores.  Returns (gflops, info dict)."""
+    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host cores: set the variable
+    # before the OpenMP runtime is loaded and, in case it already is, tell the runtime directly
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import ctypes
     import numpy as np
     import oracle
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     hp = 8 if prec == "double" else 4
     g = oracle.random_gauge(X, hp, seed=137)
     s = oracle.random_spinor(X, hp, seed=137)
     Vh = oracle.volume(X) // 2
-    cores = os.cpu_count() or 1
-    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host cores, so set it explicitly
-    # (before the OpenMP runtime of the oracle library is loaded)
-    os.environ["OMP_NUM_THREADS"] = str(cores)
     if oracle.have_ref():
         R = oracle.Reference(X)
         fn, kind = (lambda: R.wil_dslash(g, s, 0, 0)), "reference"

@@ -151,11 +151,13 @@ namespace b200
   template <> struct GaugeVec<PrecH16, 8> { using vec = s8; static constexpr int N = 8; };
 
 #ifndef B2_I2F_NATIVE
-#define B2_I2F_NATIVE 0
+#define B2_I2F_NATIVE 1
 #endif
-  // int16 pair -> two floats.  On the device this avoids the quarter-rate I2F conversion unit: PRMT sign-extends a half
-  // word, adding it to the bit pattern of 1.5*2^23 puts the integer into the mantissa, one FADD removes the bias
-  // (exact; the integer analogue of the reference's QUDA_ALTERNATIVE_I_TO_F path, convert.h:66-78).
+  // int16 pair -> two floats.  The half-precision kernels are issue-bound, so the conversions are split between two
+  // pipes (B2_I2F_NATIVE == 1, measured best on B200: half recon-12 49.6 us vs 55.7 all-magic vs 51.5 all-native): the low
+  // half goes through the conversion unit (I2F.S16, one issue slot, slow pipe), the high half through the integer/FP32
+  // pipes -- PRMT sign-extends it, adding it to the bit pattern of 1.5*2^23 puts the integer into the mantissa and one
+  // FADD removes the bias (exact; the integer analogue of the reference's QUDA_ALTERNATIVE_I_TO_F path, convert.h:66-78).
   B2_HD void s16x2_to_f32(unsigned w, float &lo, float &hi)
   {
 #if defined(__CUDA_ARCH__) && (B2_I2F_NATIVE == 2)
