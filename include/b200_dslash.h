@@ -165,6 +165,23 @@ size_t b200_ghost_face_bytes(int precision, const int X[4], int dim);
 int b200_copy_spinor(const b200_spinor *native, int native_precision, void *host_order, int host_precision, int to_native,
                      void *stream);
 
+/* Device-side gauge marshaling (the Wilson slice of lib/copy_gauge*.cu + lib/extract_gauge_ghost*.cu as used by
+ * loadGaugeQuda, lib/interface_quda.cpp:571-764): host interface order QUDA_QDP_GAUGE_ORDER
+ * (qdp[mu][(parity*volume_cb + x_cb)][3][3][2], fp64 or fp32, already resident on the device) -> native FloatN order
+ * at `native_precision` with 18/12/8-parameter packing, and the pad of every direction filled with the backward
+ * neighbour's boundary links.  ghost_links[mu] (may be NULL = this rank is its own neighbour in mu, i.e. periodic
+ * wrap) points to those links in face order: [parity][face_cb][3][3][2] at host precision.
+ * `native` must describe a buffer of 2 * parity_stride_bytes with stride = volume_cb + pad. */
+int b200_copy_gauge(const b200_gauge *native, int native_precision, const int X[4], void *const qdp[4],
+                    void *const ghost_links[4], int host_precision, void *stream);
+
+/* Device-side clover marshaling (lib/copy_clover.cu): host packed order [site (parity-major)][2 chiral blocks][36]
+ * (6 real diagonals + 15 complex strictly-lower entries, fp64 / fp32, on the device) -> native order holding A/2,
+ * optionally compressed to 28 reals per block (native->compressed, native->diagonal) and, for half precision, scaled
+ * by native->max_element. */
+int b200_copy_clover(const b200_clover *native, int native_precision, const int X[4], const void *packed, int host_precision,
+                     void *stream);
+
 /* Halo buffers that peer GPUs must be able to map: plain cudaMalloc allocations (zero-filled) plus CUDA-IPC
  * export / import.  Replaces the reference's static ghost buffers + IPC handle exchange
  * (lib/lattice_field.cpp:252-470, lib/targets/cuda/comm_target.cpp:37-167); the 64-byte handles travel between

@@ -122,6 +122,57 @@ int b200_copy_spinor(const b200_spinor *native, int native_precision, void *host
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", native_precision);
 }
 
+int b200_copy_gauge(const b200_gauge *native, int native_precision, const int X[4], void *const qdp[4],
+                    void *const ghost_links[4], int host_precision, void *stream)
+{
+  if (!native || !native->gauge || !X || !qdp) return set_error(B200_ERR_INVALID, "b200_copy_gauge: null argument");
+  if (int rc = require_device()) return rc;
+  if (host_precision != B200_DOUBLE && host_precision != B200_SINGLE)
+    return set_error(B200_ERR_INVALID, "host gauge precision must be 8 or 4 (got %d)", host_precision);
+  GaugeCopyRequest rq;
+  rq.native = *native;
+  for (int d = 0; d < 4; d++) {
+    if (X[d] < 2 || (X[d] & 1)) return set_error(B200_ERR_INVALID, "X[%d]=%d must be even and >= 2", d, X[d]);
+    rq.X[d] = X[d];
+    if (!qdp[d]) return set_error(B200_ERR_INVALID, "qdp[%d] is NULL", d);
+    rq.qdp[d] = qdp[d];
+    rq.ghost[d] = ghost_links ? ghost_links[d] : nullptr;
+  }
+  if (native_precision == B200_HALF && native->reconstruct == 18 && !(native->link_max > 0.0))
+    return set_error(B200_ERR_INVALID, "half recon-18 needs link_max > 0");
+  rq.host_precision = host_precision;
+  rq.stream = stream;
+  switch (native_precision) {
+  case B200_DOUBLE: return launch_gauge_copy_precision<PrecF64>(rq);
+  case B200_SINGLE: return launch_gauge_copy_precision<PrecF32>(rq);
+  case B200_HALF: return launch_gauge_copy_precision<PrecH16>(rq);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", native_precision);
+}
+
+int b200_copy_clover(const b200_clover *native, int native_precision, const int X[4], const void *packed, int host_precision,
+                     void *stream)
+{
+  if (!native || !native->clover || !X || !packed) return set_error(B200_ERR_INVALID, "b200_copy_clover: null argument");
+  if (int rc = require_device()) return rc;
+  if (host_precision != B200_DOUBLE && host_precision != B200_SINGLE)
+    return set_error(B200_ERR_INVALID, "host clover precision must be 8 or 4 (got %d)", host_precision);
+  if (native_precision == B200_HALF && !(native->max_element > 0.0))
+    return set_error(B200_ERR_INVALID, "half precision clover needs max_element > 0");
+  CloverCopyRequest rq;
+  rq.native = *native;
+  for (int d = 0; d < 4; d++) rq.X[d] = X[d];
+  rq.packed = packed;
+  rq.host_precision = host_precision;
+  rq.stream = stream;
+  switch (native_precision) {
+  case B200_DOUBLE: return launch_clover_copy_precision<PrecF64>(rq);
+  case B200_SINGLE: return launch_clover_copy_precision<PrecF32>(rq);
+  case B200_HALF: return launch_clover_copy_precision<PrecH16>(rq);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", native_precision);
+}
+
 int b200_comm_alloc(void **ptr, size_t bytes)
 {
   if (!ptr || bytes == 0) return set_error(B200_ERR_INVALID, "b200_comm_alloc: null pointer or zero size");

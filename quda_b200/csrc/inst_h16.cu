@@ -7,4 +7,6 @@ namespace b200
   template int launch_clover_precision<PrecH16>(const CloverRequest &);
   template int launch_pack_precision<PrecH16>(const PackRequest &);
   template int launch_copy_precision<PrecH16>(const CopyRequest &);
+  template int launch_gauge_copy_precision<PrecH16>(const GaugeCopyRequest &);
+  template int launch_clover_copy_precision<PrecH16>(const CloverCopyRequest &);
 } // namespace b200

@@ -270,6 +270,159 @@ namespace b200
     return check_cuda(cudaGetLastError(), "copy_spinor launch");
   }
 
+  // ---- gauge: QDP host order -> native packed order incl. the ghost links in the pad (loadGaugeQuda's device work)
+  template <class P, int recon, typename H> struct GaugeCopyArgs {
+    Geom geom;
+    typename P::store *g[2];
+    int stride;
+    const H *qdp[4];
+    const H *ghost[4];
+    typename P::real link_max_inv;
+  };
+
+  template <class P, int recon, typename H>
+  __global__ void __launch_bounds__(128) copy_gauge_kernel(const __grid_constant__ GaugeCopyArgs<P, recon, H> arg)
+  {
+    using real = typename P::real;
+    using store = typename P::store;
+    constexpr int N = GaugeVec<P, recon>::N;
+    const Geom &g = arg.geom;
+    const int mu = blockIdx.y >> 1, parity = blockIdx.y & 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.volume_cb + g.face_cb[mu]) return;
+    const H *src;
+    if (idx < g.volume_cb) {
+      src = arg.qdp[mu] + ((size_t)parity * g.volume_cb + idx) * 18;
+    } else {
+      const int f = idx - g.volume_cb;
+      if (arg.ghost[mu]) {
+        src = arg.ghost[mu] + ((size_t)parity * g.face_cb[mu] + f) * 18;
+      } else { // this rank is its own backward neighbour: links of the x[mu] = X[mu]-1 slice, in face order
+        int x[4];
+        coords_from_face(x, g, mu, g.X[mu] - 1, f, parity);
+        src = arg.qdp[mu] + ((size_t)parity * g.volume_cb + cb_from_coords(x, g)) * 18;
+      }
+    }
+    double u[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) u[i] = (double)src[i];
+    real t[recon];
+    if constexpr (recon == 18) {
+#pragma unroll
+      for (int i = 0; i < 18; i++) t[i] = (real)(P::fixed ? u[i] * (double)arg.link_max_inv : u[i]);
+    } else if constexpr (recon == 12) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) t[i] = (real)u[i];
+    } else { // gauge_field_order.h:1303-1316
+      constexpr double inv_pi = 0.31830988618379067154;
+      t[0] = (real)(atan2(u[7], u[6]) * inv_pi);
+      t[1] = (real)(atan2(-u[13], -u[12]) * inv_pi);
+      t[2] = (real)u[8];
+      t[3] = (real)u[9];
+      t[4] = (real)u[10];
+      t[5] = (real)u[11];
+      t[6] = (real)u[0];
+      t[7] = (real)u[1];
+    }
+#pragma unroll
+    for (int i = 0; i < recon; i++) {
+      store v;
+      if constexpr (P::fixed)
+        v = f2s((float)t[i] * kFixedMax);
+      else
+        v = t[i];
+      arg.g[parity][((size_t)(mu * (recon / N) + i / N) * arg.stride + idx) * N + i % N] = v;
+    }
+  }
+
+  template <class P, int recon, typename H> int launch_gauge_copy_typed(const GaugeCopyRequest &rq)
+  {
+    GaugeCopyArgs<P, recon, H> a;
+    geom_init(a.geom, rq.X);
+    a.g[0] = reinterpret_cast<typename P::store *>(const_cast<void *>(rq.native.gauge));
+    a.g[1] = reinterpret_cast<typename P::store *>(reinterpret_cast<char *>(const_cast<void *>(rq.native.gauge)) + rq.native.parity_stride_bytes);
+    a.stride = rq.native.stride;
+    a.link_max_inv = (typename P::real)(1.0 / rq.native.link_max);
+    int max_face = 0;
+    for (int d = 0; d < 4; d++) {
+      a.qdp[d] = reinterpret_cast<const H *>(rq.qdp[d]);
+      a.ghost[d] = reinterpret_cast<const H *>(rq.ghost[d]);
+      if (a.geom.face_cb[d] > max_face) max_face = a.geom.face_cb[d];
+    }
+    if (a.stride < a.geom.volume_cb + max_face) return set_error(B200_ERR_INVALID, "gauge stride %d leaves no room for the ghost pad", a.stride);
+    dim3 grid((a.geom.volume_cb + max_face + 127) / 128, 8, 1);
+    copy_gauge_kernel<P, recon, H><<<grid, 128, 0, (cudaStream_t)rq.stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "copy_gauge launch");
+  }
+
+  template <class P> int launch_gauge_copy_precision(const GaugeCopyRequest &rq)
+  {
+    const bool dbl = rq.host_precision == 8;
+    switch (rq.native.reconstruct) {
+    case 18: return dbl ? launch_gauge_copy_typed<P, 18, double>(rq) : launch_gauge_copy_typed<P, 18, float>(rq);
+    case 12: return dbl ? launch_gauge_copy_typed<P, 12, double>(rq) : launch_gauge_copy_typed<P, 12, float>(rq);
+    case 8: return dbl ? launch_gauge_copy_typed<P, 8, double>(rq) : launch_gauge_copy_typed<P, 8, float>(rq);
+    }
+    return set_error(B200_ERR_INVALID, "reconstruct %d not in {18,12,8}", rq.native.reconstruct);
+  }
+
+  // ---- clover: packed host order -> native (A/2, optional 28-real compression, block-float scale)
+  template <class P, typename H>
+  __global__ void __launch_bounds__(128) copy_clover_kernel(typename P::store *c0, typename P::store *c1, const H *packed,
+                                                            int volume_cb, int compressed, double diagonal, double nrm_inv)
+  {
+    using store = typename P::store;
+    constexpr int N = P::Ns;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= volume_cb) return;
+    const int parity = blockIdx.y;
+    store *dst = parity ? c1 : c0;
+    const H *src = packed + ((size_t)parity * volume_cb + x) * 72;
+    const int CB = compressed ? 28 : 36;
+#pragma unroll
+    for (int chi = 0; chi < 2; chi++) {
+      double a[36];
+#pragma unroll
+      for (int i = 0; i < 36; i++) a[i] = 0.5 * (double)src[chi * 36 + i];
+      for (int k = 0; k < CB; k++) {
+        double v;
+        if (!compressed)
+          v = a[k];
+        else if (k < 3)
+          v = a[k] - diagonal;
+        else if (k == 3)
+          v = 0.0;
+        else
+          v = a[k + 2];
+        const int flat = chi * CB + k;
+        store o;
+        if constexpr (P::fixed)
+          o = f2s((float)(v * nrm_inv));
+        else
+          o = (store)v;
+        dst[((size_t)(flat / N) * volume_cb + x) * N + flat % N] = o;
+      }
+    }
+  }
+
+  template <class P> int launch_clover_copy_precision(const CloverCopyRequest &rq)
+  {
+    Geom g;
+    geom_init(g, rq.X);
+    auto *c0 = reinterpret_cast<typename P::store *>(const_cast<void *>(rq.native.clover));
+    auto *c1 = reinterpret_cast<typename P::store *>(reinterpret_cast<char *>(const_cast<void *>(rq.native.clover)) + rq.native.parity_stride_bytes);
+    const double nrm_inv = P::fixed ? (2.0 * 32767.0) / rq.native.max_element : 1.0;
+    dim3 grid((g.volume_cb + 127) / 128, 2, 1);
+    cudaStream_t s = (cudaStream_t)rq.stream;
+    if (rq.host_precision == 8)
+      copy_clover_kernel<P, double><<<grid, 128, 0, s>>>(c0, c1, (const double *)rq.packed, g.volume_cb, rq.native.compressed, rq.native.diagonal, nrm_inv);
+    else
+      copy_clover_kernel<P, float><<<grid, 128, 0, s>>>(c0, c1, (const float *)rq.packed, g.volume_cb, rq.native.compressed, rq.native.diagonal, nrm_inv);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "copy_clover launch");
+  }
+
   // ------------------------------------------------------------------ host-side dispatch for one precision
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   int launch_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)

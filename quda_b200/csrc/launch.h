@@ -39,6 +39,22 @@ namespace b200
     void *stream;
   };
 
+  struct GaugeCopyRequest {
+    b200_gauge native;
+    int X[4];
+    void *qdp[4], *ghost[4];
+    int host_precision;
+    void *stream;
+  };
+
+  struct CloverCopyRequest {
+    b200_clover native;
+    int X[4];
+    const void *packed;
+    int host_precision;
+    void *stream;
+  };
+
   struct PackRequest {
     int X[4], parity, dagger, comm_dim[4];
     void *in, *in_norm;
@@ -300,5 +316,7 @@ namespace b200
   template <class P> int launch_clover_precision(const CloverRequest &rq);
   template <class P> int launch_pack_precision(const PackRequest &rq);
   template <class P> int launch_copy_precision(const CopyRequest &rq);
+  template <class P> int launch_gauge_copy_precision(const GaugeCopyRequest &rq);
+  template <class P> int launch_clover_copy_precision(const CloverCopyRequest &rq);
 
 } // namespace b200

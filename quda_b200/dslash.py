@@ -170,6 +170,67 @@ def copy_spinor(native, host_order, to_native, stream=None):
     L.check(lib.b200_copy_spinor(C.byref(d), native.prec, host_order.data_ptr(), hp, int(bool(to_native)), stream))
 
 
+def load_gauge(host_gauge, X, prec, recon, anisotropy=1.0, t_boundary=1, ghost_links=None, first_time_slice=True,
+               last_time_slice=True, stream=None):
+    """loadGaugeQuda's device work: host QDP-order gauge (numpy [4][V][3][3][2], fp64/fp32) -> resident native GaugeField
+    at (`prec`, `recon`) with the pad filled (ghost_links[mu]: neighbour's boundary links, None = periodic self).
+    Reference: lib/interface_quda.cpp:571-764, lib/copy_gauge*.cu, lib/extract_gauge_ghost*."""
+    import torch
+    lib = L.load()
+    Vh = F.volume_cb(X)
+    pad = F.gauge_pad(X)
+    stride = Vh + pad
+    h = torch.from_numpy(np.ascontiguousarray(host_gauge)).cuda()
+    link_max = float(np.abs(host_gauge).max())
+    nbytes = 2 * 4 * recon * stride * prec
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    meta = dict(stride=stride, parity_stride_bytes=nbytes // 2, link_max=link_max, pad=pad)
+    U = GaugeField(buf, X, prec, recon, meta, anisotropy=anisotropy, t_boundary=t_boundary,
+                   first_time_slice=first_time_slice, last_time_slice=last_time_slice)
+    d = U.desc()
+    Xc = (C.c_int * 4)(*[int(v) for v in X])
+    qdp = (C.c_void_p * 4)(*[h[mu].data_ptr() for mu in range(4)])
+    keep = []
+    gl = (C.c_void_p * 4)()
+    for mu in range(4):
+        if ghost_links is not None and ghost_links[mu] is not None:
+            t = torch.from_numpy(np.ascontiguousarray(ghost_links[mu]).astype(host_gauge.dtype)).cuda()
+            keep.append(t)
+            gl[mu] = t.data_ptr()
+        else:
+            gl[mu] = None
+    L.check(lib.b200_copy_gauge(C.byref(d), prec, Xc, qdp, gl, host_gauge.dtype.itemsize, stream))
+    torch.cuda.synchronize()
+    return U
+
+
+def load_clover(host_clover, X, prec, compressed=True, dynamic=True, stream=None):
+    """loadCloverQuda's device work: packed host clover (numpy [V][2][36]) -> resident native CloverField.
+    Reference: lib/interface_quda.cpp:804-923, lib/copy_clover.cu."""
+    import torch
+    lib = L.load()
+    Vh = F.volume_cb(X)
+    c = np.asarray(host_clover).reshape(-1, 36)
+    diagonal = float(np.mean(0.25 * (c[:, 0:3] + c[:, 3:6]))) if compressed else 0.0
+    CB = 28 if compressed else 36
+    # max |stored value| x 2 (CloverField::max_element convention, clover_field_order.h:621-624)
+    half = 0.5 * c.astype(np.float64)
+    if compressed:
+        mx = max(np.abs(half[:, 0:3] - diagonal).max(), np.abs(half[:, 6:30]).max())
+    else:
+        mx = np.abs(half).max()
+    nbytes = 2 * 2 * CB * Vh * prec
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    meta = dict(parity_stride_bytes=nbytes // 2, diagonal=diagonal, max_element=2.0 * float(mx), compressed=int(compressed))
+    A = CloverField(buf, X, prec, meta, dynamic=dynamic)
+    d = A.desc()
+    h = torch.from_numpy(np.ascontiguousarray(host_clover)).cuda()
+    Xc = (C.c_int * 4)(*[int(v) for v in X])
+    L.check(lib.b200_copy_clover(C.byref(d), prec, Xc, h.data_ptr(), host_clover.dtype.itemsize, stream))
+    torch.cuda.synchronize()
+    return A
+
+
 def flops_per_site(op=L.OP_WILSON, xpay=False):
     """Reference flop model: include/dslash.h:475-528, lib/dslash_wilson_clover_preconditioned.hpp:52-57."""
     f = 1320 + (48 if xpay else 0)

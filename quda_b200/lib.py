@@ -105,6 +105,11 @@ def load():
         lib.b200_ghost_face_bytes.restype = C.c_size_t
         lib.b200_copy_spinor.argtypes = [C.POINTER(Spinor), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.b200_copy_spinor.restype = C.c_int
+        lib.b200_copy_gauge.argtypes = [C.POINTER(Gauge), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        lib.b200_copy_gauge.restype = C.c_int
+        lib.b200_copy_clover.argtypes = [C.POINTER(Clover), C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_void_p]
+        lib.b200_copy_clover.restype = C.c_int
         lib.b200_comm_alloc.argtypes, lib.b200_comm_alloc.restype = [C.POINTER(C.c_void_p), C.c_size_t], C.c_int
         lib.b200_comm_free.argtypes, lib.b200_comm_free.restype = [C.c_void_p], C.c_int
         lib.b200_ipc_get_handle.argtypes, lib.b200_ipc_get_handle.restype = [C.c_void_p, C.c_char_p], C.c_int
@@ -141,7 +146,7 @@ def check(rc, lib=None, prefix="b200"):
 
 
 EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
-                    "b200_copy_spinor", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
+                    "b200_copy_spinor", "b200_copy_gauge", "b200_copy_clover", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
                     "b200_dirac_create", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",
                     "b200_dirac_reconstruct", "b200_invert_cg",

@@ -101,3 +101,53 @@ def test_device_side_spinor_marshaling(prec, host_dtype):
     D.copy_spinor(P.to_dev(s), back, False)
     torch.cuda.synchronize()
     assert_close(s, back.cpu().numpy(), prec, 18, "from native")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("recon", RECONS)
+def test_device_side_gauge_marshaling(prec, recon):
+    """b200_copy_gauge (QDP host order -> native packed order + ghost pad, on the device) against the numpy marshaling"""
+    from quda_b200 import fields as F
+    X = (4, 6, 4, 8)
+    hp = 8 if prec == 8 else 4
+    g = oracle.random_gauge(X, hp, seed=21, anisotropy=1.4)
+    want, meta = F.gauge_to_native(g, X, prec, recon)
+    U = D.load_gauge(g, X, prec, recon, anisotropy=1.4, t_boundary=-1)
+    got = U.buf.cpu().numpy()
+    assert U.meta["stride"] == meta["stride"] and U.meta["parity_stride_bytes"] == meta["parity_stride_bytes"]
+    if prec == 2:
+        d = np.abs(got.view(np.int16).astype(int) - want.view(np.int16).astype(int))
+        assert d.max() <= 1
+    else:
+        a, b = got.view(F.real_dtype(prec)), want.view(F.real_dtype(prec))
+        assert np.allclose(a, b, rtol=0, atol=1e-14 if prec == 8 else 2e-7)
+    # and the loaded field drives the operator
+    P = Problem(X, prec, recon, CudaMem, seed=21, anisotropy=1.4)
+    s = P.spinor(seed=2)
+    out = P.empty()
+    D.ApplyWilson(out, P.to_dev(s), U, 0.0, None, 0, 0)
+    assert_close(oracle.wil_dslash(P.gauge, s, X, 0, 0), P.to_host(out), prec, recon, "dslash on device-marshaled gauge")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("compressed", [True, False])
+def test_device_side_clover_marshaling(prec, compressed):
+    from quda_b200 import fields as F
+    X = (4, 4, 6, 4)
+    hp = 8 if prec == 8 else 4
+    c = oracle.random_clover(X, hp, seed=33)
+    want, meta = F.clover_to_native(c, X, prec, compressed=compressed)
+    A = D.load_clover(c, X, prec, compressed=compressed)
+    got = A.buf.cpu().numpy()
+    assert A.meta["parity_stride_bytes"] == meta["parity_stride_bytes"]
+    assert abs(A.meta["diagonal"] - meta["diagonal"]) < 1e-6 and abs(A.meta["max_element"] - meta["max_element"]) < 1e-6 * meta["max_element"]
+    if prec == 2:
+        d = np.abs(got.view(np.int16).astype(int) - want.view(np.int16).astype(int))
+        assert d.max() <= 1
+    else:
+        assert np.allclose(got.view(F.real_dtype(prec)), want.view(F.real_dtype(prec)), rtol=0, atol=1e-14 if prec == 8 else 2e-7)
+    P = Problem(X, prec, 12, CudaMem, clover=True, compressed=compressed, dynamic=True)
+    s = P.spinor(seed=2)
+    out = P.empty()
+    D.ApplyClover(out, P.to_dev(s), A, False, 1)
+    assert_close(oracle.apply_clover(c, s.astype(c.dtype), X, 1), P.to_host(out), prec, 12, "A x on device-marshaled clover")
