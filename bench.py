@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--tile", type=int, nargs=4, default=None)
     ap.add_argument("--op", default="wilson", choices=["wilson", "clover_pc"],
                     help="clover_pc: ApplyWilsonCloverPreconditioned (BASELINE config 3), compressed clover, dynamic inverse")
+    ap.add_argument("--nsrc", type=int, default=1, help="sources per call (multi-RHS batch sharing the gauge field); 1 GPU")
+    ap.add_argument("--no-mrhs", action="store_true", help="skip the extra multi-RHS measurement of the default line")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -231,8 +233,18 @@ def run_b200(a):
         P["A"] = make_device_clover(X, prec)
         clover_bytes = 56 * prec
 
+    nsrc = max(1, a.nsrc)
+    if nsrc > 1:
+        assert world == 1, "--nsrc is a single-GPU measurement"
+        srcs = [src] + [new_spinor(P, seed=77 + i) for i in range(nsrc - 1)]
+        dsts = [dst] + [new_spinor(P, seed=None) for i in range(nsrc - 1)]
+
     def step(tile=None):
-        if a.op == "clover_pc":
+        if nsrc > 1:
+            fn = D.ApplyWilsonCloverPreconditioned if a.op == "clover_pc" else D.ApplyWilson
+            extra = (P["A"],) if a.op == "clover_pc" else ()
+            fn(dsts, srcs, P["U"], *extra, 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
+        elif a.op == "clover_pc":
             D.ApplyWilsonCloverPreconditioned(dst, src, P["U"], P["A"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
         elif ex is None:
             D.ApplyWilson(dst, src, P["U"], 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
@@ -282,9 +294,14 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms = ms_total / a.steps
-    flops = D.flops_per_site(L.OP_CLOVER_PC if a.op == "clover_pc" else L.OP_WILSON) * Vh * world
+    flops = D.flops_per_site(L.OP_CLOVER_PC if a.op == "clover_pc" else L.OP_WILSON) * Vh * world * nsrc
     gflops = flops / (ms * 1e-3) * 1e-9
     bmin = D.min_bytes_per_site(prec, a.recon, clover_bytes=clover_bytes)
+    if nsrc > 1:  # per launch: links once per in-thread batch (4, fp64: 2), spinors per source
+        S1 = 24 * prec + (4 if prec == 2 else 0)
+        per = 2 if prec == 8 else 4
+        nb = sum(1 for _ in mrhs_batches(nsrc, per))
+        bmin = nb * (8 * a.recon * prec + clover_bytes) + nsrc * 2 * S1
     S = 24 * prec + (4 if prec == 2 else 0)
     bquda = 8 * a.recon * prec + 8 * S
     peak, peak_src = measured_peaks()
@@ -330,6 +347,16 @@ def run_b200(a):
             2 * ex.face_bytes[d] for d in range(4) if ex.comm_dim[d])), "timed_out": bool(ex.timed_out()) if halo_mode.startswith("p2p") else False}
         out["halo"]["gbs_per_gpu"] = out["halo"]["bytes_per_step_per_gpu"] / (ms * 1e-3) * 1e-9
 
+    if nsrc > 1:
+        out["config"]["workload"] += f", {nsrc} sources per call (multi-RHS)"
+        out["roofline"]["kernel"] = "dslash_mrhs_kernel"
+        out["roofline"]["traffic"] = None
+        out["ms_per_rhs"] = ms / nsrc
+    elif world == 1 and a.op == "wilson" and not a.no_mrhs:
+        try:
+            out["multi_rhs"] = multi_rhs_line(a, P, D, L, stream, prec, Vh, peak)
+        except Exception as e:  # noqa: BLE001  -- the single-source line above stands on its own
+            out["multi_rhs"] = {"error": str(e)}
     if a.op != "wilson":
         out["metric"] = "wilson_clover_pc_dslash_gflops"
         out["config"]["workload"] = out["config"]["workload"].replace("Wilson Dslash", "Wilson-clover preconditioned Dslash (A^-1 D, compressed clover, per-site Cholesky)")
@@ -345,6 +372,58 @@ def run_b200(a):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mrhs_batches(n, per):
+    """how b200_dslash_apply_multi splits n sources (launch.h::mrhs_batch)"""
+    while n > 0:
+        b = per if n >= per else (2 if n >= 2 and per >= 2 else 1)
+        yield b
+        n -= b
+
+
+def new_spinor(P, seed=None):
+    """another native spinor of P's shape: uniform random (seed given) or zero"""
+    import torch
+    from quda_b200 import dslash as D
+    ref = P["in"]
+    if seed is None:
+        buf = torch.zeros_like(ref.buf)
+    else:
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        if ref.prec == 2:
+            buf = ref.buf.clone()  # block-float layout: reuse the (valid) source image
+        else:
+            dt = torch.float64 if ref.prec == 8 else torch.float32
+            buf = torch.rand(ref.buf.numel() * ref.buf.element_size() // ref.prec, dtype=dt, device="cuda", generator=g).view(torch.uint8)
+    return D.ColorSpinorField(buf, ref.X, ref.prec, ref.n_parity)
+
+
+def multi_rhs_line(a, P, D, L, stream, prec, Vh, peak, nsrc=8, steps=50):
+    """Batched Dslash (the reference's cvector_ref form): nsrc sources sharing the gauge field in one
+    call; per-source time and the fraction of the (amortised) compulsory traffic 8G/batch + 2S per source."""
+    import torch
+    srcs = [P["in"]] + [new_spinor(P, seed=77 + i) for i in range(nsrc - 1)]
+    dsts = [P["out"]] + [new_spinor(P, seed=None) for i in range(nsrc - 1)]
+    call = lambda: D.ApplyWilson(dsts, srcs, P["U"], 0.0, None, 0, 0, tile=a.tile, stream=stream)  # noqa: E731
+    for _ in range(5):
+        call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    per = 2 if prec == 8 else 4
+    S1 = 24 * prec + (4 if prec == 2 else 0)
+    nb = sum(1 for _ in mrhs_batches(nsrc, per))
+    bytes_call = (nb * 8 * a.recon * prec + nsrc * 2 * S1) * Vh
+    ach = bytes_call / (ms * 1e-3) * 1e-9
+    return {"n_src": nsrc, "sources_per_thread": per, "ms_per_call": ms, "us_per_rhs": ms / nsrc * 1e3,
+            "value": 1320 * Vh * nsrc / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s",
+            "algorithmic_bytes_per_call": bytes_call, "hbm_gbs_effective": ach, "frac": ach / peak, "steps": steps}
 
 
 def ncu_traffic(a):

@@ -124,6 +124,17 @@ typedef struct {
  * (include/dslash_quda.h:83,137,234; lib/dslash_wilson.cu:9-20) */
 int b200_dslash_apply(const b200_dslash_args *args);
 
+/* The multi-RHS form of the same three entry points: QUDA passes cvector_ref<ColorSpinorField> batches that share
+ * one gauge (and clover) field (include/dslash_quda.h:83-234; WilsonArg::out/in/x[MAX_MULTI_RHS],
+ * include/kernels/dslash_wilson.cuh:37-69; QUDA_MAX_MULTI_RHS defaults to 16, lib/CMakeLists.txt:298-300).
+ * `args` is read as for b200_dslash_apply except that args->out / in / x are ignored in favour of out[i], in[i], x[i]
+ * (x may be NULL when a == 0).  On an unpartitioned lattice each thread updates its site for up to 4 sources at once
+ * (2 in fp64) with the links held in registers, so the link stream is read once per batch; with partitioned dimensions
+ * or an explicit kernel selector the sources are applied one after the other. */
+#define B200_MAX_MULTI_RHS 16
+int b200_dslash_apply_multi(const b200_dslash_args *args, int n_src, const b200_spinor *out, const b200_spinor *in,
+                            const b200_spinor *x);
+
 /* replaces quda::ApplyClover(out, in, clover, inverse, parity) (include/dslash_quda.h:811;
  * lib/dslash_clover_helper.cu:46-54): out = A in or A^-1 in on one parity */
 int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_clover *A, int precision, int inverse,

@@ -1,5 +1,6 @@
 // C ABI of libquda_b200.so (declared in include/b200_dslash.h).  Plain pointers and sizes only.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "launch.h"
@@ -66,6 +67,32 @@ int b200_dslash_apply(const b200_dslash_args *a)
   case B200_DOUBLE: return launch_precision<PrecF64>(rq);
   case B200_SINGLE: return launch_precision<PrecF32>(rq);
   case B200_HALF: return launch_precision<PrecH16>(rq);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
+}
+
+int b200_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spinor *out, const b200_spinor *in,
+                            const b200_spinor *x)
+{
+  if (int rc = require_device()) return rc;
+  MrhsRequest rq;
+  bool batched = false;
+  if (int rc = make_mrhs_request(rq, a, n_src, out, in, x, batched)) return rc;
+  if (!batched) { // per-source halo schedule
+    for (int i = 0; i < n_src; i++) {
+      b200_dslash_args one = *a;
+      one.out = out[i];
+      one.in = in[i];
+      if (a->a != 0.0) one.x = x[i];
+      if (int rc = b200_dslash_apply(&one)) return rc;
+    }
+    return B200_SUCCESS;
+  }
+  if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e); // tuning knob: 1, 2 or 4 sources per thread
+  switch (a->precision) {
+  case B200_DOUBLE: return launch_mrhs_precision<PrecF64>(rq);
+  case B200_SINGLE: return launch_mrhs_precision<PrecF32>(rq);
+  case B200_HALF: return launch_mrhs_precision<PrecH16>(rq);
   }
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
 }

@@ -345,6 +345,92 @@ namespace b200
     arg.out[parity].save(acc, x_cb);
   }
 
+  // ------------------------------------------------------------------ multi-RHS (batched) stencil
+  // NS sources share one gauge (and clover) field: the reference batches them through cvector_ref and a source index
+  // in the thread grid (include/kernels/dslash_wilson.cuh:37-40,65-69, include/dslash_helper.cuh src_idx), relying on
+  // the caches to serve the repeated link loads.  Here ONE THREAD owns a site for all NS sources: each link is loaded
+  // and reconstructed once into registers and multiplied into NS independent accumulators, so the link stream (2/3 of
+  // the single-source traffic) is amortised exactly -- B_min per source = 8G/NS + 2S -- and every thread has NS times
+  // as many independent spinor loads in flight.
+  template <class P, int NS> struct MrhsFields {
+    SpinorView<P> out[NS][kMaxParity], in[NS][kMaxParity], x[NS][kMaxParity]; // [source][parity the view holds]
+  };
+
+  template <class P, int recon, bool dagger, bool fwd, int NS>
+  B2_HD void hop_local_mrhs(typename P::real (*acc)[24], const DslashArgs<P, recon> &arg, const MrhsFields<P, NS> &f,
+                            const int *x, int x_cb, int parity, int d, const typename GaugeView<P, recon>::Raw *raw)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
+    real u[18];
+    const int n_cb = neighbor_cb<fwd>(x, g, d);
+    if (raw)
+      arg.U.unpack(u, *raw, d, fwd ? x_cb : n_cb);
+    else if (fwd)
+      arg.U.load(u, d, x_cb, parity);
+    else
+      arg.U.load(u, d, n_cb, 1 - parity);
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      const SpinorView<P> &in = f.in[s][1 - parity];
+      real h[12], r[12];
+      if (d == 3) {
+        real t[12];
+        load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+#pragma unroll
+        for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+      } else {
+        real v[24];
+        in.load(v, n_cb);
+        project(h, v, d, sign);
+      }
+      su3_mul<!fwd>(r, u, h);
+      reconstruct_add(acc[s], r, d, sign);
+    }
+  }
+
+  // Unpartitioned lattices only (the launcher falls back to per-source launches otherwise).  The per-source arithmetic
+  // is the single-source one operation for operation, so results are bit-identical to NS separate applications.
+  template <class P, int recon, bool dagger, bool xpay, OpType op, int NS>
+  B2_HD void dslash_site_mrhs(const DslashArgs<P, recon> &arg, const MrhsFields<P, NS> &f, const int *x, int x_cb, int parity)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    real acc[NS][24];
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+#pragma unroll
+      for (int i = 0; i < 24; i++) acc[s][i] = 0;
+
+    constexpr bool preload = PreloadLinks<P, recon>::value;
+    typename GaugeView<P, recon>::Raw raw[preload ? 8 : 1];
+    if constexpr (preload) {
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        arg.U.load_raw(raw[2 * d], d, x_cb, parity);
+        arg.U.load_raw(raw[2 * d + 1], d, neighbor_cb<false>(x, g, d), 1 - parity);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      hop_local_mrhs<P, recon, dagger, true, NS>(acc, arg, f, x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr);
+      hop_local_mrhs<P, recon, dagger, false, NS>(acc, arg, f, x, x_cb, parity, d, preload ? &raw[2 * d + 1] : nullptr);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      if constexpr (op == OP_CLOVER_PC) clover_apply_site<P, true>(acc[s], arg.A, x_cb, parity);
+      if constexpr (xpay) {
+        real xv[24];
+        f.x[s][parity].template load<Cache::STREAM>(xv, x_cb);
+        if constexpr (op == OP_CLOVER) clover_apply_site<P, false>(xv, arg.A, x_cb, parity);
+#pragma unroll
+        for (int i = 0; i < 24; i++) acc[s][i] = xv[i] + arg.a * acc[s][i];
+      }
+      f.out[s][parity].save(acc[s], x_cb);
+    }
+  }
+
   // Exterior update: out += ghost hops (read-modify-write), applying what the interior kernel had to defer.
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   B2_HD void dslash_site_exterior(const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)

@@ -26,6 +26,14 @@ namespace b200
     void *stream;
   };
 
+  // multi-RHS: `base` carries everything but the spinors (its out/in/x mirror source 0 for validation)
+  struct MrhsRequest {
+    LaunchRequest base;
+    int n_src;
+    int max_batch; // sources per thread: 0 = built-in (4, fp64: 2); 1 disables in-thread batching
+    const b200_spinor *out, *in, *x;
+  };
+
   struct CloverRequest {
     void *out, *out_norm, *in, *in_norm;
     b200_clover A;
@@ -160,6 +168,40 @@ namespace b200
   }
 
 
+  // sources handled by one thread in the next multi-RHS launch: as many as the register file carries
+  // (fp32 / half: 4, fp64: 2), then 2, then the single-source kernel
+  template <class P> int mrhs_batch(int remaining, int max_batch)
+  {
+    int cap = sizeof(typename P::real) == 8 ? 2 : 4;
+    if (max_batch > 0 && max_batch < cap) cap = max_batch;
+    if (remaining >= 4 && cap >= 4) return 4;
+    if (remaining >= 2 && cap >= 2) return 2;
+    return 1;
+  }
+
+  template <class P, int NS> void fill_mrhs_fields(MrhsFields<P, NS> &f, const MrhsRequest &rq, int s0)
+  {
+    const LaunchRequest &b = rq.base;
+    for (int s = 0; s < NS; s++) {
+      for (int p = 0; p < 2; p++) {
+        f.out[s][p] = SpinorView<P> {};
+        f.in[s][p] = SpinorView<P> {};
+        f.x[s][p] = SpinorView<P> {};
+      }
+      if (b.n_parity == 2) {
+        for (int p = 0; p < 2; p++) {
+          fill_spinor_parity(f.out[s][p], rq.out[s0 + s], p);
+          fill_spinor_parity(f.in[s][p], rq.in[s0 + s], p);
+          if (b.xpay) fill_spinor_parity(f.x[s][p], rq.x[s0 + s], p);
+        }
+      } else {
+        fill_spinor_parity(f.out[s][b.parity], rq.out[s0 + s], 0);
+        fill_spinor_parity(f.in[s][1 - b.parity], rq.in[s0 + s], 0);
+        if (b.xpay) fill_spinor_parity(f.x[s][b.parity], rq.x[s0 + s], 0);
+      }
+    }
+  }
+
   // default launch geometry per precision: tile of checkerboard sites (x/2, y, z, t); tuned on B200, see DESIGN.md
   inline void default_tile(int *tile, int precision, const int *X)
   {
@@ -228,6 +270,44 @@ namespace b200
     if (rq.kernel < B200_KERNEL_AUTO || rq.kernel > B200_KERNEL_BOUNDARY_TILES)
       return set_error(B200_ERR_INVALID, "unknown kernel selector %d", rq.kernel);
     if ((rq.kernel == B200_KERNEL_EXTERIOR || rq.kernel == B200_KERNEL_BOUNDARY_TILES) && !any_comm) nothing_to_do = true;
+    return 0;
+  }
+
+  // Validate the multi-RHS form: `a` as for b200_dslash_apply (its out/in/x are ignored), n_src sources sharing U / A.
+  // `batched` comes back false when the request must run source by source (partitioned lattice or an explicit
+  // kernel selector: the halo schedule is per source).
+  inline int make_mrhs_request(MrhsRequest &rq, const b200_dslash_args *a, int n_src, const b200_spinor *out,
+                               const b200_spinor *in, const b200_spinor *x, bool &batched)
+  {
+    if (!a) return set_error(B200_ERR_INVALID, "null args");
+    if (n_src < 1 || n_src > B200_MAX_MULTI_RHS)
+      return set_error(B200_ERR_INVALID, "n_src %d not in [1, %d]", n_src, B200_MAX_MULTI_RHS);
+    if (!out || !in) return set_error(B200_ERR_INVALID, "null source / destination array");
+    if (a->a != 0.0 && !x) return set_error(B200_ERR_INVALID, "a != 0 but x is null");
+    for (int i = 0; i < n_src; i++) {
+      if (out[i].n_parity != out[0].n_parity || in[i].n_parity != out[0].n_parity || out[i].volume_cb != out[0].volume_cb
+          || in[i].volume_cb != out[0].volume_cb)
+        return set_error(B200_ERR_INVALID, "source %d: site subset / volume differs from source 0", i);
+      if (!out[i].v || !in[i].v || (a->a != 0.0 && !x[i].v)) return set_error(B200_ERR_INVALID, "source %d: null field pointer", i);
+      for (int j = 0; j < n_src; j++) {
+        if (out[i].v == in[j].v) return set_error(B200_ERR_INVALID, "out[%d] aliases in[%d]", i, j);
+        if (j != i && out[i].v == out[j].v) return set_error(B200_ERR_INVALID, "out[%d] aliases out[%d]", i, j);
+      }
+    }
+    b200_dslash_args first = *a;
+    first.out = out[0];
+    first.in = in[0];
+    if (a->a != 0.0) first.x = x[0];
+    bool nothing = false;
+    if (int rc = make_request(rq.base, &first, nothing)) return rc;
+    rq.n_src = n_src;
+    rq.max_batch = 0;
+    rq.out = out;
+    rq.in = in;
+    rq.x = x;
+    bool any_comm = false;
+    for (int d = 0; d < 4; d++) any_comm |= (a->halo.comm_dim[d] != 0);
+    batched = !any_comm && a->kernel == B200_KERNEL_AUTO;
     return 0;
   }
 
@@ -313,6 +393,7 @@ namespace b200
   }
 
   template <class P> int launch_precision(const LaunchRequest &rq);
+  template <class P> int launch_mrhs_precision(const MrhsRequest &rq);
   template <class P> int launch_clover_precision(const CloverRequest &rq);
   template <class P> int launch_pack_precision(const PackRequest &rq);
   template <class P> int launch_copy_precision(const CopyRequest &rq);

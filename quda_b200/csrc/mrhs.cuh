@@ -1,0 +1,125 @@
+// Multi-RHS (batched) Dslash: kernel wrapper + per-precision launcher.  The site code is dslash_site_mrhs
+// (dslash_site.h); one translation unit per storage precision includes this header (inst_mrhs_*.cu).
+//
+// Reference interface: the cvector_ref<ColorSpinorField> form of ApplyWilson / ApplyWilsonClover /
+// ApplyWilsonCloverPreconditioned (include/dslash_quda.h:83-234), i.e. WilsonArg::out/in/x[MAX_MULTI_RHS] and the
+// source index in the thread grid (include/kernels/dslash_wilson.cuh:37-69).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <type_traits>
+
+#include "dslash_site.h"
+#include "launch.h"
+
+namespace b200
+{
+
+#ifndef B2_MAXTILE
+#define B2_MAXTILE 128
+#endif
+
+  // Register budget: NS accumulators of 24 reals + the NS x 24-real spinor loads in flight.  2 CTAs of <= 128 threads
+  // per SM gives ptxas the full 255 registers (fp64 NS = 2, fp32/half NS = 4); NS = 2 in fp32/half fits 168.
+#ifndef B2_MRHS_MINBLOCKS_4
+#define B2_MRHS_MINBLOCKS_4 2
+#endif
+#ifndef B2_MRHS_MINBLOCKS_2
+#define B2_MRHS_MINBLOCKS_2 3
+#endif
+  template <class P, int NS> struct MrhsMinBlocks { static constexpr int value = NS >= 4 ? B2_MRHS_MINBLOCKS_4 : B2_MRHS_MINBLOCKS_2; };
+  template <int NS> struct MrhsMinBlocks<PrecF64, NS> { static constexpr int value = 2; };
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op, int NS>
+  __global__ void __launch_bounds__(B2_MAXTILE, MrhsMinBlocks<P, NS>::value)
+    dslash_mrhs_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ MrhsFields<P, NS> f,
+                       const __grid_constant__ TileMap tm)
+  {
+    int x[4], x_cb, parity;
+    if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x))
+      return;
+    dslash_site_mrhs<P, recon, dagger, xpay, op, NS>(arg, f, x, x_cb, parity);
+  }
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op, int NS>
+  int launch_mrhs_batch(const MrhsRequest &rq, const DslashArgs<P, recon> &arg, int s0)
+  {
+    MrhsFields<P, NS> f;
+    fill_mrhs_fields(f, rq, s0);
+    TileMap tm;
+    int threads, gx, gy, gz, rc;
+    if (int e = make_tile_map(tm, threads, rq.base.tile, arg.geom, B2_MAXTILE)) return e;
+    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+    dslash_mrhs_kernel<P, recon, dagger, xpay, op, NS><<<dim3(gx, gy, gz), threads, 0, (cudaStream_t)rq.base.stream>>>(arg, f, tm);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "multi-RHS dslash launch");
+  }
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  int launch_mrhs_config(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
+  {
+    int s0 = 0;
+    while (s0 < rq.n_src) {
+      const int ns = mrhs_batch<P>(rq.n_src - s0, rq.max_batch);
+      int rc;
+      if constexpr (!std::is_same<P, PrecF64>::value) {
+        if (ns == 4) {
+          if ((rc = launch_mrhs_batch<P, recon, dagger, xpay, op, 4>(rq, arg, s0))) return rc;
+          s0 += 4;
+          continue;
+        }
+      }
+      if (ns >= 2) {
+        if ((rc = launch_mrhs_batch<P, recon, dagger, xpay, op, 2>(rq, arg, s0))) return rc;
+        s0 += 2;
+      } else { // odd one out: the single-source kernel (inst_*.cu)
+        LaunchRequest one = rq.base;
+        one.out = rq.out[s0];
+        one.in = rq.in[s0];
+        if (rq.base.xpay) one.x = rq.x[s0];
+        if ((rc = launch_precision<P>(one))) return rc;
+        s0 += 1;
+      }
+    }
+    return B200_SUCCESS;
+  }
+
+  template <class P, int recon> int launch_mrhs_recon(const MrhsRequest &rq)
+  {
+    DslashArgs<P, recon> arg;
+    if (int rc = fill_args(arg, rq.base)) return rc;
+    const bool xp = rq.base.xpay, dg = rq.base.dagger;
+    switch (rq.base.op) {
+    case OP_WILSON:
+      if (dg)
+        return xp ? launch_mrhs_config<P, recon, true, true, OP_WILSON>(rq, arg) :
+                    launch_mrhs_config<P, recon, true, false, OP_WILSON>(rq, arg);
+      else
+        return xp ? launch_mrhs_config<P, recon, false, true, OP_WILSON>(rq, arg) :
+                    launch_mrhs_config<P, recon, false, false, OP_WILSON>(rq, arg);
+    case OP_CLOVER:
+      if (!xp) return set_error(B200_ERR_INVALID, "ApplyWilsonClover exists in xpay form only (a != 0)");
+      return dg ? launch_mrhs_config<P, recon, true, true, OP_CLOVER>(rq, arg) :
+                  launch_mrhs_config<P, recon, false, true, OP_CLOVER>(rq, arg);
+    case OP_CLOVER_PC:
+      if (dg)
+        return xp ? launch_mrhs_config<P, recon, true, true, OP_CLOVER_PC>(rq, arg) :
+                    launch_mrhs_config<P, recon, true, false, OP_CLOVER_PC>(rq, arg);
+      else
+        return xp ? launch_mrhs_config<P, recon, false, true, OP_CLOVER_PC>(rq, arg) :
+                    launch_mrhs_config<P, recon, false, false, OP_CLOVER_PC>(rq, arg);
+    }
+    return set_error(B200_ERR_INVALID, "unknown op %d", rq.base.op);
+  }
+
+  template <class P> int launch_mrhs_precision(const MrhsRequest &rq)
+  {
+    switch (rq.base.reconstruct) {
+    case 18: return launch_mrhs_recon<P, 18>(rq);
+    case 12: return launch_mrhs_recon<P, 12>(rq);
+    case 8: return launch_mrhs_recon<P, 8>(rq);
+    }
+    return set_error(B200_ERR_INVALID, "reconstruct %d not in {18,12,8}", rq.base.reconstruct);
+  }
+
+} // namespace b200

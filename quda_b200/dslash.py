@@ -101,6 +101,13 @@ class Halo:
 def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=None, kernel=L.KERNEL_AUTO, tile=None,
            stream=None, backend=None):
     be = backend or cuda_backend()
+    multi = isinstance(out, (list, tuple))  # the reference's cvector_ref batch: sources sharing U (and A)
+    if multi:
+        outs, ins = list(out), list(in_)
+        xs = list(x) if x is not None else None
+        if len(ins) != len(outs) or (xs is not None and len(xs) != len(outs)):
+            raise L.B200Error("multi-RHS: out / in / x batches differ in length")
+        out, in_, x = outs[0], ins[0], (xs[0] if xs else None)
     args = L.DslashArgs()
     args.abi_version = L.ABI_VERSION
     args.op, args.kernel, args.precision = op, kernel, out.prec
@@ -118,11 +125,19 @@ def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=No
         args.A = A.desc()
     args.halo = (halo or Halo()).desc(comm_override)
     args.stream = stream
-    be.call("dslash_apply", C.byref(args))
+    if multi:
+        n = len(outs)
+        o = (L.Spinor * n)(*[f.desc() for f in outs])
+        i = (L.Spinor * n)(*[f.desc() for f in ins])
+        xa = (L.Spinor * n)(*[f.desc() for f in xs]) if xs else None
+        be.call("dslash_apply_multi", C.byref(args), n, o, i, xa)
+    else:
+        be.call("dslash_apply", C.byref(args))
 
 
 def ApplyWilson(out, in_, U, a, x, parity, dagger, comm_override=None, halo=None, **kw):
-    """out = D in (a == 0) or x + a D in.  Reference: lib/dslash_wilson.cu:9-20."""
+    """out = D in (a == 0) or x + a D in.  Reference: lib/dslash_wilson.cu:9-20.
+    `out` / `in_` / `x` may be lists of fields (multi-RHS, the reference's cvector_ref form); likewise below."""
     _apply(L.OP_WILSON, out, in_, U, a, x, parity, dagger, comm_override, halo=halo, **kw)
 
 

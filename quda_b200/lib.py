@@ -70,6 +70,7 @@ class SolverParam(C.Structure):
                 ("reliable_updates", C.c_int), ("true_res", C.c_double), ("secs", C.c_double), ("gflops", C.c_double)]
 
 
+MAX_MULTI_RHS = 16
 DIRAC_WILSON, DIRAC_WILSONPC, DIRAC_CLOVER, DIRAC_CLOVERPC = 0, 1, 2, 3
 APPLY_M, APPLY_MDAG, APPLY_MDAGM, APPLY_DSLASH, APPLY_DSLASH_XPAY = 0, 1, 2, 3, 4
 
@@ -78,6 +79,9 @@ def declare(lib, prefix="b200"):
     """Attach argtypes/restypes for the entry points shared by the CUDA library and the test-only host twin."""
     f = getattr(lib, prefix + "_dslash_apply")
     f.argtypes, f.restype = [C.POINTER(DslashArgs)], C.c_int
+    f = getattr(lib, prefix + "_dslash_apply_multi")
+    f.argtypes = [C.POINTER(DslashArgs), C.c_int, C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(Spinor)]
+    f.restype = C.c_int
     f = getattr(lib, prefix + "_clover_apply")
     f.argtypes = [C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(Clover), C.c_int, C.c_int, C.c_int, C.c_void_p]
     f.restype = C.c_int
@@ -145,7 +149,7 @@ def check(rc, lib=None, prefix="b200"):
         raise B200Error(f"{prefix} error {rc}: {msg}")
 
 
-EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
+EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_dslash_apply_multi", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
                     "b200_copy_spinor", "b200_copy_gauge", "b200_copy_clover", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
                     "b200_dirac_create", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",

@@ -6,6 +6,7 @@
 // libquda_b200.so has no CPU path.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../quda_b200/csrc/launch.h"
@@ -126,6 +127,88 @@ namespace b200
     return set_error(B200_ERR_INVALID, "reconstruct %d", rq.reconstruct);
   }
 
+  // ---- multi-RHS: same batches (launch.h::mrhs_batch) and the same tile grid as mrhs.cuh
+  template <class P, int recon, bool dagger, bool xpay, OpType op, int NS>
+  int run_mrhs_batch(const MrhsRequest &rq, const DslashArgs<P, recon> &arg, int s0)
+  {
+    MrhsFields<P, NS> f;
+    fill_mrhs_fields(f, rq, s0);
+    const Geom &g = arg.geom;
+    TileMap tm;
+    int threads, gx, gy, gz, rc;
+    if (int e = make_tile_map(tm, threads, rq.base.tile, g, 128)) return e;
+    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+    long visited = 0;
+#pragma omp parallel for collapse(2) reduction(+ : visited)
+    for (int bz = 0; bz < gz; bz++)
+      for (int by = 0; by < gy; by++)
+        for (int bx = 0; bx < gx; bx++)
+          for (int tid = 0; tid < threads; tid++) {
+            int x[4], x_cb, par;
+            if (!tile_site(x, x_cb, par, g, tm, arg.n_parity, arg.parity, bx, by, bz, tid)) continue;
+            dslash_site_mrhs<P, recon, dagger, xpay, op, NS>(arg, f, x, x_cb, par);
+            visited++;
+          }
+    if (visited != (long)g.volume_cb * arg.n_parity) return set_error(B200_ERR_INVALID, "multi-RHS tile map visited %ld sites", visited);
+    return 0;
+  }
+
+  template <class P> int run_precision(const LaunchRequest &rq);
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op> int run_mrhs_config(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
+  {
+    int s0 = 0;
+    while (s0 < rq.n_src) {
+      const int ns = mrhs_batch<P>(rq.n_src - s0, rq.max_batch);
+      int rc = 0;
+      if (ns == 4) {
+        rc = run_mrhs_batch<P, recon, dagger, xpay, op, 4>(rq, arg, s0);
+      } else if (ns == 2) {
+        rc = run_mrhs_batch<P, recon, dagger, xpay, op, 2>(rq, arg, s0);
+      } else {
+        LaunchRequest one = rq.base;
+        one.out = rq.out[s0];
+        one.in = rq.in[s0];
+        if (rq.base.xpay) one.x = rq.x[s0];
+        rc = run_precision<P>(one);
+      }
+      if (rc) return rc;
+      s0 += ns;
+    }
+    return 0;
+  }
+
+  template <class P, int recon> int run_mrhs_recon(const MrhsRequest &rq)
+  {
+    DslashArgs<P, recon> arg;
+    if (int rc = fill_args(arg, rq.base)) return rc;
+    const bool xp = rq.base.xpay, dg = rq.base.dagger;
+#define GO(D, X, O) return run_mrhs_config<P, recon, D, X, O>(rq, arg)
+    switch (rq.base.op) {
+    case OP_WILSON:
+      if (dg) { if (xp) GO(true, true, OP_WILSON); else GO(true, false, OP_WILSON); }
+      else { if (xp) GO(false, true, OP_WILSON); else GO(false, false, OP_WILSON); }
+    case OP_CLOVER:
+      if (!xp) return set_error(B200_ERR_INVALID, "ApplyWilsonClover exists in xpay form only (a != 0)");
+      if (dg) GO(true, true, OP_CLOVER); else GO(false, true, OP_CLOVER);
+    case OP_CLOVER_PC:
+      if (dg) { if (xp) GO(true, true, OP_CLOVER_PC); else GO(true, false, OP_CLOVER_PC); }
+      else { if (xp) GO(false, true, OP_CLOVER_PC); else GO(false, false, OP_CLOVER_PC); }
+    }
+#undef GO
+    return set_error(B200_ERR_INVALID, "unknown op");
+  }
+
+  template <class P> int run_mrhs_precision(const MrhsRequest &rq)
+  {
+    switch (rq.base.reconstruct) {
+    case 18: return run_mrhs_recon<P, 18>(rq);
+    case 12: return run_mrhs_recon<P, 12>(rq);
+    case 8: return run_mrhs_recon<P, 8>(rq);
+    }
+    return set_error(B200_ERR_INVALID, "reconstruct %d", rq.base.reconstruct);
+  }
+
   template <class P> int run_clover(const b200_spinor *out, const b200_spinor *in, const b200_clover *Ac, int inverse, int parity)
   {
     SpinorView<P> o, i;
@@ -188,6 +271,30 @@ int twin_dslash_apply(const b200_dslash_args *a)
   case B200_DOUBLE: return run_precision<PrecF64>(rq);
   case B200_SINGLE: return run_precision<PrecF32>(rq);
   case B200_HALF: return run_precision<PrecH16>(rq);
+  }
+  return -1;
+}
+
+int twin_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spinor *out, const b200_spinor *in, const b200_spinor *x)
+{
+  MrhsRequest rq;
+  bool batched = false;
+  if (int rc = make_mrhs_request(rq, a, n_src, out, in, x, batched)) return rc;
+  if (!batched) {
+    for (int i = 0; i < n_src; i++) {
+      b200_dslash_args one = *a;
+      one.out = out[i];
+      one.in = in[i];
+      if (a->a != 0.0) one.x = x[i];
+      if (int rc = twin_dslash_apply(&one)) return rc;
+    }
+    return 0;
+  }
+  if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e);
+  switch (a->precision) {
+  case B200_DOUBLE: return run_mrhs_precision<PrecF64>(rq);
+  case B200_SINGLE: return run_mrhs_precision<PrecF32>(rq);
+  case B200_HALF: return run_mrhs_precision<PrecH16>(rq);
   }
   return -1;
 }

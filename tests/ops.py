@@ -62,6 +62,60 @@ def check_clover(mem, be, prec, recon, compressed, dynamic, X=(4, 4, 6, 4)):
         assert_close(ref, P.to_host(out), prec, tolr, "clover-pc xpay")
 
 
+def check_multi_rhs(mem, be, prec, recon, n_src, op="wilson", xpay=False, dagger=0, X=(4, 6, 4, 8), nparity=1, comm_dim=None,
+                    tile=None):
+    """The reference's cvector_ref form: n_src sources sharing U (and A) in one call.  Every source is checked against
+    the oracle AND must be bit-identical to its own single-source application (same arithmetic, same order)."""
+    P = Problem(X, prec, recon, mem, clover=(op != "wilson"), compressed=True, dynamic=True)
+    kappa = 0.12195
+    a = -kappa if xpay else 0.0
+    src = [P.spinor(seed=50 + i, nparity=nparity) for i in range(n_src)]
+    xsrc = [P.spinor(seed=90 + i, nparity=nparity) for i in range(n_src)]
+    parities = (0, 1) if nparity == 1 else (D.QUDA_INVALID_PARITY,)
+    for parity in parities:
+        ins = [P.to_dev(s, nparity) for s in src]
+        xs = [P.to_dev(s, nparity) for s in xsrc] if xpay else None
+        outs = [P.empty(nparity) for _ in range(n_src)]
+        halo = None
+        if comm_dim is not None:  # partitioned: the per-source fallback; one shared halo only makes sense for n_src == 1
+            assert n_src == 1
+            halo = self_halo(P, mem, comm_dim)
+            self_exchange(P, halo, ins[0], 1 - parity, dagger, be)
+        kw = dict(backend=be, tile=tile, halo=halo)
+        if op == "wilson":
+            D.ApplyWilson(outs, ins, P.U, a, xs, parity, dagger, **kw)
+        elif op == "clover_pc":
+            D.ApplyWilsonCloverPreconditioned(outs, ins, P.U, P.A, a, xs, parity, dagger, **kw)
+        else:
+            D.ApplyWilsonClover(outs, ins, P.U, P.A, a, xs, parity, dagger, **kw)
+        for i in range(n_src):
+            one = P.empty(nparity)
+            xi = xs[i] if xpay else None
+            if op == "wilson":
+                D.ApplyWilson(one, ins[i], P.U, a, xi, parity, dagger, **kw)
+            elif op == "clover_pc":
+                D.ApplyWilsonCloverPreconditioned(one, ins[i], P.U, P.A, a, xi, parity, dagger, **kw)
+            else:
+                D.ApplyWilsonClover(one, ins[i], P.U, P.A, a, xi, parity, dagger, **kw)
+            got = P.to_host(outs[i])
+            if nparity == 1:
+                if op == "wilson":
+                    ref = oracle.wil_dslash(P.gauge, src[i], X, parity, dagger).astype(np.float64)
+                    if xpay:
+                        ref = xsrc[i].astype(np.float64) - kappa * ref
+                elif op == "clover_pc":
+                    ref = oracle.clover_dslash(P.gauge, P.clover_inv, src[i], X, parity, dagger).astype(np.float64)
+                    if xpay:
+                        ref = xsrc[i].astype(np.float64) - kappa * ref
+                else:
+                    ref = oracle.apply_clover(P.clover, xsrc[i], X, parity).astype(np.float64) \
+                        - kappa * oracle.wil_dslash(P.gauge, src[i], X, parity, dagger).astype(np.float64)
+                assert_close(ref, got, prec, recon, f"multi-RHS {op} src {i}/{n_src} p={parity}")
+            single = P.to_host(one)
+            assert np.array_equal(got, single), \
+                f"multi-RHS source {i} differs from its single-source application (max {np.abs(got - single).max():g})"
+
+
 def self_halo(P, mem, comm_dim, nparity=1):
     """Ghost buffers for a single rank that is its own neighbour in every partitioned dimension."""
     h = D.Halo()

@@ -55,3 +55,28 @@ def test_self_exchange_with_arrival_flags(prec, recon):
         comm.apply_wilson_distributed(ex, out, din, P.U, 0.0, None, 0, 0)
     assert_close(ref, P.to_host(out), prec, recon, "self exchange")
     assert not ex.timed_out()
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (8, 12), (4, 18), (4, 12), (4, 8), (2, 12), (2, 8)])
+@pytest.mark.parametrize("n_src", [2, 7, 8])
+def test_multi_rhs_wilson(prec, recon, n_src):
+    """batched Dslash (the reference's cvector_ref form): oracle parity per source + bit-identity with the
+    single-source kernel; 7 = one 4-batch, one 2-batch and the single-source tail (fp64: 2+2+2+1)"""
+    ops.check_multi_rhs(CudaMem, None, prec, recon, n_src, xpay=(n_src == 7), dagger=n_src % 2)
+
+
+@pytest.mark.parametrize("op", ["clover_pc", "clover"])
+@pytest.mark.parametrize("prec", [8, 4, 2])
+def test_multi_rhs_clover(op, prec):
+    ops.check_multi_rhs(CudaMem, None, prec, 12, 4, op=op, xpay=True)
+
+
+def test_multi_rhs_full_fields_and_fallback():
+    ops.check_multi_rhs(CudaMem, None, 4, 12, 4, xpay=True, nparity=2)
+    ops.check_multi_rhs(CudaMem, None, 8, 18, 1, comm_dim=(1, 0, 0, 1), X=(4, 4, 4, 4))
+
+
+def test_multi_rhs_16cubed_tiles():
+    """a lattice large enough for the production tile shapes (full x rows), 16 sources = QUDA_MAX_MULTI_RHS"""
+    ops.check_multi_rhs(CudaMem, None, 4, 12, 16, X=(16, 8, 8, 8))
+    ops.check_multi_rhs(CudaMem, None, 2, 8, 4, X=(16, 8, 8, 8), tile=(8, 8, 1, 1))

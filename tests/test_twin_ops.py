@@ -65,3 +65,40 @@ def test_boundary_and_interior_tiles_are_independent(op, comm_dim):
     """BOUNDARY_TILES and INTERIOR_TILES launches write disjoint sites, in any order (they run on different streams)"""
     ops.check_partitioned(HostMem, twin_backend(), 4, 12, comm_dim, op=op, X=(8, 6, 4, 8), xpay=True, split="tiles",
                           clover_kw=dict(compressed=True, dynamic=True))
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (8, 12), (4, 12), (4, 8), (2, 12), (2, 8)])
+@pytest.mark.parametrize("n_src", [2, 5, 8])
+def test_multi_rhs_wilson(prec, recon, n_src):
+    """batched Dslash (cvector_ref form): in-thread batches of 4 / 2 + single-source tail"""
+    ops.check_multi_rhs(HostMem, twin_backend(), prec, recon, n_src, xpay=(n_src == 5), dagger=n_src % 2)
+
+
+@pytest.mark.parametrize("op", ["clover_pc", "clover"])
+@pytest.mark.parametrize("prec", [8, 4, 2])
+def test_multi_rhs_clover(op, prec):
+    ops.check_multi_rhs(HostMem, twin_backend(), prec, 12, 3, op=op, xpay=True)
+
+
+def test_multi_rhs_full_fields_and_fallback():
+    be = twin_backend()
+    ops.check_multi_rhs(HostMem, be, 4, 12, 4, xpay=True, nparity=2)                     # full fields (both parities)
+    ops.check_multi_rhs(HostMem, be, 8, 18, 1, comm_dim=(1, 0, 0, 1), X=(4, 4, 4, 4))    # partitioned -> per-source path
+
+
+def test_multi_rhs_argument_checks():
+    from common import Problem
+    from quda_b200 import dslash as D
+    from quda_b200.lib import B200Error
+    be = twin_backend()
+    P = Problem((4, 4, 4, 4), 4, 12, HostMem)
+    ins = [P.to_dev(P.spinor(seed=i)) for i in range(3)]
+    outs = [P.empty() for _ in range(3)]
+    with pytest.raises(B200Error, match="aliases"):
+        D.ApplyWilson([outs[0], outs[0], outs[2]], ins, P.U, 0.0, None, 0, 0, backend=be)
+    with pytest.raises(B200Error, match="aliases"):
+        D.ApplyWilson([outs[0], ins[2], outs[2]], ins, P.U, 0.0, None, 0, 0, backend=be)
+    with pytest.raises(B200Error, match="n_src"):
+        D.ApplyWilson([P.empty() for _ in range(17)], [ins[0]] * 17, P.U, 0.0, None, 0, 0, backend=be)
+    with pytest.raises(B200Error, match="x is null"):
+        D.ApplyWilson(outs, ins, P.U, -0.1, None, 0, 0, backend=be)

@@ -13,9 +13,16 @@ from quda_b200 import dslash as D  # noqa: E402
 
 pname, recon = (sys.argv[1], int(sys.argv[2])) if len(sys.argv) > 2 else ("single", 12)
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+nsrc = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 P = bench.make_device_problem([32, 32, 32, 32], bench.PREC_BYTES[pname], recon)
 st = torch.cuda.current_stream().cuda_stream
+if nsrc > 1:
+    srcs = [P["in"]] + [bench.new_spinor(P, seed=77 + i) for i in range(nsrc - 1)]
+    dsts = [P["out"]] + [bench.new_spinor(P, seed=None) for i in range(nsrc - 1)]
 for _ in range(n):
-    D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, stream=st)
+    if nsrc > 1:
+        D.ApplyWilson(dsts, srcs, P["U"], 0.0, None, 0, 0, stream=st)
+    else:
+        D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, stream=st)
 torch.cuda.synchronize()
 print("prof_target done", pname, recon)
