@@ -38,8 +38,11 @@ def parse():
     ap.add_argument("--recon", type=int, default=12, choices=[18, 12, 8])
     ap.add_argument("--dim", type=int, nargs=4, default=[32, 32, 32, 32])
     ap.add_argument("--tile", type=int, nargs=4, default=None)
-    ap.add_argument("--op", default="wilson", choices=["wilson", "clover_pc"],
+    ap.add_argument("--op", default="wilson", choices=["wilson", "clover_pc", "cg"],
                     help="clover_pc: ApplyWilsonCloverPreconditioned (BASELINE config 3), compressed clover, dynamic inverse")
+    ap.add_argument("--global-dim", type=int, nargs=4, default=[48, 48, 48, 96], help="--op cg: global lattice (config 5)")
+    ap.add_argument("--tol", type=float, default=1e-10, help="--op cg: relative residual target")
+    ap.add_argument("--kappa", type=float, default=0.12195)
     ap.add_argument("--nsrc", type=int, default=1, help="sources per call (multi-RHS batch sharing the gauge field); 1 GPU")
     ap.add_argument("--no-mrhs", action="store_true", help="skip the extra multi-RHS measurement of the default line")
     ap.add_argument("--sweep", action="store_true")
@@ -426,6 +429,187 @@ def multi_rhs_line(a, P, D, L, stream, prec, Vh, peak, nsrc=8, steps=50):
             "algorithmic_bytes_per_call": bytes_call, "hbm_gbs_effective": ach, "frac": ach / peak, "steps": steps}
 
 
+def random_su3_device(X):
+    """random SU(3) links [4][V][3][3][2] fp64 on the device, built like the reference's tests do
+    (tests/utils/host_utils.cpp:1022-1098): two random rows, Gram-Schmidt, third row = conjugate cross product"""
+    import torch
+    V = X[0] * X[1] * X[2] * X[3]
+    r1 = torch.randn(4 * V, 3, dtype=torch.complex128, device="cuda")
+    r2 = torch.randn(4 * V, 3, dtype=torch.complex128, device="cuda")
+    r1 = r1 / torch.linalg.vector_norm(r1, dim=1, keepdim=True)
+    r2 = r2 - (r1.conj() * r2).sum(dim=1, keepdim=True) * r1
+    r2 = r2 / torch.linalg.vector_norm(r2, dim=1, keepdim=True)
+    r0 = torch.stack([r1[:, 1] * r2[:, 2] - r1[:, 2] * r2[:, 1], r1[:, 2] * r2[:, 0] - r1[:, 0] * r2[:, 2],
+                      r1[:, 0] * r2[:, 1] - r1[:, 1] * r2[:, 0]], dim=1).conj()
+    q = torch.stack([r0, r1, r2], dim=1)
+    return torch.view_as_real(q).reshape(4, V, 3, 3, 2).contiguous()
+
+
+def boundary_links_from_neighbours(u, X, grid):
+    """per partitioned dimension: the backward neighbour's x[d] = X[d]-1 links of direction d, in face order (NCCL)"""
+    import torch
+    import torch.distributed as dist
+    from quda_b200 import fields as F
+    Vh = F.volume_cb(X)
+    faces = [None] * 4
+    for d in range(4):
+        if grid is None or grid.dims[d] == 1:
+            continue
+        g6 = u.reshape(4, 2, Vh, 3, 3, 2)
+        mine = torch.stack([g6[d, p][torch.from_numpy(F.face_sites(X, d, X[d] - 1, p)).cuda()] for p in range(2)]).contiguous()
+        theirs = torch.empty_like(mine)
+        ops = [dist.P2POp(dist.isend, mine, grid.neighbor(d, +1)), dist.P2POp(dist.irecv, theirs, grid.neighbor(d, -1))]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        torch.cuda.synchronize()
+        faces[d] = theirs
+    return faces
+
+
+def device_clover(X, prec, seed=5):
+    """Synthetic clover term built on the device (1 + Hermitian noise of norm 0.01 with the symmetry the compressed format
+    assumes, as tests/utils/host_utils.cpp:1162-1188) and marshaled by b200_copy_clover into the native compressed layout."""
+    import ctypes as C
+    import torch
+    from quda_b200 import dslash as D
+    from quda_b200 import fields as F
+    from quda_b200 import lib as L
+    Vh = F.volume_cb(X)
+    V = 2 * Vh
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    c = torch.rand((V, 2, 36), dtype=torch.float64, device="cuda", generator=g) * 0.02 - 0.01
+    for dst, src in zip((3, 4, 5, 30, 31, 32, 33, 34, 35), (0, 1, 2, 6, 7, 8, 9, 16, 17)):
+        c[:, :, dst] = -c[:, :, src]
+    c[:, :, :6] += 1.0
+    blk = c.reshape(-1, 36)
+    diagonal = float((0.25 * (blk[:, 0:3] + blk[:, 3:6])).mean())
+    half = 0.5 * blk
+    mx = float(torch.maximum((half[:, 0:3] - diagonal).abs().max(), half[:, 6:30].abs().max()))
+    nbytes = 2 * 2 * 28 * Vh * prec
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    meta = dict(parity_stride_bytes=nbytes // 2, diagonal=diagonal, max_element=2.0 * mx, compressed=1)
+    A = D.CloverField(buf, X, prec, meta, dynamic=True)
+    d = A.desc()
+    Xc = (C.c_int * 4)(*[int(v) for v in X])
+    L.check(L.load().b200_copy_clover(C.byref(d), prec, Xc, c.data_ptr(), 8, None))
+    torch.cuda.synchronize()
+    return A
+
+
+def run_cg(a):
+    """BASELINE config 5: Wilson-clover, even-odd preconditioned (symmetric, even-even), CG on the normal equations to
+    `--tol`, double precision with single-precision sloppy operator + reliable updates (lib/inv_cg_quda.cpp), on a FIXED
+    global lattice (default 48^3 x 96) split over the ranks -- strong scaling.  Reports iterations, time to solution and
+    the solver's sustained GFLOP/s (the reference's own accounting, tests/invert_test.cpp:335-338)."""
+    import torch
+    from quda_b200 import comm, dirac as DR, dslash as D, fields as F, lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if not os.environ.get("NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    dims = comm.ProcessGrid.default_dims(world)
+    grid = comm.ProcessGrid(dims, rank) if world > 1 else None
+    Xg = a.global_dim
+    X = [Xg[d] // dims[d] for d in range(4)]
+    assert all(X[d] * dims[d] == Xg[d] and X[d] % 2 == 0 for d in range(4)), f"global lattice {Xg} does not split over {dims}"
+    Vh = F.volume_cb(X)
+    torch.manual_seed(4321 + rank)
+    u = random_su3_device(X)
+    faces = boundary_links_from_neighbours(u, X, grid)
+    ops, keep = {}, []
+    stream = torch.cuda.current_stream().cuda_stream
+    for prec, recon in ((8, 18), (4, 12)):
+        gbuf, gmeta = F.gauge_to_native_torch(u, X, prec, recon, ghost_faces=faces)
+        U = D.GaugeField(gbuf, X, prec, recon, gmeta, anisotropy=1.0, t_boundary=-1,
+                         first_time_slice=grid.first_time_slice() if grid else True,
+                         last_time_slice=grid.last_time_slice() if grid else True)
+        A = device_clover(X, prec)
+        cs = None
+        if world > 1:
+            ex = comm.HaloExchange(grid, X, prec, mode="p2p", dist=dist)
+            cs = ex.comm_struct()
+            keep += [ex, cs]
+        ops[prec] = DR.Dirac("cloverpc", U, a.kappa, clover=A, comm=cs, stream=stream)
+        keep += [U, A]
+    del u
+    pc = ops[8]
+    pb = F.spinor_bytes(X, 8)
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    b = torch.rand(2 * pb // 8, dtype=torch.float64, device="cuda", generator=g).view(torch.uint8)
+    bdev = D.ColorSpinorField(b, X, 8, 2)
+    xdev = D.ColorSpinorField(torch.zeros(2 * pb, dtype=torch.uint8, device="cuda"), X, 8, 2)
+    rhs = D.ColorSpinorField(torch.zeros(pb, dtype=torch.uint8, device="cuda"), X, 8)
+
+    def solve():
+        xdev.buf.zero_()
+        src_p, sol_p = pc.prepare(xdev, bdev)
+        src = D.ColorSpinorField(xdev.buf[src_p * pb:(src_p + 1) * pb], X, 8)
+        sol = D.ColorSpinorField(xdev.buf[sol_p * pb:(sol_p + 1) * pb], X, 8)
+        pc.Mdag(rhs, src)
+        sol.buf.zero_()
+        res = DR.invert_cg(pc, ops[4], sol, rhs, tol=a.tol, maxiter=20000)
+        pc.reconstruct(xdev, bdev)
+        return res
+
+    with ClockSampler(local_rank) as cs_clk:
+        for _ in range(1 if a.warmup > 0 else 0):
+            solve()  # one untimed solve: first-use allocations, clocks
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.b200_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = solve()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = lib.b200_launch_count()
+    secs = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([secs, res.secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs, solver_secs = float(t[0]), float(t[1])
+    else:
+        solver_secs = res.secs
+    # full-system true residual |b - M x| / |b| recomputed with the UNpreconditioned double-precision operator
+    full = DR.Dirac("clover", ops[8].U, a.kappa, clover=ops[8].clover, comm=ops[8].comm, stream=stream)
+    Mx = D.ColorSpinorField(torch.zeros(2 * pb, dtype=torch.uint8, device="cuda"), X, 8, 2)
+    full.M(Mx, xdev)
+    torch.cuda.synchronize()
+    # plain sums over the native buffers are layout independent
+    d2 = (Mx.buf.view(torch.float64) - bdev.buf.view(torch.float64)).pow(2).sum()
+    b2 = bdev.buf.view(torch.float64).pow(2).sum()
+    nrm = torch.stack([d2, b2])
+    if world > 1:
+        dist.all_reduce(nrm)
+    true_res = float((nrm[0] / nrm[1]).sqrt())
+    gflops = res.gflops * res.secs / solver_secs * world  # per-rank flop count is identical on every rank
+    out = {"metric": "wilson_clover_cg_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": 1,
+           "warmup": 1 if a.warmup > 0 else 0, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64/f32 mixed", "data": "synthetic",
+           "config": {"workload": f"Wilson-clover CG (MdagM of the symmetric even-even preconditioned operator, prepare + "
+                                  f"reconstruct included), global {'x'.join(map(str, Xg))}, local {'x'.join(map(str, X))}, "
+                                  f"double recon-18 / single recon-12 sloppy with reliable updates, tol {a.tol:g}, kappa {a.kappa}",
+                      "grid": dims},
+           "cg": {"iterations": res.iter, "reliable_updates": res.reliable_updates, "time_to_solution_s": secs,
+                  "solver_secs": solver_secs, "solver_true_res_normal_eq": res.true_res, "true_res_full_system": true_res,
+                  "flop_accounting": "blas flops + 1320 per Dslash site application (clover flops not counted), as the reference"},
+           "gpu_launches": int(launches), "clocks": cs_clk.summary()}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def ncu_traffic(a):
     """dram bytes per launch of the interior kernel from the committed ncu capture (profiles/), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -607,5 +791,7 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.op == "cg":
+        run_cg(args)
     else:
         run_b200(args)

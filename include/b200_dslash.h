@@ -211,6 +211,9 @@ int b200_comm_copy(void *dst, const void *src, size_t bytes);
  * DiracWilson[PC] / DiracClover[PC] (lib/dirac_wilson.cpp, lib/dirac_clover.cpp) and CG with reliable updates
  * (lib/inv_cg_quda.cpp); these entry points expose them to non-C++ hosts the way MatQuda / invertQuda
  * (include/quda.h:1206,1337) expose QUDA's. */
+#define B200_MAX_RANKS 16
+#define B200_REDUCE_SLOT_BYTES 64                                              /* 4 doubles + sequence word, padded */
+#define B200_REDUCE_MAILBOX_BYTES (2 * B200_MAX_RANKS * B200_REDUCE_SLOT_BYTES) /* [buffer parity][source rank] */
 typedef struct {
   int comm_dim[4];
   void *send_dst[2][4][2];    /* [buffer][dim][face] peer-mapped destination of our faces */
@@ -223,6 +226,15 @@ typedef struct {
   void *pack_stream;          /* optional cudaStream_t: pack kernels run there, concurrently with the interior tiles */
   void (*allreduce_sum)(double *data, int n, void *user); /* NULL on a single rank */
   void *user;
+  /* Optional NVLink all-reduce for the solver's scalars (dot products / norms), replacing the host callback above and
+   * the reference's MPI_Allreduce on the host (lib/reduce_quda.cu -> comm_allreduce_sum, lib/communicator_mpi.cpp):
+   * reduce_peer[r] is rank r's mailbox region (B200_REDUCE_MAILBOX_BYTES, zero-initialised comm memory) as mapped into
+   * THIS process, reduce_peer[rank] the local one.  Every rank remote-writes its partial sums into its slot of every
+   * mailbox, raises the slot's sequence number (st.release.sys), waits for all slots of its own mailbox and adds them
+   * in rank order -- so all ranks obtain bit-identical sums.  n_ranks == 0: not available, use allreduce_sum. */
+  int rank, n_ranks;
+  void *reduce_peer[B200_MAX_RANKS];
+  unsigned reduce_seq; /* reductions done so far (all ranks advance in lock step) */
 } b200_comm;
 
 typedef struct b200_dirac_s b200_dirac; /* opaque */

@@ -16,6 +16,7 @@ No host polling, no MPI in the critical path.  Modes:
   "host"  CPU-tier tests only: numpy buffers + gloo send/recv, compute by the host twin
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -124,7 +125,12 @@ class HaloExchange:
         o += 8 * 4
         self.timeout_off = o
         o += 64
+        self.mailbox_off = (o + 255) // 256 * 256   # NVLink all-reduce mailboxes (b200_comm::reduce_peer)
+        o = self.mailbox_off + L.REDUCE_MAILBOX_BYTES
         self.slab_bytes = (o + 255) // 256 * 256
+        # solver scalars: "callback" = torch.distributed all-reduce from the host (validated default);
+        # "nvlink" = the mailbox kernel over peer memory (needs every rank mapped, world <= 16)
+        self.allreduce_mode = os.environ.get("B200_ALLREDUCE", "callback")
         self.send_off = None
         if mode in ("p2p", "self"):
             self._init_device_slab()
@@ -155,6 +161,10 @@ class HaloExchange:
             if self.comm_dim[d]:
                 need.add(self.grid.neighbor(d, +1))
                 need.add(self.grid.neighbor(d, -1))
+        if self.allreduce_mode == "nvlink":
+            if self.grid.size > L.MAX_RANKS:
+                raise L.B200Error(f"B200_ALLREDUCE=nvlink supports up to {L.MAX_RANKS} ranks")
+            need.update(range(self.grid.size))
         for r in need:
             if r == self.grid.rank:
                 continue
@@ -305,6 +315,10 @@ class HaloExchange:
 
             self._allreduce_cb = L.ALLREDUCE_FN(_allreduce)  # keep the callback object alive
             c.allreduce_sum = C.cast(self._allreduce_cb, C.c_void_p)
+            if self.allreduce_mode == "nvlink":
+                c.rank, c.n_ranks = g.rank, g.size
+                for r in range(g.size):
+                    c.reduce_peer[r] = self.peer[r] + self.mailbox_off
         self._comm_struct = c
         return c
 

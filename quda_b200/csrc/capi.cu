@@ -88,7 +88,12 @@ int b200_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spi
     }
     return B200_SUCCESS;
   }
-  if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e); // tuning knob: 1, 2 or 4 sources per thread
+  // tuning knobs (defaults are the measured best): B200_MRHS_MODE=thread|cta, B200_MRHS_BATCH (sources per thread),
+  // B200_MRHS_CTA_SOURCES (sources per CTA), B200_MRHS_L1=0|1 (link loads allocate in L1)
+  if (const char *e = getenv("B200_MRHS_MODE")) rq.mode = (strcmp(e, "cta") == 0) ? 1 : 0;
+  if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e);
+  if (const char *e = getenv("B200_MRHS_CTA_SOURCES")) rq.cta_sources = atoi(e);
+  if (const char *e = getenv("B200_MRHS_L1")) rq.l1_links = atoi(e) ? 1 : 0;
   switch (a->precision) {
   case B200_DOUBLE: return launch_mrhs_precision<PrecF64>(rq);
   case B200_SINGLE: return launch_mrhs_precision<PrecF32>(rq);

@@ -499,11 +499,13 @@ namespace b200
       V w[M];
     };
 
-    B2_HD void load_raw(Raw &r, int dir, int x_cb, int parity) const
+    // `c`: STREAM for the single-source kernels (each link is read once), REUSE where sibling warps of the CTA load the
+    // same link (multi-RHS, CTA flavour) and L1 should serve the repeats
+    template <Cache c = Cache::STREAM> B2_HD void load_raw(Raw &r, int dir, int x_cb, int parity) const
     {
       const V *base = reinterpret_cast<const V *>(g[parity]);
 #pragma unroll
-      for (int i = 0; i < M; i++) r.w[i] = ld<Cache::STREAM>(base + (size_t)(dir * M + i) * stride + x_cb);
+      for (int i = 0; i < M; i++) r.w[i] = ld<c>(base + (size_t)(dir * M + i) * stride + x_cb);
     }
 
     B2_HD void unpack(real *u, const Raw &r, int dir, int x_cb) const
@@ -541,10 +543,10 @@ namespace b200
     }
 
     // load link (dir, x_cb, parity) into row-major u[18] = U[row][col] (re, im)
-    B2_HD void load(real *u, int dir, int x_cb, int parity) const
+    template <Cache c = Cache::STREAM> B2_HD void load(real *u, int dir, int x_cb, int parity) const
     {
       Raw r;
-      load_raw(r, dir, x_cb, parity);
+      load_raw<c>(r, dir, x_cb, parity);
       unpack(u, r, dir, x_cb);
     }
 

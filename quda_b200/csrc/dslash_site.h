@@ -154,22 +154,23 @@ namespace b200
     static constexpr bool value = B2_PRELOAD_LINKS && (sizeof(typename GaugeView<P, recon>::Raw) <= 48);
   };
 
-  template <class P, int recon, bool dagger, bool fwd>
-  B2_HD void hop_local(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d,
-                       const typename GaugeView<P, recon>::Raw *raw = nullptr)
+  // `in` is passed explicitly so that the multi-RHS kernels can aim the same code at any source; `lc` is the cache
+  // policy of the link loads
+  template <class P, int recon, bool dagger, bool fwd, Cache lc = Cache::STREAM>
+  B2_HD void hop_from(typename P::real *r, const DslashArgs<P, recon> &arg, const SpinorView<P> &in, const int *x, int x_cb,
+                      int parity, int d, const typename GaugeView<P, recon>::Raw *raw = nullptr)
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
-    const SpinorView<P> &in = arg.in[1 - parity];
     constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
     real u[18], h[12];
     const int n_cb = neighbor_cb<fwd>(x, g, d);
     if (raw)
       arg.U.unpack(u, *raw, d, fwd ? x_cb : n_cb);
     else if (fwd)
-      arg.U.load(u, d, x_cb, parity);
+      arg.U.template load<lc>(u, d, x_cb, parity);
     else
-      arg.U.load(u, d, n_cb, 1 - parity);
+      arg.U.template load<lc>(u, d, n_cb, 1 - parity);
     if (d == 3) {
       real t[12];
       load_spin_pair<P, (sign > 0)>(t, in, n_cb);
@@ -181,6 +182,13 @@ namespace b200
       project(h, v, d, sign);
     }
     su3_mul<!fwd>(r, u, h);
+  }
+
+  template <class P, int recon, bool dagger, bool fwd>
+  B2_HD void hop_local(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d,
+                       const typename GaugeView<P, recon>::Raw *raw = nullptr)
+  {
+    hop_from<P, recon, dagger, fwd>(r, arg, arg.in[1 - parity], x, x_cb, parity, d, raw);
   }
 
   // ---- one hop across a partitioned face: pre-projected half spinor from the ghost buffer, backward link from the pad
@@ -429,6 +437,53 @@ namespace b200
       }
       f.out[s][parity].save(acc[s], x_cb);
     }
+  }
+
+  // Multi-RHS, CTA flavour: one thread = one (site, source) pair, the sources of a site sit in the same CTA
+  // (threadIdx.y), and the links are loaded with the default caching policy so that the first warp's miss fills L1 for
+  // its siblings.  Register footprint and instruction stream per thread are those of the single-source kernel; what
+  // shrinks is the DRAM traffic per source.  The reference's multi-RHS kernels work this way (source index in the
+  // thread grid, include/dslash_helper.cuh:664-713).
+  constexpr int kMaxRhs = 16;
+  template <class P> struct MrhsViews {
+    SpinorView<P> out[kMaxRhs][kMaxParity], in[kMaxRhs][kMaxParity], x[kMaxRhs][kMaxParity];
+  };
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op, Cache lc>
+  B2_HD void dslash_site_src(const DslashArgs<P, recon> &arg, const SpinorView<P> &in, const SpinorView<P> &out,
+                             const SpinorView<P> &xf, const int *x, int x_cb, int parity)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    real acc[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) acc[i] = 0;
+    constexpr bool preload = PreloadLinks<P, recon>::value;
+    typename GaugeView<P, recon>::Raw raw[preload ? 8 : 1];
+    if constexpr (preload) {
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        arg.U.template load_raw<lc>(raw[2 * d], d, x_cb, parity);
+        arg.U.template load_raw<lc>(raw[2 * d + 1], d, neighbor_cb<false>(x, g, d), 1 - parity);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      real r[12];
+      hop_from<P, recon, dagger, true, lc>(r, arg, in, x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr);
+      reconstruct_add(acc, r, d, dagger ? +1 : -1);
+      hop_from<P, recon, dagger, false, lc>(r, arg, in, x, x_cb, parity, d, preload ? &raw[2 * d + 1] : nullptr);
+      reconstruct_add(acc, r, d, dagger ? -1 : +1);
+    }
+    if constexpr (op == OP_CLOVER_PC) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+    if constexpr (xpay) {
+      real xv[24];
+      xf.template load<Cache::STREAM>(xv, x_cb);
+      if constexpr (op == OP_CLOVER) clover_apply_site<P, false>(xv, arg.A, x_cb, parity);
+#pragma unroll
+      for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
+    }
+    out.save(acc, x_cb);
   }
 
   // Exterior update: out += ghost hops (read-modify-write), applying what the interior kernel had to defer.

@@ -264,6 +264,69 @@ namespace b200
         return v;
       }
 
+      // ---- NVLink mailbox all-reduce of up to 4 doubles (b200_comm::reduce_peer).  One warp: lane r < n_ranks pushes this
+      // rank's partial sums into its slot of rank r's mailbox and raises the slot's sequence number, then waits for
+      // rank r's contribution in the local mailbox; lane 0 adds the contributions in rank order (identical on every
+      // rank).  Slots are double buffered by the parity of `seq`: a rank can only be one reduction ahead of the
+      // slowest one, because finishing reduction k needs everybody's contribution to k.
+      struct ReduceSlot {
+        double v[4];
+        unsigned seq;
+        unsigned pad[7];
+      };
+      static_assert(sizeof(ReduceSlot) == B200_REDUCE_SLOT_BYTES, "mailbox slot layout");
+      struct ReducePeers {
+        ReduceSlot *box[B200_MAX_RANKS];
+      };
+
+      __global__ void mailbox_allreduce_kernel(double *__restrict__ val, int n, ReducePeers peers, int rank, int n_ranks,
+                                               unsigned seq, int *timeout_flag)
+      {
+        __shared__ double part[B200_MAX_RANKS][4];
+        const int t = threadIdx.x;
+        const int b = seq & 1;
+        if (t < n_ranks) {
+          ReduceSlot *dst = peers.box[t] + b * B200_MAX_RANKS + rank;
+          for (int i = 0; i < n; i++) dst->v[i] = val[i];
+          __threadfence_system();
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->seq), "r"(seq) : "memory");
+          const ReduceSlot *src = peers.box[rank] + b * B200_MAX_RANKS + t;
+          const long long t0 = clock64();
+          for (;;) {
+            unsigned got;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(&src->seq) : "memory");
+            if ((int)(got - seq) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) { // ~2 s: a lost peer must never hang the GPU
+              if (timeout_flag) *timeout_flag = 1;
+              break;
+            }
+            __nanosleep(50);
+          }
+          for (int i = 0; i < n; i++) part[t][i] = *reinterpret_cast<const volatile double *>(&src->v[i]);
+        }
+        __syncthreads();
+        if (t == 0) {
+          for (int i = 0; i < n; i++) {
+            double acc = 0;
+            for (int r = 0; r < n_ranks; r++) acc += part[r][i];
+            val[i] = acc;
+          }
+        }
+      }
+
+      // sum `n` device doubles over all ranks in place (stream-ordered); false if this CommContext has no mailboxes
+      static bool device_allreduce(double *val, int n, CommContext *comm)
+      {
+        if (!comm || comm->n_ranks < 2) return false;
+        if (n > 4 || comm->n_ranks > B200_MAX_RANKS) throw Error("mailbox all-reduce: too many values / ranks");
+        ReducePeers peers;
+        for (int r = 0; r < B200_MAX_RANKS; r++) peers.box[r] = reinterpret_cast<ReduceSlot *>(comm->reduce_peer[r]);
+        comm->reduce_seq++;
+        mailbox_allreduce_kernel<<<1, 32>>>(val, n, peers, comm->rank, comm->n_ranks, comm->reduce_seq, comm->timeout_flag);
+        cuda_ok(cudaGetLastError(), "all-reduce launch");
+        return true;
+      }
+
       // y = a x + b y (+ optional z update), optional reduction of |y|^2 or <x,y>; one template keeps it compact
       enum { R_NONE = 0, R_NORM_Y = 1, R_DOT_XY = 2 };
       template <typename Tx, typename Ty, int R>
@@ -318,8 +381,9 @@ namespace b200
         g_flops += 3 * (long long)n;
         if (R == R_NONE) return 0.0;
         double h = 0;
+        const bool on_device = device_allreduce(red, 1, comm); // NVLink mailboxes if wired, else the host callback
         cuda_ok(cudaMemcpy(&h, red, sizeof(double), cudaMemcpyDeviceToHost), "memcpy(reduce)");
-        if (comm && comm->allreduce_sum) comm->allreduce_sum(&h, 1, comm->user);
+        if (!on_device && comm && comm->allreduce_sum) comm->allreduce_sum(&h, 1, comm->user);
         return h;
       }
 

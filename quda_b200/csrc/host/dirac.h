@@ -51,6 +51,10 @@ namespace b200
       void *pack_stream = nullptr; // cudaStream_t for the pack kernels (nullptr: same stream as the Dslash)
       void (*allreduce_sum)(double *data, int n, void *user) = nullptr; // nullptr: single rank
       void *user = nullptr;
+      // NVLink mailbox all-reduce (b200_comm::reduce_peer); n_ranks == 0: use the callback
+      int rank = 0, n_ranks = 0;
+      void *reduce_peer[B200_MAX_RANKS] = {};
+      unsigned reduce_seq = 0;
       bool partitioned() const { return comm_dim[0] || comm_dim[1] || comm_dim[2] || comm_dim[3]; }
     };
 

@@ -39,10 +39,17 @@ static void pull_comm(b200_dirac_s *h)
   k.pack_stream = c->pack_stream;
   k.allreduce_sum = c->allreduce_sum;
   k.user = c->user;
+  k.rank = c->rank;
+  k.n_ranks = c->n_ranks;
+  memcpy(k.reduce_peer, c->reduce_peer, sizeof(k.reduce_peer));
+  k.reduce_seq = c->reduce_seq;
 }
 static void push_comm(b200_dirac_s *h)
 {
-  if (h->has_comm) h->user_comm->seq = h->comm.seq;
+  if (h->has_comm) {
+    h->user_comm->seq = h->comm.seq;
+    h->user_comm->reduce_seq = h->comm.reduce_seq;
+  }
 }
 
 template <typename F> static int guarded(F &&f)

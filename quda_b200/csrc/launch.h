@@ -31,6 +31,10 @@ namespace b200
     LaunchRequest base;
     int n_src;
     int max_batch; // sources per thread: 0 = built-in (4, fp64: 2); 1 disables in-thread batching
+    int mode;      // 0: sources batched inside a thread (links in registers); 1: one thread per (site, source), sources
+                   //    of a site in one CTA sharing the links through L1
+    int cta_sources; // mode 1: sources per CTA (0: as many as fit next to the tile in kMaxTile threads)
+    int l1_links;  // mode 1: link loads allocate in L1 (1, default) or stream past it (0: repeats are served by L2)
     const b200_spinor *out, *in, *x;
   };
 
@@ -202,6 +206,41 @@ namespace b200
     }
   }
 
+  template <class P> void fill_mrhs_views(MrhsViews<P> &f, const MrhsRequest &rq)
+  {
+    static_assert(kMaxRhs == B200_MAX_MULTI_RHS, "kMaxRhs mirrors the C ABI limit");
+    const LaunchRequest &b = rq.base;
+    for (int s = 0; s < kMaxRhs; s++)
+      for (int p = 0; p < 2; p++) {
+        f.out[s][p] = SpinorView<P> {};
+        f.in[s][p] = SpinorView<P> {};
+        f.x[s][p] = SpinorView<P> {};
+      }
+    for (int s = 0; s < rq.n_src; s++) {
+      if (b.n_parity == 2) {
+        for (int p = 0; p < 2; p++) {
+          fill_spinor_parity(f.out[s][p], rq.out[s], p);
+          fill_spinor_parity(f.in[s][p], rq.in[s], p);
+          if (b.xpay) fill_spinor_parity(f.x[s][p], rq.x[s], p);
+        }
+      } else {
+        fill_spinor_parity(f.out[s][b.parity], rq.out[s], 0);
+        fill_spinor_parity(f.in[s][1 - b.parity], rq.in[s], 0);
+        if (b.xpay) fill_spinor_parity(f.x[s][b.parity], rq.x[s], 0);
+      }
+    }
+  }
+
+  // CTA flavour launch shape: `tile_threads` sites x `nsb` sources per CTA (<= max_threads), n_batch CTAs per tile
+  inline void mrhs_cta_shape(int &nsb, int &n_batch, int n_src, int tile_threads, int max_threads, int requested)
+  {
+    nsb = max_threads / tile_threads;
+    if (nsb < 1) nsb = 1;
+    if (requested > 0 && requested < nsb) nsb = requested;
+    if (nsb > n_src) nsb = n_src;
+    n_batch = (n_src + nsb - 1) / nsb;
+  }
+
   // default launch geometry per precision: tile of checkerboard sites (x/2, y, z, t); tuned on B200, see DESIGN.md
   inline void default_tile(int *tile, int precision, const int *X)
   {
@@ -302,6 +341,9 @@ namespace b200
     if (int rc = make_request(rq.base, &first, nothing)) return rc;
     rq.n_src = n_src;
     rq.max_batch = 0;
+    rq.mode = 0;
+    rq.cta_sources = 0;
+    rq.l1_links = 1;
     rq.out = out;
     rq.in = in;
     rq.x = x;

@@ -41,6 +41,52 @@ namespace b200
     dslash_site_mrhs<P, recon, dagger, xpay, op, NS>(arg, f, x, x_cb, parity);
   }
 
+  // ---- CTA flavour: blockDim = (tile sites, sources per CTA); blockIdx.x = tile * n_batch + batch, so the CTAs that
+  // share a tile's links are adjacent in launch order (L2 serves what L1 cannot)
+#ifndef B2_MRHS_CTA_MINBLOCKS_F64
+#define B2_MRHS_CTA_MINBLOCKS_F64 2
+#endif
+#ifndef B2_MRHS_CTA_MINBLOCKS
+#define B2_MRHS_CTA_MINBLOCKS 4
+#endif
+  template <class P> struct MrhsCtaMinBlocks { static constexpr int value = B2_MRHS_CTA_MINBLOCKS; };
+  template <> struct MrhsCtaMinBlocks<PrecF64> { static constexpr int value = B2_MRHS_CTA_MINBLOCKS_F64; };
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op, bool l1_links>
+  __global__ void __launch_bounds__(B2_MAXTILE, MrhsCtaMinBlocks<P>::value)
+    dslash_mrhs_cta_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ MrhsViews<P> f,
+                           const __grid_constant__ TileMap tm, int n_src, int n_batch)
+  {
+    const unsigned tile = blockIdx.x / (unsigned)n_batch;
+    const int s = (int)(blockIdx.x - tile * n_batch) * blockDim.y + threadIdx.y;
+    if (s >= n_src) return;
+    int x[4], x_cb, parity;
+    if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, tile, blockIdx.y, blockIdx.z, threadIdx.x)) return;
+    dslash_site_src<P, recon, dagger, xpay, op, l1_links ? Cache::REUSE : Cache::STREAM>(arg, f.in[s][1 - parity], f.out[s][parity],
+                                                                                        f.x[s][parity], x, x_cb, parity);
+  }
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  int launch_mrhs_cta(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
+  {
+    MrhsViews<P> f;
+    fill_mrhs_views(f, rq);
+    TileMap tm;
+    int threads, gx, gy, gz, rc, nsb, n_batch;
+    if (int e = make_tile_map(tm, threads, rq.base.tile, arg.geom, B2_MAXTILE)) return e;
+    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+    mrhs_cta_shape(nsb, n_batch, rq.n_src, threads, B2_MAXTILE, rq.cta_sources);
+    if ((long long)gx * n_batch >= (1ll << 31)) return set_error(B200_ERR_INVALID, "lattice too large for the multi-RHS grid");
+    const dim3 grid(gx * n_batch, gy, gz), block(threads, nsb, 1);
+    cudaStream_t st = (cudaStream_t)rq.base.stream;
+    if (rq.l1_links)
+      dslash_mrhs_cta_kernel<P, recon, dagger, xpay, op, true><<<grid, block, 0, st>>>(arg, f, tm, rq.n_src, n_batch);
+    else
+      dslash_mrhs_cta_kernel<P, recon, dagger, xpay, op, false><<<grid, block, 0, st>>>(arg, f, tm, rq.n_src, n_batch);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "multi-RHS (CTA) dslash launch");
+  }
+
   template <class P, int recon, bool dagger, bool xpay, OpType op, int NS>
   int launch_mrhs_batch(const MrhsRequest &rq, const DslashArgs<P, recon> &arg, int s0)
   {
@@ -58,6 +104,7 @@ namespace b200
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   int launch_mrhs_config(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
   {
+    if (rq.mode == 1) return launch_mrhs_cta<P, recon, dagger, xpay, op>(rq, arg);
     int s0 = 0;
     while (s0 < rq.n_src) {
       const int ns = mrhs_batch<P>(rq.n_src - s0, rq.max_batch);

@@ -59,7 +59,11 @@ class Comm(C.Structure):
                 ("send_signal", ((C.c_void_p * 2) * 4) * 2), ("recv", ((C.c_void_p * 2) * 4) * 2),
                 ("recv_flag", ((C.c_void_p * 2) * 4) * 2), ("block_counter", C.c_void_p),
                 ("timeout_flag", C.c_void_p), ("seq", C.c_uint), ("pack_stream", C.c_void_p),
-                ("allreduce_sum", C.c_void_p), ("user", C.c_void_p)]
+                ("allreduce_sum", C.c_void_p), ("user", C.c_void_p),
+                ("rank", C.c_int), ("n_ranks", C.c_int), ("reduce_peer", C.c_void_p * 16), ("reduce_seq", C.c_uint)]
+
+
+MAX_RANKS, REDUCE_MAILBOX_BYTES = 16, 2 * 16 * 64
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_void_p)

@@ -155,8 +155,40 @@ namespace b200
 
   template <class P> int run_precision(const LaunchRequest &rq);
 
+  // CTA flavour: walk blockIdx.x = tile * n_batch + batch and threadIdx = (site in tile, source in CTA) as mrhs.cuh does
+  template <class P, int recon, bool dagger, bool xpay, OpType op> int run_mrhs_cta(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
+  {
+    MrhsViews<P> f;
+    fill_mrhs_views(f, rq);
+    const Geom &g = arg.geom;
+    TileMap tm;
+    int threads, gx, gy, gz, rc, nsb, n_batch;
+    if (int e = make_tile_map(tm, threads, rq.base.tile, g, 128)) return e;
+    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+    mrhs_cta_shape(nsb, n_batch, rq.n_src, threads, 128, rq.cta_sources);
+    long visited = 0;
+#pragma omp parallel for collapse(2) reduction(+ : visited)
+    for (int bz = 0; bz < gz; bz++)
+      for (int by = 0; by < gy; by++)
+        for (int bx = 0; bx < gx * n_batch; bx++)
+          for (int ty = 0; ty < nsb; ty++)
+            for (int tid = 0; tid < threads; tid++) {
+              const unsigned tile = (unsigned)bx / (unsigned)n_batch;
+              const int s = (bx - (int)tile * n_batch) * nsb + ty;
+              if (s >= rq.n_src) continue;
+              int x[4], x_cb, par;
+              if (!tile_site(x, x_cb, par, g, tm, arg.n_parity, arg.parity, tile, by, bz, tid)) continue;
+              dslash_site_src<P, recon, dagger, xpay, op, Cache::REUSE>(arg, f.in[s][1 - par], f.out[s][par], f.x[s][par], x, x_cb, par);
+              visited++;
+            }
+    if (visited != (long)g.volume_cb * arg.n_parity * rq.n_src)
+      return set_error(B200_ERR_INVALID, "multi-RHS (CTA) grid visited %ld (site, source) pairs", visited);
+    return 0;
+  }
+
   template <class P, int recon, bool dagger, bool xpay, OpType op> int run_mrhs_config(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
   {
+    if (rq.mode == 1) return run_mrhs_cta<P, recon, dagger, xpay, op>(rq, arg);
     int s0 = 0;
     while (s0 < rq.n_src) {
       const int ns = mrhs_batch<P>(rq.n_src - s0, rq.max_batch);
@@ -290,7 +322,9 @@ int twin_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spi
     }
     return 0;
   }
+  if (const char *e = getenv("B200_MRHS_MODE")) rq.mode = (strcmp(e, "cta") == 0) ? 1 : 0;
   if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e);
+  if (const char *e = getenv("B200_MRHS_CTA_SOURCES")) rq.cta_sources = atoi(e);
   switch (a->precision) {
   case B200_DOUBLE: return run_mrhs_precision<PrecF64>(rq);
   case B200_SINGLE: return run_mrhs_precision<PrecF32>(rq);

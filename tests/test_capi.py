@@ -31,15 +31,18 @@ def test_struct_sizes_match_header():
     """ctypes mirrors vs. the C compiler's view of include/b200_dslash.h"""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "b200_dslash.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "b200_dslash.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(b200_spinor),sizeof(b200_gauge),sizeof(b200_clover),sizeof(b200_halo),sizeof(b200_dslash_args),' \
-          'sizeof(b200_pack_args), offsetof(b200_dslash_args, halo));return 0;}'
+          'sizeof(b200_pack_args), offsetof(b200_dslash_args, halo), sizeof(b200_comm), offsetof(b200_comm, reduce_peer),' \
+          'offsetof(b200_comm, reduce_seq), sizeof(b200_solver_param));return 0;}'
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "t.c"), "w").write("#include <stddef.h>\n" + src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "t.c"), "-o", os.path.join(td, "t")])
         got = [int(v) for v in subprocess.check_output([os.path.join(td, "t")]).split()]
     want = [C.sizeof(L.Spinor), C.sizeof(L.Gauge), C.sizeof(L.Clover), C.sizeof(L.Halo), C.sizeof(L.DslashArgs),
-            C.sizeof(L.PackArgs), L.DslashArgs.halo.offset]
+            C.sizeof(L.PackArgs), L.DslashArgs.halo.offset, C.sizeof(L.Comm), L.Comm.reduce_peer.offset,
+            L.Comm.reduce_seq.offset, C.sizeof(L.SolverParam)]
+    assert L.REDUCE_MAILBOX_BYTES == 2 * L.MAX_RANKS * 64
     assert got == want
 
 

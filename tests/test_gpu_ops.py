@@ -80,3 +80,21 @@ def test_multi_rhs_16cubed_tiles():
     """a lattice large enough for the production tile shapes (full x rows), 16 sources = QUDA_MAX_MULTI_RHS"""
     ops.check_multi_rhs(CudaMem, None, 4, 12, 16, X=(16, 8, 8, 8))
     ops.check_multi_rhs(CudaMem, None, 2, 8, 4, X=(16, 8, 8, 8), tile=(8, 8, 1, 1))
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (4, 8), (2, 12), (2, 8)])
+@pytest.mark.parametrize("n_src,cta_sources,l1", [(2, 0, 1), (7, 2, 1), (8, 0, 0), (16, 3, 1)])
+def test_multi_rhs_cta_flavour(monkeypatch, prec, recon, n_src, cta_sources, l1):
+    """B200_MRHS_MODE=cta: one thread per (site, source), the sources of a site share a CTA and the links through L1"""
+    monkeypatch.setenv("B200_MRHS_MODE", "cta")
+    monkeypatch.setenv("B200_MRHS_CTA_SOURCES", str(cta_sources))
+    monkeypatch.setenv("B200_MRHS_L1", str(l1))
+    ops.check_multi_rhs(CudaMem, None, prec, recon, n_src, xpay=(n_src == 7), dagger=n_src % 2, X=(16, 4, 4, 4),
+                        tile=(8, 2, 1, 1))
+
+
+def test_multi_rhs_cta_flavour_clover_and_full(monkeypatch):
+    monkeypatch.setenv("B200_MRHS_MODE", "cta")
+    ops.check_multi_rhs(CudaMem, None, 4, 12, 3, op="clover_pc", xpay=True)
+    ops.check_multi_rhs(CudaMem, None, 2, 12, 3, op="clover", xpay=True, tile=(2, 2, 1, 1))
+    ops.check_multi_rhs(CudaMem, None, 4, 12, 4, xpay=True, nparity=2, tile=(2, 2, 2, 2))

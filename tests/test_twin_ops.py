@@ -102,3 +102,21 @@ def test_multi_rhs_argument_checks():
         D.ApplyWilson([P.empty() for _ in range(17)], [ins[0]] * 17, P.U, 0.0, None, 0, 0, backend=be)
     with pytest.raises(B200Error, match="x is null"):
         D.ApplyWilson(outs, ins, P.U, -0.1, None, 0, 0, backend=be)
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (4, 8), (2, 12), (2, 18)])
+@pytest.mark.parametrize("n_src,cta_sources", [(2, 0), (5, 2), (8, 0), (16, 3)])
+def test_multi_rhs_cta_flavour(monkeypatch, prec, recon, n_src, cta_sources):
+    """B200_MRHS_MODE=cta: one thread per (site, source), sources of a site share a CTA; ragged last batch included"""
+    monkeypatch.setenv("B200_MRHS_MODE", "cta")
+    monkeypatch.setenv("B200_MRHS_CTA_SOURCES", str(cta_sources))
+    ops.check_multi_rhs(HostMem, twin_backend(), prec, recon, n_src, xpay=(n_src == 5), dagger=n_src % 2,
+                        tile=(2, 2, 2, 1))
+
+
+def test_multi_rhs_cta_flavour_clover_and_full(monkeypatch):
+    monkeypatch.setenv("B200_MRHS_MODE", "cta")
+    be = twin_backend()
+    ops.check_multi_rhs(HostMem, be, 4, 12, 3, op="clover_pc", xpay=True)
+    ops.check_multi_rhs(HostMem, be, 2, 12, 3, op="clover", xpay=True, tile=(2, 2, 1, 1))
+    ops.check_multi_rhs(HostMem, be, 4, 12, 4, xpay=True, nparity=2, tile=(2, 2, 2, 2))

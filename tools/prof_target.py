@@ -16,13 +16,14 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 nsrc = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 P = bench.make_device_problem([32, 32, 32, 32], bench.PREC_BYTES[pname], recon)
 st = torch.cuda.current_stream().cuda_stream
+tile = [int(v) for v in os.environ["PROF_TILE"].split()] if os.environ.get("PROF_TILE") else None
 if nsrc > 1:
     srcs = [P["in"]] + [bench.new_spinor(P, seed=77 + i) for i in range(nsrc - 1)]
     dsts = [P["out"]] + [bench.new_spinor(P, seed=None) for i in range(nsrc - 1)]
 for _ in range(n):
     if nsrc > 1:
-        D.ApplyWilson(dsts, srcs, P["U"], 0.0, None, 0, 0, stream=st)
+        D.ApplyWilson(dsts, srcs, P["U"], 0.0, None, 0, 0, stream=st, tile=tile)
     else:
-        D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, stream=st)
+        D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, stream=st, tile=tile)
 torch.cuda.synchronize()
 print("prof_target done", pname, recon)
