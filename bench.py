@@ -300,11 +300,9 @@ def run_b200(a):
     flops = D.flops_per_site(L.OP_CLOVER_PC if a.op == "clover_pc" else L.OP_WILSON) * Vh * world * nsrc
     gflops = flops / (ms * 1e-3) * 1e-9
     bmin = D.min_bytes_per_site(prec, a.recon, clover_bytes=clover_bytes)
-    if nsrc > 1:  # per launch: links once per in-thread batch (4, fp64: 2), spinors per source
+    if nsrc > 1:  # compulsory traffic of one call: the link (and clover) stream once, the spinors once per source
         S1 = 24 * prec + (4 if prec == 2 else 0)
-        per = 2 if prec == 8 else 4
-        nb = sum(1 for _ in mrhs_batches(nsrc, per))
-        bmin = nb * (8 * a.recon * prec + clover_bytes) + nsrc * 2 * S1
+        bmin = (8 * a.recon * prec + clover_bytes) + nsrc * 2 * S1
     S = 24 * prec + (4 if prec == 2 else 0)
     bquda = 8 * a.recon * prec + 8 * S
     peak, peak_src = measured_peaks()
@@ -352,7 +350,7 @@ def run_b200(a):
 
     if nsrc > 1:
         out["config"]["workload"] += f", {nsrc} sources per call (multi-RHS)"
-        out["roofline"]["kernel"] = "dslash_mrhs_kernel"
+        out["roofline"]["kernel"] = "dslash_mrhs_kernel" if mrhs_flavour(prec) == "thread" else "dslash_mrhs_cta_kernel"
         out["roofline"]["traffic"] = None
         out["ms_per_rhs"] = ms / nsrc
     elif world == 1 and a.op == "wilson" and not a.no_mrhs:
@@ -377,12 +375,12 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-def mrhs_batches(n, per):
-    """how b200_dslash_apply_multi splits n sources (launch.h::mrhs_batch)"""
-    while n > 0:
-        b = per if n >= per else (2 if n >= 2 and per >= 2 else 1)
-        yield b
-        n -= b
+def mrhs_flavour(prec):
+    """launch.h::mrhs_mode: which multi-RHS kernel b200_dslash_apply_multi picks (unless B200_MRHS_MODE overrides)"""
+    env = os.environ.get("B200_MRHS_MODE")
+    if env in ("thread", "cta"):
+        return env
+    return "thread" if prec == 2 else "cta"
 
 
 def new_spinor(P, seed=None):
@@ -419,12 +417,10 @@ def multi_rhs_line(a, P, D, L, stream, prec, Vh, peak, nsrc=8, steps=50):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    per = 2 if prec == 8 else 4
     S1 = 24 * prec + (4 if prec == 2 else 0)
-    nb = sum(1 for _ in mrhs_batches(nsrc, per))
-    bytes_call = (nb * 8 * a.recon * prec + nsrc * 2 * S1) * Vh
+    bytes_call = (8 * a.recon * prec + nsrc * 2 * S1) * Vh  # B_min = 8G/n + 2S per site and source
     ach = bytes_call / (ms * 1e-3) * 1e-9
-    return {"n_src": nsrc, "sources_per_thread": per, "ms_per_call": ms, "us_per_rhs": ms / nsrc * 1e3,
+    return {"n_src": nsrc, "flavour": mrhs_flavour(prec), "ms_per_call": ms, "us_per_rhs": ms / nsrc * 1e3,
             "value": 1320 * Vh * nsrc / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s",
             "algorithmic_bytes_per_call": bytes_call, "hbm_gbs_effective": ach, "frac": ach / peak, "steps": steps}
 

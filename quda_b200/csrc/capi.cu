@@ -63,6 +63,7 @@ int b200_dslash_apply(const b200_dslash_args *a)
   bool nothing_to_do = false;
   if (int rc = make_request(rq, a, nothing_to_do)) return rc;
   if (nothing_to_do) return B200_SUCCESS;
+  if (const char *e = getenv("B200_MARCH_T")) rq.march_t = atoi(e); // experimental: time-marching CTAs (kernels.cuh)
   switch (a->precision) {
   case B200_DOUBLE: return launch_precision<PrecF64>(rq);
   case B200_SINGLE: return launch_precision<PrecF32>(rq);
@@ -88,12 +89,13 @@ int b200_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spi
     }
     return B200_SUCCESS;
   }
-  // tuning knobs (defaults are the measured best): B200_MRHS_MODE=thread|cta, B200_MRHS_BATCH (sources per thread),
+  // tuning knobs (defaults are the measured best): B200_MRHS_MODE=thread|cta|auto, B200_MRHS_BATCH (sources per thread),
   // B200_MRHS_CTA_SOURCES (sources per CTA), B200_MRHS_L1=0|1 (link loads allocate in L1)
-  if (const char *e = getenv("B200_MRHS_MODE")) rq.mode = (strcmp(e, "cta") == 0) ? 1 : 0;
+  if (const char *e = getenv("B200_MRHS_MODE")) rq.mode = (strcmp(e, "cta") == 0) ? 1 : (strcmp(e, "thread") == 0 ? 0 : -1);
   if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e);
   if (const char *e = getenv("B200_MRHS_CTA_SOURCES")) rq.cta_sources = atoi(e);
   if (const char *e = getenv("B200_MRHS_L1")) rq.l1_links = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("B200_MRHS_CTA_CFG")) rq.cta_cfg = atoi(e);
   switch (a->precision) {
   case B200_DOUBLE: return launch_mrhs_precision<PrecF64>(rq);
   case B200_SINGLE: return launch_mrhs_precision<PrecF32>(rq);

@@ -85,6 +85,26 @@ namespace b200
     dslash_site_interior<P, recon, dagger, xpay, op, part>(arg, x, x_cb, parity);
   }
 
+  // Marching variant (experimental, B200_MARCH_T): a CTA keeps its (x,y,z) tile and walks `march` consecutive time
+  // slices.  The stencil is bound by the SM <- L2 crossbar (~32 B/clk/SM): 8 neighbour loads per
+  // site, of which L1 catches only ~25 % when every CTA sees its tile once.  Walking in t lets the slices t-1 and t
+  // (loaded one and two steps ago by the SAME SM) be served from L1 instead of crossing the crossbar again.
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  __global__ void __launch_bounds__(kMaxTile, MinBlocks<P>::value)
+    dslash_march_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TileMap tm, int n_chunks,
+                        int march)
+  {
+    int b0, b1, b2, t0, parity;
+    march_tile(b0, b1, b2, t0, parity, tm, arg.n_parity, arg.parity, n_chunks, march, blockIdx.x, blockIdx.y, blockIdx.z);
+    for (int dt = 0; dt < march; dt++) {
+      const int t = t0 + dt;
+      if (t >= arg.geom.X[3]) break;
+      int x[4], x_cb;
+      if (!tile_thread_site(x, x_cb, arg.geom, tm, parity, tm.org[0] + b0, tm.org[1] + b1, tm.org[2] + b2, t, threadIdx.x)) break;
+      dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, parity);
+    }
+  }
+
   // ---- system-scope flag helpers for the NVLink remote-write halo path (used by the kernels below)
   __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
   {
@@ -453,6 +473,14 @@ namespace b200
         dslash_boundary_kernel<P, recon, dagger, xpay, op><<<dim3(nb, arg.n_parity, 1), threads, 0, s>>>(arg, tm, st);
         count_launch();
       }
+      return check_cuda(cudaGetLastError(), "dslash launch");
+    }
+    if (rq.march_t > 0 && !partitioned && tiles_path && tm.sh[3] == 0) {
+      int n_chunks;
+      if (!march_grid(tm, arg.n_parity, arg.geom.X[3], rq.march_t, gx, gy, gz, n_chunks, rc))
+        return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+      dslash_march_kernel<P, recon, dagger, xpay, op><<<dim3(gx, gy, gz), threads, 0, s>>>(arg, tm, n_chunks, rq.march_t);
+      count_launch();
       return check_cuda(cudaGetLastError(), "dslash launch");
     }
     if (rq.kernel != B200_KERNEL_EXTERIOR) { // AUTO / INTERIOR_TILES on an unpartitioned lattice, or reference-style INTERIOR

@@ -18,6 +18,7 @@ namespace b200
   struct LaunchRequest {
     int op, kernel, reconstruct, dagger, xpay, parity, n_parity;
     int X[4], tile[4];
+    int march_t; // > 0: every CTA walks `march_t` consecutive time slices with its (x,y,z) tile (L1 reuse of the slices)
     double a;
     b200_spinor out, in, x;
     b200_gauge U;
@@ -32,9 +33,11 @@ namespace b200
     int n_src;
     int max_batch; // sources per thread: 0 = built-in (4, fp64: 2); 1 disables in-thread batching
     int mode;      // 0: sources batched inside a thread (links in registers); 1: one thread per (site, source), sources
-                   //    of a site in one CTA sharing the links through L1
+                   //    of a site in one CTA sharing the links through L1; -1: measured best per precision
+                   //    (fp64 / fp32: CTA flavour, half: thread flavour -- profiles/r01_mrhs_*.jsonl)
     int cta_sources; // mode 1: sources per CTA (0: as many as fit next to the tile in kMaxTile threads)
     int l1_links;  // mode 1: link loads allocate in L1 (1, default) or stream past it (0: repeats are served by L2)
+    int cta_cfg;   // mode 1: occupancy configuration 0 / 1 / 2 (mrhs.cuh::MrhsCtaCfg)
     const b200_spinor *out, *in, *x;
   };
 
@@ -231,6 +234,12 @@ namespace b200
     }
   }
 
+  inline int mrhs_mode(const MrhsRequest &rq, int precision)
+  {
+    if (rq.mode == 0 || rq.mode == 1) return rq.mode;
+    return precision == B200_HALF ? 0 : 1;
+  }
+
   // CTA flavour launch shape: `tile_threads` sites x `nsb` sources per CTA (<= max_threads), n_batch CTAs per tile
   inline void mrhs_cta_shape(int &nsb, int &n_batch, int n_src, int tile_threads, int max_threads, int requested)
   {
@@ -296,6 +305,7 @@ namespace b200
     } else {
       default_tile(rq.tile, a->precision, a->X);
     }
+    rq.march_t = 0;
     rq.out = a->out;
     rq.in = a->in;
     rq.x = a->x;
@@ -341,9 +351,10 @@ namespace b200
     if (int rc = make_request(rq.base, &first, nothing)) return rc;
     rq.n_src = n_src;
     rq.max_batch = 0;
-    rq.mode = 0;
+    rq.mode = -1;
     rq.cta_sources = 0;
     rq.l1_links = 1;
+    rq.cta_cfg = 0;
     rq.out = out;
     rq.in = in;
     rq.x = x;
@@ -388,6 +399,16 @@ namespace b200
     gx = tm.cnt[0] * tm.cnt[1];
     gy = tm.cnt[2];
     gz = tm.cnt[3] * n_parity;
+    return true;
+  }
+
+  // Marching launch: the tile map must have t-extent 1; the CTA of (x,y,z)-tile column c and chunk k updates the slices
+  // t = k*march .. k*march + march - 1 one after the other.  grid = (cnt0*cnt1, cnt2, n_chunks * n_parity)
+  inline bool march_grid(TileMap &tm, int n_parity, int X3, int march, int &gx, int &gy, int &gz, int &n_chunks, int &rc)
+  {
+    if (!box_grid(tm, n_parity, gx, gy, gz, rc)) return false;
+    n_chunks = (X3 + march - 1) / march;
+    gz = n_chunks * n_parity;
     return true;
   }
 

@@ -43,17 +43,21 @@ namespace b200
 
   // ---- CTA flavour: blockDim = (tile sites, sources per CTA); blockIdx.x = tile * n_batch + batch, so the CTAs that
   // share a tile's links are adjacent in launch order (L2 serves what L1 cannot)
-#ifndef B2_MRHS_CTA_MINBLOCKS_F64
-#define B2_MRHS_CTA_MINBLOCKS_F64 2
-#endif
-#ifndef B2_MRHS_CTA_MINBLOCKS
-#define B2_MRHS_CTA_MINBLOCKS 4
-#endif
-  template <class P> struct MrhsCtaMinBlocks { static constexpr int value = B2_MRHS_CTA_MINBLOCKS; };
-  template <> struct MrhsCtaMinBlocks<PrecF64> { static constexpr int value = B2_MRHS_CTA_MINBLOCKS_F64; };
+  // Occupancy / register configurations of the CTA flavour (B200_MRHS_CTA_CFG): with the links shared through L1 / L2
+  // the DRAM stream has head-room, so the kernel is bound by the per-thread load-latency chain and more resident warps
+  // (fewer registers, no register-resident link preload) can pay:  cfg 0 = the single-source budget (128 regs, links
+  // preloaded), cfg 1 = 6 CTAs of 128 threads (85 regs), cfg 2 = 8 CTAs (64 regs); fp64: 255 / 168 / 128 regs.
+  template <class P, int CFG> struct MrhsCtaCfg {
+    static constexpr int min_blocks = CFG == 0 ? 4 : (CFG == 1 ? 6 : 8);
+    static constexpr bool preload = CFG == 0;
+  };
+  template <int CFG> struct MrhsCtaCfg<PrecF64, CFG> {
+    static constexpr int min_blocks = CFG == 0 ? 2 : (CFG == 1 ? 3 : 4);
+    static constexpr bool preload = false;
+  };
 
-  template <class P, int recon, bool dagger, bool xpay, OpType op, bool l1_links>
-  __global__ void __launch_bounds__(B2_MAXTILE, MrhsCtaMinBlocks<P>::value)
+  template <class P, int recon, bool dagger, bool xpay, OpType op, bool l1_links, int CFG>
+  __global__ void __launch_bounds__(B2_MAXTILE, MrhsCtaCfg<P, CFG>::min_blocks)
     dslash_mrhs_cta_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ MrhsViews<P> f,
                            const __grid_constant__ TileMap tm, int n_src, int n_batch)
   {
@@ -62,8 +66,8 @@ namespace b200
     if (s >= n_src) return;
     int x[4], x_cb, parity;
     if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, tile, blockIdx.y, blockIdx.z, threadIdx.x)) return;
-    dslash_site_src<P, recon, dagger, xpay, op, l1_links ? Cache::REUSE : Cache::STREAM>(arg, f.in[s][1 - parity], f.out[s][parity],
-                                                                                        f.x[s][parity], x, x_cb, parity);
+    dslash_site_src<P, recon, dagger, xpay, op, l1_links ? Cache::REUSE : Cache::STREAM, MrhsCtaCfg<P, CFG>::preload>(
+      arg, f.in[s][1 - parity], f.out[s][parity], f.x[s][parity], x, x_cb, parity);
   }
 
   template <class P, int recon, bool dagger, bool xpay, OpType op>
@@ -79,10 +83,17 @@ namespace b200
     if ((long long)gx * n_batch >= (1ll << 31)) return set_error(B200_ERR_INVALID, "lattice too large for the multi-RHS grid");
     const dim3 grid(gx * n_batch, gy, gz), block(threads, nsb, 1);
     cudaStream_t st = (cudaStream_t)rq.base.stream;
-    if (rq.l1_links)
-      dslash_mrhs_cta_kernel<P, recon, dagger, xpay, op, true><<<grid, block, 0, st>>>(arg, f, tm, rq.n_src, n_batch);
+#define B2_CTA_LAUNCH(L1, CFG) \
+  dslash_mrhs_cta_kernel<P, recon, dagger, xpay, op, L1, CFG><<<grid, block, 0, st>>>(arg, f, tm, rq.n_src, n_batch)
+    if (!rq.l1_links)
+      B2_CTA_LAUNCH(false, 0);
+    else if (rq.cta_cfg == 1)
+      B2_CTA_LAUNCH(true, 1);
+    else if (rq.cta_cfg == 2)
+      B2_CTA_LAUNCH(true, 2);
     else
-      dslash_mrhs_cta_kernel<P, recon, dagger, xpay, op, false><<<grid, block, 0, st>>>(arg, f, tm, rq.n_src, n_batch);
+      B2_CTA_LAUNCH(true, 0);
+#undef B2_CTA_LAUNCH
     count_launch();
     return check_cuda(cudaGetLastError(), "multi-RHS (CTA) dslash launch");
   }
@@ -104,7 +115,7 @@ namespace b200
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   int launch_mrhs_config(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
   {
-    if (rq.mode == 1) return launch_mrhs_cta<P, recon, dagger, xpay, op>(rq, arg);
+    if (mrhs_mode(rq, P::bytes) == 1) return launch_mrhs_cta<P, recon, dagger, xpay, op>(rq, arg);
     int s0 = 0;
     while (s0 < rq.n_src) {
       const int ns = mrhs_batch<P>(rq.n_src - s0, rq.max_batch);

@@ -74,6 +74,29 @@ namespace b200
                          (long)g.volume_cb * arg.n_parity);
       return 0;
     }
+    if (rq.march_t > 0 && !partitioned && tiles_path && tm.sh[3] == 0) { // kernels.cuh::dslash_march_kernel
+      int n_chunks;
+      if (!march_grid(tm, arg.n_parity, g.X[3], rq.march_t, gx, gy, gz, n_chunks, rc)) return rc ? rc : -1;
+#pragma omp parallel for collapse(2) reduction(+ : visited)
+      for (int bz = 0; bz < gz; bz++)
+        for (int by = 0; by < gy; by++)
+          for (int bx = 0; bx < gx; bx++)
+            for (int tid = 0; tid < threads; tid++) {
+              int b0, b1, b2, t0, par;
+              march_tile(b0, b1, b2, t0, par, tm, arg.n_parity, arg.parity, n_chunks, rq.march_t, bx, by, bz);
+              for (int dt = 0; dt < rq.march_t; dt++) {
+                const int t = t0 + dt;
+                if (t >= g.X[3]) break;
+                int x[4], x_cb;
+                if (!tile_thread_site(x, x_cb, g, tm, par, tm.org[0] + b0, tm.org[1] + b1, tm.org[2] + b2, t, tid)) break;
+                dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par);
+                visited++;
+              }
+            }
+      if (visited != (long)g.volume_cb * arg.n_parity)
+        return set_error(B200_ERR_INVALID, "marching grid visited %ld of %ld sites", visited, (long)g.volume_cb * arg.n_parity);
+      return 0;
+    }
     if (rq.kernel != B200_KERNEL_EXTERIOR) {
       if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
       if (partitioned)
@@ -188,7 +211,7 @@ namespace b200
 
   template <class P, int recon, bool dagger, bool xpay, OpType op> int run_mrhs_config(const MrhsRequest &rq, const DslashArgs<P, recon> &arg)
   {
-    if (rq.mode == 1) return run_mrhs_cta<P, recon, dagger, xpay, op>(rq, arg);
+    if (mrhs_mode(rq, P::bytes) == 1) return run_mrhs_cta<P, recon, dagger, xpay, op>(rq, arg);
     int s0 = 0;
     while (s0 < rq.n_src) {
       const int ns = mrhs_batch<P>(rq.n_src - s0, rq.max_batch);
@@ -299,6 +322,7 @@ int twin_dslash_apply(const b200_dslash_args *a)
   bool nothing = false;
   if (int rc = make_request(rq, a, nothing)) return rc;
   if (nothing) return 0;
+  if (const char *e = getenv("B200_MARCH_T")) rq.march_t = atoi(e);
   switch (a->precision) {
   case B200_DOUBLE: return run_precision<PrecF64>(rq);
   case B200_SINGLE: return run_precision<PrecF32>(rq);
@@ -322,7 +346,7 @@ int twin_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spi
     }
     return 0;
   }
-  if (const char *e = getenv("B200_MRHS_MODE")) rq.mode = (strcmp(e, "cta") == 0) ? 1 : 0;
+  if (const char *e = getenv("B200_MRHS_MODE")) rq.mode = (strcmp(e, "cta") == 0) ? 1 : (strcmp(e, "thread") == 0 ? 0 : -1);
   if (const char *e = getenv("B200_MRHS_BATCH")) rq.max_batch = atoi(e);
   if (const char *e = getenv("B200_MRHS_CTA_SOURCES")) rq.cta_sources = atoi(e);
   switch (a->precision) {

@@ -59,15 +59,19 @@ def test_self_exchange_with_arrival_flags(prec, recon):
 
 @pytest.mark.parametrize("prec,recon", [(8, 18), (8, 12), (4, 18), (4, 12), (4, 8), (2, 12), (2, 8)])
 @pytest.mark.parametrize("n_src", [2, 7, 8])
-def test_multi_rhs_wilson(prec, recon, n_src):
+@pytest.mark.parametrize("flavour", ["thread", "auto"])
+def test_multi_rhs_wilson(monkeypatch, prec, recon, n_src, flavour):
     """batched Dslash (the reference's cvector_ref form): oracle parity per source + bit-identity with the
-    single-source kernel; 7 = one 4-batch, one 2-batch and the single-source tail (fp64: 2+2+2+1)"""
+    single-source kernel; thread flavour: 7 = one 4-batch, one 2-batch and the single-source tail (fp64: 2+2+2+1);
+    "auto" = the library's default flavour for the precision"""
+    monkeypatch.setenv("B200_MRHS_MODE", flavour)
     ops.check_multi_rhs(CudaMem, None, prec, recon, n_src, xpay=(n_src == 7), dagger=n_src % 2)
 
 
 @pytest.mark.parametrize("op", ["clover_pc", "clover"])
 @pytest.mark.parametrize("prec", [8, 4, 2])
-def test_multi_rhs_clover(op, prec):
+def test_multi_rhs_clover(monkeypatch, op, prec):
+    monkeypatch.setenv("B200_MRHS_MODE", "thread")
     ops.check_multi_rhs(CudaMem, None, prec, 12, 4, op=op, xpay=True)
 
 
@@ -83,12 +87,14 @@ def test_multi_rhs_16cubed_tiles():
 
 
 @pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (4, 8), (2, 12), (2, 8)])
-@pytest.mark.parametrize("n_src,cta_sources,l1", [(2, 0, 1), (7, 2, 1), (8, 0, 0), (16, 3, 1)])
-def test_multi_rhs_cta_flavour(monkeypatch, prec, recon, n_src, cta_sources, l1):
-    """B200_MRHS_MODE=cta: one thread per (site, source), the sources of a site share a CTA and the links through L1"""
+@pytest.mark.parametrize("n_src,cta_sources,l1,cfg", [(2, 0, 1, 0), (7, 2, 1, 1), (8, 0, 0, 0), (16, 3, 1, 2), (8, 0, 1, 1)])
+def test_multi_rhs_cta_flavour(monkeypatch, prec, recon, n_src, cta_sources, l1, cfg):
+    """B200_MRHS_MODE=cta: one thread per (site, source), the sources of a site share a CTA and the links through L1;
+    cfg = occupancy configuration (register budget) of the kernel"""
     monkeypatch.setenv("B200_MRHS_MODE", "cta")
     monkeypatch.setenv("B200_MRHS_CTA_SOURCES", str(cta_sources))
     monkeypatch.setenv("B200_MRHS_L1", str(l1))
+    monkeypatch.setenv("B200_MRHS_CTA_CFG", str(cfg))
     ops.check_multi_rhs(CudaMem, None, prec, recon, n_src, xpay=(n_src == 7), dagger=n_src % 2, X=(16, 4, 4, 4),
                         tile=(8, 2, 1, 1))
 

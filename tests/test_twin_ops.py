@@ -69,14 +69,18 @@ def test_boundary_and_interior_tiles_are_independent(op, comm_dim):
 
 @pytest.mark.parametrize("prec,recon", [(8, 18), (8, 12), (4, 12), (4, 8), (2, 12), (2, 8)])
 @pytest.mark.parametrize("n_src", [2, 5, 8])
-def test_multi_rhs_wilson(prec, recon, n_src):
-    """batched Dslash (cvector_ref form): in-thread batches of 4 / 2 + single-source tail"""
+@pytest.mark.parametrize("flavour", ["thread", "auto"])
+def test_multi_rhs_wilson(monkeypatch, prec, recon, n_src, flavour):
+    """batched Dslash (cvector_ref form): in-thread batches of 4 / 2 + single-source tail ("thread"), and whatever
+    the library picks by default for the precision ("auto")"""
+    monkeypatch.setenv("B200_MRHS_MODE", flavour)
     ops.check_multi_rhs(HostMem, twin_backend(), prec, recon, n_src, xpay=(n_src == 5), dagger=n_src % 2)
 
 
 @pytest.mark.parametrize("op", ["clover_pc", "clover"])
 @pytest.mark.parametrize("prec", [8, 4, 2])
-def test_multi_rhs_clover(op, prec):
+def test_multi_rhs_clover(monkeypatch, op, prec):
+    monkeypatch.setenv("B200_MRHS_MODE", "thread")
     ops.check_multi_rhs(HostMem, twin_backend(), prec, 12, 3, op=op, xpay=True)
 
 
