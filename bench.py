@@ -350,7 +350,7 @@ def run_b200(a):
 
     if nsrc > 1:
         out["config"]["workload"] += f", {nsrc} sources per call (multi-RHS)"
-        out["roofline"]["kernel"] = "dslash_mrhs_kernel" if mrhs_flavour(prec) == "thread" else "dslash_mrhs_cta_kernel"
+        out["roofline"]["kernel"] = "dslash_mrhs_kernel" if mrhs_flavour(prec, a.recon) == "thread" else "dslash_mrhs_cta_kernel"
         out["roofline"]["traffic"] = None
         out["ms_per_rhs"] = ms / nsrc
     elif world == 1 and a.op == "wilson" and not a.no_mrhs:
@@ -375,12 +375,12 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-def mrhs_flavour(prec):
+def mrhs_flavour(prec, recon):
     """launch.h::mrhs_mode: which multi-RHS kernel b200_dslash_apply_multi picks (unless B200_MRHS_MODE overrides)"""
     env = os.environ.get("B200_MRHS_MODE")
     if env in ("thread", "cta"):
         return env
-    return "thread" if prec == 2 else "cta"
+    return "cta" if (prec == 8 or (prec == 4 and recon == 12)) else "thread"
 
 
 def new_spinor(P, seed=None):
@@ -420,7 +420,7 @@ def multi_rhs_line(a, P, D, L, stream, prec, Vh, peak, nsrc=8, steps=50):
     S1 = 24 * prec + (4 if prec == 2 else 0)
     bytes_call = (8 * a.recon * prec + nsrc * 2 * S1) * Vh  # B_min = 8G/n + 2S per site and source
     ach = bytes_call / (ms * 1e-3) * 1e-9
-    return {"n_src": nsrc, "flavour": mrhs_flavour(prec), "ms_per_call": ms, "us_per_rhs": ms / nsrc * 1e3,
+    return {"n_src": nsrc, "flavour": mrhs_flavour(prec, a.recon), "ms_per_call": ms, "us_per_rhs": ms / nsrc * 1e3,
             "value": 1320 * Vh * nsrc / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s",
             "algorithmic_bytes_per_call": bytes_call, "hbm_gbs_effective": ach, "frac": ach / peak, "steps": steps}
 

@@ -34,7 +34,7 @@ namespace b200
     int max_batch; // sources per thread: 0 = built-in (4, fp64: 2); 1 disables in-thread batching
     int mode;      // 0: sources batched inside a thread (links in registers); 1: one thread per (site, source), sources
                    //    of a site in one CTA sharing the links through L1; -1: measured best per precision
-                   //    (fp64 / fp32: CTA flavour, half: thread flavour -- profiles/r01_mrhs_*.jsonl)
+                   //    and reconstruct (mrhs_mode below)
     int cta_sources; // mode 1: sources per CTA (0: as many as fit next to the tile in kMaxTile threads)
     int l1_links;  // mode 1: link loads allocate in L1 (1, default) or stream past it (0: repeats are served by L2)
     int cta_cfg;   // mode 1: occupancy configuration 0 / 1 / 2 (mrhs.cuh::MrhsCtaCfg)
@@ -237,7 +237,11 @@ namespace b200
   inline int mrhs_mode(const MrhsRequest &rq, int precision)
   {
     if (rq.mode == 0 || rq.mode == 1) return rq.mode;
-    return precision == B200_HALF ? 0 : 1;
+    // measured at 32^4, 8 sources (profiles/r01_final_mrhs_sweep.jsonl, r01_mrhs_cta_sweep_*.jsonl), us per source:
+    // fp64 r18 thread 93.8 / cta 89.7; fp32 r12 40.0 / 38.5; fp32 r18 44.0 / 45.2; fp32 r8 40.1 / 49.7; half r12 43.3 / 45.9
+    if (precision == B200_DOUBLE) return 1;
+    if (precision == B200_SINGLE && rq.base.reconstruct == 12) return 1;
+    return 0;
   }
 
   // CTA flavour launch shape: `tile_threads` sites x `nsb` sources per CTA (<= max_threads), n_batch CTAs per tile
