@@ -111,9 +111,8 @@ int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_
   if (int rc = require_device()) return rc;
   if (out->n_parity != 1 || in->n_parity != 1) return set_error(B200_ERR_INVALID, "ApplyClover acts on single-parity fields");
   if (parity != 0 && parity != 1) return set_error(B200_ERR_INVALID, "parity %d", parity);
-  if (inverse && !A->dynamic_inverse) {
-    // static inverse: caller passes the inverse field and we multiply -- same code path as a forward apply
-  }
+  // inverse with a static-inverse build: the caller passes the A^-1 field and the kernel multiplies (same path as a
+  // forward apply); with dynamic_inverse the field holds A and the kernel solves by Cholesky
   CloverRequest rq;
   rq.out = out->v;
   rq.out_norm = out->norm;

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #include <type_traits>
+#include <utility>
 
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__ __forceinline__
@@ -158,9 +159,23 @@ namespace b200
   // half goes through the conversion unit (I2F.S16, one issue slot, slow pipe), the high half through the integer/FP32
   // pipes -- PRMT sign-extends it, adding it to the bit pattern of 1.5*2^23 puts the integer into the mantissa and one
   // FADD removes the bias (exact; the integer analogue of the reference's QUDA_ALTERNATIVE_I_TO_F path, convert.h:66-78).
-  B2_HD void s16x2_to_f32(unsigned w, float &lo, float &hi)
+  // B2_I2F_NATIVE == 3 (experimental): the conversion unit takes 7 of 8 values, the integer/FP32 pipes every 8th (the
+  // high half of words with phase % 4 == 3).  Issue-slot model per site and SM (half recon-12, 272 conversions, I2F at
+  // 16 lanes/clk/SM): split 50/50 -> 552 issue cycles vs 264 on the conversion unit; 7/8 -> ~500 vs ~476: balanced.
+  template <int phase = 0> B2_HD void s16x2_to_f32(unsigned w, float &lo, float &hi)
   {
-#if defined(__CUDA_ARCH__) && (B2_I2F_NATIVE == 2)
+#if defined(__CUDA_ARCH__) && (B2_I2F_NATIVE == 3)
+    short s0, s1;
+    asm("mov.b32 {%0, %1}, %2;" : "=h"(s0), "=h"(s1) : "r"(w));
+    lo = (float)s0;
+    if constexpr (phase % 4 == 3) {
+      unsigned b;
+      asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(b) : "r"(w));
+      hi = __int_as_float((int)(b + 0x4B400000u)) - 12582912.0f;
+    } else {
+      hi = (float)s1;
+    }
+#elif defined(__CUDA_ARCH__) && (B2_I2F_NATIVE == 2)
     // both halves through the conversion unit (I2F.S16 reads either half of a register directly: one issue slot each)
     short s0, s1;
     asm("mov.b32 {%0, %1}, %2;" : "=h"(s0), "=h"(s1) : "r"(w));
@@ -187,33 +202,34 @@ namespace b200
   }
 
   // generic "vector of storage elements -> reals" used by every accessor
-  template <typename real, typename V> B2_HD void vec_to_real(real *out, const V &v)
+  // `phase`: position of the vector in its site record (only used to spread conversions over pipes, B2_I2F_NATIVE == 3)
+  template <int phase = 0, typename real, typename V> B2_HD void vec_to_real(real *out, const V &v)
   {
     if constexpr (sizeof(V) == sizeof(short) * 8 && alignof(V) == 16 && std::is_same<V, struct s8>::value) {
       unsigned w[4];
       memcpy(w, &v, sizeof(w)); // (type punning through memcpy: folded to register moves, no aliasing UB on the host)
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        float lo, hi;
-        s16x2_to_f32(w[k], lo, hi);
-        out[2 * k] = lo;
-        out[2 * k + 1] = hi;
-      }
+      float lo, hi;
+      s16x2_to_f32<0>(w[0], lo, hi);
+      out[0] = lo, out[1] = hi;
+      s16x2_to_f32<1>(w[1], lo, hi);
+      out[2] = lo, out[3] = hi;
+      s16x2_to_f32<2>(w[2], lo, hi);
+      out[4] = lo, out[5] = hi;
+      s16x2_to_f32<3>(w[3], lo, hi);
+      out[6] = lo, out[7] = hi;
     } else if constexpr (std::is_same<V, struct s4>::value) {
       unsigned w[2];
       memcpy(w, &v, sizeof(w));
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        float lo, hi;
-        s16x2_to_f32(w[k], lo, hi);
-        out[2 * k] = lo;
-        out[2 * k + 1] = hi;
-      }
+      float lo, hi;
+      s16x2_to_f32<2 * (phase % 2)>(w[0], lo, hi);
+      out[0] = lo, out[1] = hi;
+      s16x2_to_f32<2 * (phase % 2) + 1>(w[1], lo, hi);
+      out[2] = lo, out[3] = hi;
     } else if constexpr (std::is_same<V, struct s2>::value) {
       float lo, hi;
       unsigned w;
       memcpy(&w, &v, sizeof(w));
-      s16x2_to_f32(w, lo, hi);
+      s16x2_to_f32<phase % 4>(w, lo, hi);
       out[0] = lo;
       out[1] = hi;
     } else if constexpr (std::is_same<V, struct f4>::value) {
@@ -221,6 +237,17 @@ namespace b200
     } else {
       out[0] = v.x; out[1] = v.y;
     }
+  }
+
+  // vec_to_real over an array of M vectors with the vector index as compile-time phase
+  template <int N, typename real, typename V, int... I>
+  B2_HD void vecs_to_real_impl(real *out, const V *v, std::integer_sequence<int, I...>)
+  {
+    (vec_to_real<I>(out + I * N, v[I]), ...);
+  }
+  template <int M, int N, typename real, typename V> B2_HD void vecs_to_real(real *out, const V *v)
+  {
+    vecs_to_real_impl<N>(out, v, std::make_integer_sequence<int, M> {});
   }
 
   // round-to-nearest-even float -> int16 as the reference's device path does (convert.h:84-107)
@@ -542,6 +569,43 @@ namespace b200
       }
     }
 
+    // Fixed-point links, scaling deferred: u = U / scale with the raw int16 values (exact in fp32) in rows 0,1, so that
+    // the caller can fold `scale` (and the neighbour spinor's block-float norm) into the ONE multiply-add that
+    // accumulates the hop -- removes the 12..18 per-link and 24 per-spinor scaling multiplies from the instruction-bound
+    // half-precision kernels.  recon-12: row 2 = u0 * conj(row0 x row1) is quadratic in the raw values, so it gets
+    // the missing power of 1/32767 here; recon-8 is not linear in its parameters and keeps the plain path (scale = 1).
+    B2_HD void unpack_deferred(real *u, real &scale, const Raw &r, int dir, int x_cb) const
+    {
+      static_assert(P::fixed, "deferred scaling is for the fixed-point formats");
+      if constexpr (recon == 8) {
+        unpack(u, r, dir, x_cb);
+        scale = (real)1;
+      } else {
+        real t[recon];
+        vecs_to_real<M, N>(t, r.w);
+        if constexpr (recon == 18) {
+#pragma unroll
+          for (int i = 0; i < 18; i++) u[i] = t[i];
+          scale = link_scale * kFixedInvMax;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 12; i++) u[i] = t[i];
+          const real s = u0(dir, x_cb) * kFixedInvMax;
+          const cplx<real> a0 {u[0], u[1]}, a1 {u[2], u[3]}, a2 {u[4], u[5]};
+          const cplx<real> b0 {u[6], u[7]}, b1 {u[8], u[9]}, b2 {u[10], u[11]};
+          cplx<real> c0 = cmul(a1, b2), c1 = cmul(a2, b0), c2 = cmul(a0, b1);
+          const cplx<real> d0 = cmul(a2, b1), d1 = cmul(a0, b2), d2_ = cmul(a1, b0);
+          u[12] = s * (c0.re - d0.re);
+          u[13] = -s * (c0.im - d0.im);
+          u[14] = s * (c1.re - d1.re);
+          u[15] = -s * (c1.im - d1.im);
+          u[16] = s * (c2.re - d2_.re);
+          u[17] = -s * (c2.im - d2_.im);
+          scale = kFixedInvMax;
+        }
+      }
+    }
+
     // load link (dir, x_cb, parity) into row-major u[18] = U[row][col] (re, im)
     template <Cache c = Cache::STREAM> B2_HD void load(real *u, int dir, int x_cb, int parity) const
     {
@@ -761,6 +825,37 @@ namespace b200
           a0[0] += h0r; a0[1] += h0i; a1[0] += h1r; a1[1] += h1i;
         } else {
           a2[0] += h0r; a2[1] += h0i; a3[0] += h1r; a3[1] += h1i;
+        }
+      }
+    }
+  }
+
+  // acc += s * reconstruct(h): the deferred-scaling form (one FFMA per component instead of FADD + earlier FMULs)
+  template <typename real> B2_HD void reconstruct_add_scaled(real *acc, const real *h, int mu, int sign, real s)
+  {
+    const real sg = (real)sign * s;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const real h0r = h[(0 * 3 + c) * 2], h0i = h[(0 * 3 + c) * 2 + 1];
+      const real h1r = h[(1 * 3 + c) * 2], h1i = h[(1 * 3 + c) * 2 + 1];
+      real *a0 = acc + (0 * 3 + c) * 2, *a1 = acc + (1 * 3 + c) * 2, *a2 = acc + (2 * 3 + c) * 2, *a3 = acc + (3 * 3 + c) * 2;
+      if (mu == 0) {
+        a0[0] += s * h0r; a0[1] += s * h0i; a1[0] += s * h1r; a1[1] += s * h1i;
+        a2[0] += sg * h1i; a2[1] -= sg * h1r;
+        a3[0] += sg * h0i; a3[1] -= sg * h0r;
+      } else if (mu == 1) {
+        a0[0] += s * h0r; a0[1] += s * h0i; a1[0] += s * h1r; a1[1] += s * h1i;
+        a2[0] -= sg * h1r; a2[1] -= sg * h1i;
+        a3[0] += sg * h0r; a3[1] += sg * h0i;
+      } else if (mu == 2) {
+        a0[0] += s * h0r; a0[1] += s * h0i; a1[0] += s * h1r; a1[1] += s * h1i;
+        a2[0] += sg * h0i; a2[1] -= sg * h0r;
+        a3[0] -= sg * h1i; a3[1] += sg * h1r;
+      } else {
+        if (sign > 0) {
+          a0[0] += s * h0r; a0[1] += s * h0i; a1[0] += s * h1r; a1[1] += s * h1i;
+        } else {
+          a2[0] += s * h0r; a2[1] += s * h0i; a3[0] += s * h1r; a3[1] += s * h1i;
         }
       }
     }

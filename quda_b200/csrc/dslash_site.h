@@ -133,15 +133,20 @@ namespace b200
   }
 
   // which spin pair the t-direction projector keeps: P(3,+1) -> upper (spins 0,1), P(3,-1) -> lower
-  template <class P, bool upper, Cache c = Cache::REUSE>
+  template <class P, bool upper, Cache c = Cache::REUSE, bool scaled = true>
   B2_HD void load_spin_pair(typename P::real *h, const SpinorView<P> &f, int x_cb)
   {
     if constexpr (P::Ns == 8) { // fixed point, 3 planes of 8: reals 0..11 live in planes 0,1 ; 12..23 in planes 1,2
       typename P::real t[16];
       f.template load_planes<upper ? 0 : 1, 2, c>(t, x_cb);
-      const float n = f.load_norm(x_cb);
+      if constexpr (scaled) {
+        const float n = f.load_norm(x_cb);
 #pragma unroll
-      for (int i = 0; i < 12; i++) h[i] = (upper ? t[i] : t[i + 4]) * n;
+        for (int i = 0; i < 12; i++) h[i] = (upper ? t[i] : t[i + 4]) * n;
+      } else { // raw fixed-point values; the caller folds the norm into the accumulation
+#pragma unroll
+        for (int i = 0; i < 12; i++) h[i] = upper ? t[i] : t[i + 4];
+      }
     } else {
       constexpr int np = 12 / P::Ns;
       f.template load_planes<upper ? 0 : np, np, c>(h, x_cb);
@@ -207,6 +212,71 @@ namespace b200
     hop_from<P, recon, dagger, fwd>(r, arg, arg.in[1 - parity], x, x_cb, parity, d, raw);
   }
 
+  // Half precision: keep the int16 values of link and neighbour spinor unscaled through projection and SU(3) multiply
+  // (exact small integers in fp32) and apply link scale x block-float norm (x 2 for the t direction) in the single
+  // FFMA per component that accumulates the hop.  Removes ~250 of the 2 400 instructions per site of the issue-bound
+  // half kernels.  B2_HALF_DEFERRED_SCALE=0 restores the scale-on-load arithmetic.
+#ifndef B2_HALF_DEFERRED_SCALE
+#define B2_HALF_DEFERRED_SCALE 1
+#endif
+  template <class P> struct DeferredScale {
+    static constexpr bool value = P::fixed && B2_HALF_DEFERRED_SCALE;
+  };
+
+  // r = (U or U^dagger) P h with everything unscaled; `scale` is the factor the result still has to be multiplied by
+  template <class P, int recon, bool dagger, bool fwd, Cache lc = Cache::STREAM>
+  B2_HD void hop_from_deferred(typename P::real *r, typename P::real &scale, const DslashArgs<P, recon> &arg,
+                               const SpinorView<P> &in, const int *x, int x_cb, int parity, int d,
+                               const typename GaugeView<P, recon>::Raw *raw = nullptr)
+  {
+    using real = typename P::real;
+    const Geom &g = arg.geom;
+    constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
+    real u[18], h[12], us;
+    const int n_cb = neighbor_cb<fwd>(x, g, d);
+    if (raw) {
+      arg.U.unpack_deferred(u, us, *raw, d, fwd ? x_cb : n_cb);
+    } else {
+      typename GaugeView<P, recon>::Raw w;
+      arg.U.template load_raw<lc>(w, d, fwd ? x_cb : n_cb, fwd ? parity : 1 - parity);
+      arg.U.unpack_deferred(u, us, w, d, fwd ? x_cb : n_cb);
+    }
+    const real n = in.load_norm(n_cb);
+    if (d == 3) {
+      load_spin_pair<P, (sign > 0), Cache::REUSE, false>(h, in, n_cb);
+      scale = (us * n) * (real)2;
+    } else {
+      real v[24];
+      in.template load_planes<0, 24 / P::Ns>(v, n_cb);
+      project(h, v, d, sign);
+      scale = us * n;
+    }
+    su3_mul<!fwd>(r, u, h);
+  }
+
+  // acc += hop (+ optional 0/1 mask for the masked interior kernel); every local hop of every kernel goes through here
+  template <class P, int recon, bool dagger, bool fwd, bool masked, Cache lc = Cache::STREAM>
+  B2_HD void hop_add(typename P::real *acc, const DslashArgs<P, recon> &arg, const SpinorView<P> &in, const int *x, int x_cb,
+                     int parity, int d, const typename GaugeView<P, recon>::Raw *raw, typename P::real mask)
+  {
+    using real = typename P::real;
+    constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
+    real r[12];
+    if constexpr (DeferredScale<P>::value) {
+      real scale;
+      hop_from_deferred<P, recon, dagger, fwd, lc>(r, scale, arg, in, x, x_cb, parity, d, raw);
+      if constexpr (masked) scale *= mask;
+      reconstruct_add_scaled(acc, r, d, sign, scale);
+    } else {
+      hop_from<P, recon, dagger, fwd, lc>(r, arg, in, x, x_cb, parity, d, raw);
+      if constexpr (masked) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) r[i] *= mask;
+      }
+      reconstruct_add(acc, r, d, sign);
+    }
+  }
+
   // ---- one hop across a partitioned face: pre-projected half spinor from the ghost buffer, backward link from the pad
   template <class P, int recon, bool fwd>
   B2_HD void hop_ghost(typename P::real *r, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity, int d)
@@ -256,17 +326,19 @@ namespace b200
         const bool ghost = (x[d] + 1 >= g.X[d]) && arg.comm_dim[d];
         real r[12];
         if constexpr (kt == K_INTERIOR) {
-          hop_local<P, recon, dagger, true>(r, arg, x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr);
-          if constexpr (part) {
-            const real m = ghost ? (real)0 : (real)1;
-#pragma unroll
-            for (int i = 0; i < 12; i++) r[i] *= m;
-          }
-          reconstruct_add(acc, r, d, sign);
+          hop_add<P, recon, dagger, true, part>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr,
+                                                ghost ? (real)0 : (real)1);
         } else if constexpr (kt == K_EXTERIOR_ALL) {
           if (ghost) {
             hop_ghost<P, recon, true>(r, arg, x, x_cb, parity, d);
             reconstruct_add(acc, r, d, sign);
+          }
+        } else if constexpr (DeferredScale<P>::value) {
+          if (ghost) {
+            hop_ghost<P, recon, true>(r, arg, x, x_cb, parity, d);
+            reconstruct_add(acc, r, d, sign);
+          } else {
+            hop_add<P, recon, dagger, true, false>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d, nullptr, (real)1);
           }
         } else {
           if (ghost)
@@ -281,17 +353,19 @@ namespace b200
         const bool ghost = (x[d] - 1 < 0) && arg.comm_dim[d];
         real r[12];
         if constexpr (kt == K_INTERIOR) {
-          hop_local<P, recon, dagger, false>(r, arg, x, x_cb, parity, d, preload ? &raw[2 * d + 1] : nullptr);
-          if constexpr (part) {
-            const real m = ghost ? (real)0 : (real)1;
-#pragma unroll
-            for (int i = 0; i < 12; i++) r[i] *= m;
-          }
-          reconstruct_add(acc, r, d, sign);
+          hop_add<P, recon, dagger, false, part>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d,
+                                                 preload ? &raw[2 * d + 1] : nullptr, ghost ? (real)0 : (real)1);
         } else if constexpr (kt == K_EXTERIOR_ALL) {
           if (ghost) {
             hop_ghost<P, recon, false>(r, arg, x, x_cb, parity, d);
             reconstruct_add(acc, r, d, sign);
+          }
+        } else if constexpr (DeferredScale<P>::value) {
+          if (ghost) {
+            hop_ghost<P, recon, false>(r, arg, x, x_cb, parity, d);
+            reconstruct_add(acc, r, d, sign);
+          } else {
+            hop_add<P, recon, dagger, false, false>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d, nullptr, (real)1);
           }
         } else {
           if (ghost)
@@ -388,29 +462,56 @@ namespace b200
     const Geom &g = arg.geom;
     constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
     real u[18];
+    real us = (real)1; // deferred link scale (fixed point only)
     const int n_cb = neighbor_cb<fwd>(x, g, d);
-    if (raw)
-      arg.U.unpack(u, *raw, d, fwd ? x_cb : n_cb);
-    else if (fwd)
-      arg.U.load(u, d, x_cb, parity);
-    else
-      arg.U.load(u, d, n_cb, 1 - parity);
+    if constexpr (DeferredScale<P>::value) {
+      if (raw) {
+        arg.U.unpack_deferred(u, us, *raw, d, fwd ? x_cb : n_cb);
+      } else {
+        typename GaugeView<P, recon>::Raw w;
+        arg.U.load_raw(w, d, fwd ? x_cb : n_cb, fwd ? parity : 1 - parity);
+        arg.U.unpack_deferred(u, us, w, d, fwd ? x_cb : n_cb);
+      }
+    } else {
+      if (raw)
+        arg.U.unpack(u, *raw, d, fwd ? x_cb : n_cb);
+      else if (fwd)
+        arg.U.load(u, d, x_cb, parity);
+      else
+        arg.U.load(u, d, n_cb, 1 - parity);
+    }
 #pragma unroll
     for (int s = 0; s < NS; s++) {
       const SpinorView<P> &in = f.in[s][1 - parity];
       real h[12], r[12];
-      if (d == 3) {
-        real t[12];
-        load_spin_pair<P, (sign > 0)>(t, in, n_cb);
-#pragma unroll
-        for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+      if constexpr (DeferredScale<P>::value) { // same arithmetic as hop_from_deferred (bit-identical per source)
+        const real n = in.load_norm(n_cb);
+        real scale;
+        if (d == 3) {
+          load_spin_pair<P, (sign > 0), Cache::REUSE, false>(h, in, n_cb);
+          scale = (us * n) * (real)2;
+        } else {
+          real v[24];
+          in.template load_planes<0, 24 / P::Ns>(v, n_cb);
+          project(h, v, d, sign);
+          scale = us * n;
+        }
+        su3_mul<!fwd>(r, u, h);
+        reconstruct_add_scaled(acc[s], r, d, sign, scale);
       } else {
-        real v[24];
-        in.load(v, n_cb);
-        project(h, v, d, sign);
+        if (d == 3) {
+          real t[12];
+          load_spin_pair<P, (sign > 0)>(t, in, n_cb);
+#pragma unroll
+          for (int i = 0; i < 12; i++) h[i] = 2 * t[i];
+        } else {
+          real v[24];
+          in.load(v, n_cb);
+          project(h, v, d, sign);
+        }
+        su3_mul<!fwd>(r, u, h);
+        reconstruct_add(acc[s], r, d, sign);
       }
-      su3_mul<!fwd>(r, u, h);
-      reconstruct_add(acc[s], r, d, sign);
     }
   }
 
@@ -485,11 +586,8 @@ namespace b200
     }
 #pragma unroll
     for (int d = 0; d < 4; d++) {
-      real r[12];
-      hop_from<P, recon, dagger, true, lc>(r, arg, in, x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr);
-      reconstruct_add(acc, r, d, dagger ? +1 : -1);
-      hop_from<P, recon, dagger, false, lc>(r, arg, in, x, x_cb, parity, d, preload ? &raw[2 * d + 1] : nullptr);
-      reconstruct_add(acc, r, d, dagger ? -1 : +1);
+      hop_add<P, recon, dagger, true, false, lc>(acc, arg, in, x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr, (real)1);
+      hop_add<P, recon, dagger, false, false, lc>(acc, arg, in, x, x_cb, parity, d, preload ? &raw[2 * d + 1] : nullptr, (real)1);
     }
     if constexpr (op == OP_CLOVER_PC) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
     if constexpr (xpay) {

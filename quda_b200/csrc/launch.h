@@ -259,7 +259,6 @@ namespace b200
   {
     // full x rows (coalesced 256..512-byte runs per plane) and small CTAs won every B200 sweep (profiles/)
     int t[4] = {16, 2, 2, 1};
-    if (precision == B200_DOUBLE) { t[0] = 16; t[1] = 2; t[2] = 1; t[3] = 2; }
     if (precision == B200_DOUBLE) { t[0] = 16; t[1] = 2; t[2] = 1; t[3] = 1; }
     if (precision == B200_HALF) { t[0] = 16; t[1] = 8; t[2] = 1; t[3] = 1; }
     for (int d = 0; d < 4; d++) {
