@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 typedef enum {
   B200_SUCCESS = 0,
@@ -40,7 +40,12 @@ enum { B200_DOUBLE = 8, B200_SINGLE = 4, B200_HALF = 2 };
 typedef enum {
   B200_OP_WILSON = 0,   /* ApplyWilson:                    out = D in            | a != 0: out = x + a D in       */
   B200_OP_CLOVER = 1,   /* ApplyWilsonClover:              out = A x + a D in  (xpay form only)                   */
-  B200_OP_CLOVER_PC = 2 /* ApplyWilsonCloverPreconditioned: out = A^-1 D in      | a != 0: out = x + a A^-1 D in  */
+  B200_OP_CLOVER_PC = 2, /* ApplyWilsonCloverPreconditioned: out = A^-1 D in     | a != 0: out = x + a A^-1 D in  */
+  /* degenerate twisted mass: the same stencil with a (1 + i b gamma5) rotation in the epilogue
+   * (include/dslash_quda.h:363-406, include/kernels/dslash_twisted_mass*.cuh); b is negated for dagger */
+  B200_OP_TWISTED_MASS = 3,   /* ApplyTwistedMass:  out = a D in + (1 + i b gamma5) x   (xpay form only, a != 0)       */
+  B200_OP_TWISTED_MASS_PC = 4 /* ApplyTwistedMassPreconditioned: out = a (1 + i b gamma5) D in [+ x if x.v != NULL];
+                               * dagger without `asymmetric`: out = D^dagger a (1 - i b gamma5) in [+ x]              */
 } b200_op;
 
 typedef enum {
@@ -111,7 +116,9 @@ typedef struct {
   int X[4];           /* local lattice extents (full sites), all even */
   int parity;         /* destination parity (n_parity == 1); ignored for full fields */
   int dagger;
-  double a;           /* 0 => no xpay (include/kernels/dslash_wilson.cuh:54) */
+  double a;           /* 0 => no xpay (include/kernels/dslash_wilson.cuh:54); B200_OP_TWISTED_MASS_PC: scale of the rotation */
+  double b;           /* twisted mass only: the twist factor (2 mu kappa, or -2 kappa mu for the inverse rotation) */
+  int asymmetric;     /* B200_OP_TWISTED_MASS_PC only: asymmetric preconditioning (needs dagger, excludes x) */
   b200_spinor out, in, x;
   b200_gauge U;
   b200_clover A;      /* ignored for B200_OP_WILSON */

@@ -143,6 +143,41 @@ def wil_matpc(gauge, inp, X, kappa, matpc=MATPC_EVEN_EVEN, dagger=0):
     return out
 
 
+TWIST_SINGLET = 1  # QudaTwistFlavorType value the reference multiplies mu with
+
+
+def twist_gamma5(inp, kappa, mu, dagger=0, inverse=False, flavor=TWIST_SINGLET):
+    """b (1 + i a gamma5) inp in the DeGrand-Rossi basis (wilson_dslash_reference.cpp:139-169)"""
+    out = np.zeros_like(inp)
+    getattr(lib(), "orc_twist_gamma5" + _sfx(inp))(
+        _p(out), _p(inp), C.c_int(dagger), C.c_double(kappa), C.c_double(mu), C.c_int(flavor), C.c_long(inp.size // 24),
+        C.c_int(1 if inverse else 0))
+    return out
+
+
+def tm_dslash(gauge, inp, X, kappa, mu, parity, dagger=0, matpc=MATPC_EVEN_EVEN, flavor=TWIST_SINGLET):
+    out = np.zeros_like(inp)
+    getattr(lib(), "orc_tm_dslash" + _sfx(inp))(
+        _p(out), _gptr(gauge), _p(inp), _X(X), C.c_double(kappa), C.c_double(mu), C.c_int(flavor), C.c_int(matpc),
+        C.c_int(parity), C.c_int(dagger))
+    return out
+
+
+def tm_mat(gauge, inp, X, kappa, mu, dagger=0, flavor=TWIST_SINGLET):
+    out = np.zeros_like(inp)
+    getattr(lib(), "orc_tm_mat" + _sfx(inp))(
+        _p(out), _gptr(gauge), _p(inp), _X(X), C.c_double(kappa), C.c_double(mu), C.c_int(flavor), C.c_int(dagger))
+    return out
+
+
+def tm_matpc(gauge, inp, X, kappa, mu, matpc=MATPC_EVEN_EVEN, dagger=0, flavor=TWIST_SINGLET):
+    out = np.zeros_like(inp)
+    getattr(lib(), "orc_tm_matpc" + _sfx(inp))(
+        _p(out), _gptr(gauge), _p(inp), _X(X), C.c_double(kappa), C.c_double(mu), C.c_int(flavor), C.c_int(matpc),
+        C.c_int(dagger))
+    return out
+
+
 def apply_clover(clover, inp, X, parity):
     out = np.zeros_like(inp)
     getattr(lib(), "orc_apply_clover" + _sfx(inp))(_p(out), _p(clover), _p(inp), _X(X), C.c_int(parity))
@@ -228,6 +263,32 @@ class Reference:
         out = np.zeros_like(inp)
         self.L.ref_wil_matpc(_p(out), _gptr(gauge), _p(inp), C.c_double(kappa), C.c_int(self.L.ref_matpc_enum(matpc)),
                              C.c_int(dagger), self._pb(inp), _X(self.X))
+        return out
+
+    def twist_gamma5(self, inp, kappa, mu, dagger=0, inverse=False):
+        out = np.zeros_like(inp)
+        self.L.ref_twist_gamma5(_p(out), _p(np.ascontiguousarray(inp.copy())), C.c_int(dagger), C.c_double(kappa), C.c_double(mu),
+                                C.c_int(inp.size // 24), C.c_int(1 if inverse else 0), self._pb(inp))
+        return out
+
+    def tm_dslash(self, gauge, inp, kappa, mu, parity, dagger=0, matpc=MATPC_EVEN_EVEN):
+        out = np.zeros_like(inp)
+        work = np.ascontiguousarray(inp.copy())  # the reference twists its input in place
+        self.L.ref_tm_dslash(_p(out), _gptr(gauge), _p(work), C.c_double(kappa), C.c_double(mu),
+                             C.c_int(self.L.ref_matpc_enum(matpc)), C.c_int(parity), C.c_int(dagger), self._pb(inp), _X(self.X))
+        return out
+
+    def tm_mat(self, gauge, inp, kappa, mu, dagger=0):
+        out = np.zeros_like(inp)
+        self.L.ref_tm_mat(_p(out), _gptr(gauge), _p(inp), C.c_double(kappa), C.c_double(mu), C.c_int(dagger), self._pb(inp),
+                          _X(self.X))
+        return out
+
+    def tm_matpc(self, gauge, inp, kappa, mu, matpc=MATPC_EVEN_EVEN, dagger=0):
+        out = np.zeros_like(inp)
+        work = np.ascontiguousarray(inp.copy())
+        self.L.ref_tm_matpc(_p(out), _gptr(gauge), _p(work), C.c_double(kappa), C.c_double(mu),
+                            C.c_int(self.L.ref_matpc_enum(matpc)), C.c_int(dagger), self._pb(inp), _X(self.X))
         return out
 
     def apply_clover(self, clover, inp, parity):

@@ -169,6 +169,36 @@ EXPORT void ref_wil_matpc(void *out, void **gauge, void *in, double kappa, int m
   wil_matpc(out, gauge, in, kappa, (QudaMatPCType)matpc, dagger, prec_of(prec_bytes), p);
 }
 
+// defined (non-static, but not declared in the header) in tests/host_reference/wilson_dslash_reference.cpp:171
+void twist_gamma5(void *out, const void *in, int dagger, double kappa, double mu, QudaTwistFlavorType flavor, int V,
+                  QudaTwistGamma5Type twist, QudaPrecision precision);
+
+EXPORT void ref_twist_gamma5(void *out, void *in, int dagger, double kappa, double mu, int V_, int inverse, int prec_bytes)
+{
+  twist_gamma5(out, in, dagger, kappa, mu, QUDA_TWIST_SINGLET, V_, inverse ? QUDA_TWIST_GAMMA5_INVERSE : QUDA_TWIST_GAMMA5_DIRECT,
+               prec_of(prec_bytes));
+}
+
+EXPORT void ref_tm_dslash(void *out, void **gauge, void *in, double kappa, double mu, int matpc, int parity, int dagger,
+                          int prec_bytes, const int *X)
+{
+  QudaGaugeParam p = make_gauge_param(X, 1.0, 0);
+  tm_dslash(out, gauge, in, kappa, mu, QUDA_TWIST_SINGLET, (QudaMatPCType)matpc, parity, dagger, prec_of(prec_bytes), p);
+}
+
+EXPORT void ref_tm_mat(void *out, void **gauge, void *in, double kappa, double mu, int dagger, int prec_bytes, const int *X)
+{
+  QudaGaugeParam p = make_gauge_param(X, 1.0, 0);
+  tm_mat(out, gauge, in, kappa, mu, QUDA_TWIST_SINGLET, dagger, prec_of(prec_bytes), p);
+}
+
+EXPORT void ref_tm_matpc(void *out, void **gauge, void *in, double kappa, double mu, int matpc, int dagger, int prec_bytes,
+                         const int *X)
+{
+  QudaGaugeParam p = make_gauge_param(X, 1.0, 0);
+  tm_matpc(out, gauge, in, kappa, mu, QUDA_TWIST_SINGLET, (QudaMatPCType)matpc, dagger, prec_of(prec_bytes), p);
+}
+
 EXPORT void ref_apply_clover(void *out, void *clover, void *in, int parity, int prec_bytes)
 {
   apply_clover(out, clover, in, parity, prec_of(prec_bytes));

@@ -229,6 +229,104 @@ void FN(orc_clover_mat)(REAL *out, const REAL *const *gauge, const REAL *clover,
   free(tmp);
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Twisted mass (degenerate / singlet flavour), tests/host_reference/wilson_dslash_reference.cpp:139-315.
+ * twist_gamma5: out = b (1 + i a gamma5) in with, in the DeGrand-Rossi basis, gamma5 = diag(+1,+1,-1,-1);
+ *   direct : a = 2 kappa mu flavor,  b = 1                  inverse: a = -2 kappa mu flavor, b = 1 / (1 + a^2)
+ *   dagger flips the sign of a.  The reference evaluates a and b in double from real_t kappa / mu and rounds them to
+ *   real_t; the loop itself runs in real_t -- restated literally so that results are bit-identical. */
+void FN(orc_twist_gamma5)(REAL *out, const REAL *in, int dagger, double kappa_, double mu_, int flavor, long V, int inverse)
+{
+  const REAL kappa = (REAL)kappa_, mu = (REAL)mu_;
+  REAL a, b;
+  if (!inverse) {
+    a = (REAL)(2.0 * kappa * mu * flavor);
+    b = (REAL)1.0;
+  } else {
+    a = (REAL)(-2.0 * kappa * mu * flavor);
+    b = (REAL)(1.0 / (1.0 + a * a));
+  }
+  if (dagger) a = (REAL)(a * -1.0);
+#pragma omp parallel for
+  for (long i = 0; i < V; i++) {
+    REAL tmp[24];
+    for (int s = 0; s < 4; s++)
+      for (int c = 0; c < 3; c++) {
+        const REAL a5 = (REAL)(((s / 2) ? -1.0 : +1.0) * a);
+        tmp[s * 6 + c * 2 + 0] = b * (in[i * 24 + s * 6 + c * 2 + 0] - a5 * in[i * 24 + s * 6 + c * 2 + 1]);
+        tmp[s * 6 + c * 2 + 1] = b * (in[i * 24 + s * 6 + c * 2 + 1] + a5 * in[i * 24 + s * 6 + c * 2 + 0]);
+      }
+    for (int j = 0; j < 24; j++) out[i * 24 + j] = tmp[j];
+  }
+}
+
+/* A^{-1} D (not dagger, or dagger with asymmetric preconditioning) or D^dagger A^{-dagger} (dagger, symmetric): ibid. :182-200.
+ * The reference twists `in` in place and undoes it afterwards; a private copy gives the same `out`. */
+void FN(orc_tm_dslash)(REAL *out, const REAL *const *gauge, const REAL *in, const int *X, double kappa, double mu,
+                       int flavor, int matpc, int parity, int dagger)
+{
+  const long Vh = (long)X[0] * X[1] * X[2] * X[3] / 2;
+  const int symmetric = (matpc == ORC_MATPC_EVEN_EVEN || matpc == ORC_MATPC_ODD_ODD);
+  if (dagger && symmetric) {
+    REAL *w = (REAL *)malloc(sizeof(REAL) * Vh * 24);
+    FN(orc_twist_gamma5)(w, in, dagger, kappa, mu, flavor, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, w, X, parity, dagger);
+    free(w);
+  } else {
+    FN(orc_wil_dslash)(out, gauge, in, X, parity, dagger);
+    FN(orc_twist_gamma5)(out, out, dagger, kappa, mu, flavor, Vh, 1);
+  }
+}
+
+/* out = (1 + i 2 kappa mu gamma5) in - kappa D in on the full lattice: ibid. :217-237 */
+void FN(orc_tm_mat)(REAL *out, const REAL *const *gauge, const REAL *in, const int *X, double kappa, double mu, int flavor,
+                    int dagger)
+{
+  const long Vh = (long)X[0] * X[1] * X[2] * X[3] / 2;
+  REAL *tmp = (REAL *)malloc(sizeof(REAL) * 2 * Vh * 24);
+  FN(orc_wil_dslash)(out + Vh * 24, gauge, in, X, 1, dagger);
+  FN(orc_wil_dslash)(out, gauge, in + Vh * 24, X, 0, dagger);
+  FN(orc_twist_gamma5)(tmp, in, dagger, kappa, mu, flavor, 2 * Vh, 0);
+  FN(orc_xpay)(tmp, -kappa, out, 2 * Vh * 24);
+  free(tmp);
+}
+
+/* Even-odd preconditioned twisted-mass operator, all four matpc types x dagger: ibid. :262-315.  In the symmetric dagger
+ * case the reference twists its input in place and untwists it again before the final xpay, so that xpay sees the
+ * round-tripped (not the pristine) input; `w` reproduces exactly that. */
+void FN(orc_tm_matpc)(REAL *out, const REAL *const *gauge, const REAL *in, const int *X, double kappa, double mu, int flavor,
+                      int matpc, int dagger)
+{
+  const long Vh = (long)X[0] * X[1] * X[2] * X[3] / 2;
+  REAL *tmp = (REAL *)malloc(sizeof(REAL) * Vh * 24);
+  REAL *w = (REAL *)malloc(sizeof(REAL) * Vh * 24);
+  memcpy(w, in, sizeof(REAL) * Vh * 24);
+  const int p = (matpc == ORC_MATPC_EVEN_EVEN || matpc == ORC_MATPC_EVEN_EVEN_ASYM) ? 0 : 1;
+  const int asym = (matpc == ORC_MATPC_EVEN_EVEN_ASYM || matpc == ORC_MATPC_ODD_ODD_ASYM);
+  if (asym) {
+    FN(orc_wil_dslash)(tmp, gauge, w, X, 1 - p, dagger);
+    FN(orc_twist_gamma5)(tmp, tmp, dagger, kappa, mu, flavor, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, X, p, dagger);
+    FN(orc_twist_gamma5)(tmp, w, dagger, kappa, mu, flavor, Vh, 0);
+    FN(orc_xpay)(tmp, -kappa * kappa, out, Vh * 24);
+  } else if (!dagger) {
+    FN(orc_wil_dslash)(tmp, gauge, w, X, 1 - p, dagger);
+    FN(orc_twist_gamma5)(tmp, tmp, dagger, kappa, mu, flavor, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, X, p, dagger);
+    FN(orc_twist_gamma5)(out, out, dagger, kappa, mu, flavor, Vh, 1);
+    FN(orc_xpay)(w, -kappa * kappa, out, Vh * 24);
+  } else {
+    FN(orc_twist_gamma5)(w, w, dagger, kappa, mu, flavor, Vh, 1);
+    FN(orc_wil_dslash)(tmp, gauge, w, X, 1 - p, dagger);
+    FN(orc_twist_gamma5)(tmp, tmp, dagger, kappa, mu, flavor, Vh, 1);
+    FN(orc_wil_dslash)(out, gauge, tmp, X, p, dagger);
+    FN(orc_twist_gamma5)(w, w, dagger, kappa, mu, flavor, Vh, 0);
+    FN(orc_xpay)(w, -kappa * kappa, out, Vh * 24);
+  }
+  free(tmp);
+  free(w);
+}
+
 /*
  * Inverse of every chiral block (same packed order in and out).  The reference inverts on the
  * device (lib/clover_invert.cu, include/kernels/clover_invert.cuh: Cholesky of the Hermitian block);

@@ -13,7 +13,9 @@ namespace b200
 {
 
   enum KernelType { K_INTERIOR = 0, K_EXTERIOR_ALL = 1, K_FULL = 2 };
-  enum OpType { OP_WILSON = 0, OP_CLOVER = 1, OP_CLOVER_PC = 2 };
+  // OP_TM / OP_TM_PC / OP_TM_PC_PRE: the degenerate twisted-mass epilogues on the same stencil
+  // (include/kernels/dslash_twisted_mass.cuh:33-70, dslash_twisted_mass_preconditioned.cuh:48-175)
+  enum OpType { OP_WILSON = 0, OP_CLOVER = 1, OP_CLOVER_PC = 2, OP_TM = 3, OP_TM_PC = 4, OP_TM_PC_PRE = 5 };
 
   constexpr int kMaxParity = 2;
 
@@ -27,7 +29,7 @@ namespace b200
     GhostView<P> ghost[4][2]; // received half spinors: [dim][0 = from the backward neighbour, 1 = from the forward one]
     size_t ghost_parity_stride[4]; // elements of P::store between the parity-0 and parity-1 halves of a face buffer
     size_t ghost_norm_parity_stride[4];
-    real a;                   // xpay coefficient
+    real a;                   // xpay coefficient (twisted-mass preconditioned ops: the scale of the twist rotation)
     int n_parity;             // 1: `parity` only; 2: both (blockIdx.y / loop selects)
     int parity;
     int comm_dim[4];          // dimension d is partitioned: hops across its boundary come from ghost[d]
@@ -35,6 +37,10 @@ namespace b200
     const unsigned *wait_flag[4][2]; // arrival flags written by the neighbours' pack kernels (nullptr: stream-ordered)
     unsigned seq;             // value the flags must have reached
     int *timeout_flag;        // set to 1 if a wait gives up
+    // Twisted-mass ops have no clover term: their twist factor (sign already flipped for dagger) travels in the unused
+    // clover slot A.diagonal.  Adding a field would change sizeof(DslashArgs), shift the kernel parameters behind it and
+    // make ptxas re-schedule the Wilson / clover kernels that were measured on hardware (checked with cuobjdump).
+    B2_HD real twist_b() const { return A.diagonal; }
   };
 
   // CTA -> 4-d tile of checkerboard sites, thread -> site inside the tile (x fastest so that a warp's 16-byte plane
@@ -175,9 +181,28 @@ namespace b200
     static constexpr bool value = B2_PRELOAD_LINKS && (sizeof(typename GaugeView<P, recon>::Raw) <= 48);
   };
 
+  // v <- s (v + b i gamma5 v).  In the UKQCD basis gamma5 exchanges the spin pairs: (i gamma5 v)_s = i v_{s +- 2}
+  // (include/color_spinor.h:254-262, igamma(4)).
+  template <typename real> B2_HD void twist_apply(real *v, real s, real b)
+  {
+#pragma unroll
+    for (int sp = 0; sp < 2; sp++) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const int u = (sp * 3 + c) * 2, l = ((sp + 2) * 3 + c) * 2;
+        const real ur = v[u], ui = v[u + 1], lr = v[l], li = v[l + 1];
+        v[u] = s * (ur - b * li);
+        v[u + 1] = s * (ui + b * lr);
+        v[l] = s * (lr - b * ui);
+        v[l + 1] = s * (li + b * ur);
+      }
+    }
+  }
+
   // `in` is passed explicitly so that the multi-RHS kernels can aim the same code at any source; `lc` is the cache
-  // policy of the link loads
-  template <class P, int recon, bool dagger, bool fwd, Cache lc = Cache::STREAM>
+  // policy of the link loads; `pretwist`: the neighbour spinor is rotated by a (1 + i b gamma5) before it is projected
+  // (symmetric preconditioned twisted-mass dagger, applyWilsonTM)
+  template <class P, int recon, bool dagger, bool fwd, Cache lc = Cache::STREAM, bool pretwist = false>
   B2_HD void hop_from(typename P::real *r, const DslashArgs<P, recon> &arg, const SpinorView<P> &in, const int *x, int x_cb,
                       int parity, int d, const typename GaugeView<P, recon>::Raw *raw = nullptr)
   {
@@ -192,7 +217,12 @@ namespace b200
       arg.U.template load<lc>(u, d, x_cb, parity);
     else
       arg.U.template load<lc>(u, d, n_cb, 1 - parity);
-    if (d == 3) {
+    if constexpr (pretwist) { // gamma5 mixes the spin pairs: the full spinor is needed in every direction
+      real v[24];
+      in.load(v, n_cb);
+      twist_apply(v, arg.a, arg.twist_b());
+      project(h, v, d, sign);
+    } else if (d == 3) {
       real t[12];
       load_spin_pair<P, (sign > 0)>(t, in, n_cb);
 #pragma unroll
@@ -224,7 +254,7 @@ namespace b200
   };
 
   // r = (U or U^dagger) P h with everything unscaled; `scale` is the factor the result still has to be multiplied by
-  template <class P, int recon, bool dagger, bool fwd, Cache lc = Cache::STREAM>
+  template <class P, int recon, bool dagger, bool fwd, Cache lc = Cache::STREAM, bool pretwist = false>
   B2_HD void hop_from_deferred(typename P::real *r, typename P::real &scale, const DslashArgs<P, recon> &arg,
                                const SpinorView<P> &in, const int *x, int x_cb, int parity, int d,
                                const typename GaugeView<P, recon>::Raw *raw = nullptr)
@@ -242,7 +272,13 @@ namespace b200
       arg.U.unpack_deferred(u, us, w, d, fwd ? x_cb : n_cb);
     }
     const real n = in.load_norm(n_cb);
-    if (d == 3) {
+    if constexpr (pretwist) { // the rotation is linear, so it commutes with the deferred scale; project() carries t's factor 2
+      real v[24];
+      in.template load_planes<0, 24 / P::Ns>(v, n_cb);
+      twist_apply(v, arg.a, arg.twist_b());
+      project(h, v, d, sign);
+      scale = us * n;
+    } else if (d == 3) {
       load_spin_pair<P, (sign > 0), Cache::REUSE, false>(h, in, n_cb);
       scale = (us * n) * (real)2;
     } else {
@@ -255,7 +291,7 @@ namespace b200
   }
 
   // acc += hop (+ optional 0/1 mask for the masked interior kernel); every local hop of every kernel goes through here
-  template <class P, int recon, bool dagger, bool fwd, bool masked, Cache lc = Cache::STREAM>
+  template <class P, int recon, bool dagger, bool fwd, bool masked, Cache lc = Cache::STREAM, bool pretwist = false>
   B2_HD void hop_add(typename P::real *acc, const DslashArgs<P, recon> &arg, const SpinorView<P> &in, const int *x, int x_cb,
                      int parity, int d, const typename GaugeView<P, recon>::Raw *raw, typename P::real mask)
   {
@@ -264,11 +300,11 @@ namespace b200
     real r[12];
     if constexpr (DeferredScale<P>::value) {
       real scale;
-      hop_from_deferred<P, recon, dagger, fwd, lc>(r, scale, arg, in, x, x_cb, parity, d, raw);
+      hop_from_deferred<P, recon, dagger, fwd, lc, pretwist>(r, scale, arg, in, x, x_cb, parity, d, raw);
       if constexpr (masked) scale *= mask;
       reconstruct_add_scaled(acc, r, d, sign, scale);
     } else {
-      hop_from<P, recon, dagger, fwd, lc>(r, arg, in, x, x_cb, parity, d, raw);
+      hop_from<P, recon, dagger, fwd, lc, pretwist>(r, arg, in, x, x_cb, parity, d, raw);
       if constexpr (masked) {
 #pragma unroll
         for (int i = 0; i < 12; i++) r[i] *= mask;
@@ -305,7 +341,7 @@ namespace b200
   //   kt == K_EXTERIOR_ALL : only hops that cross a partitioned boundary, sources read from the ghost buffers
   //   kt == K_FULL         : all 8 hops, each from the ghost buffer if it crosses a partitioned face, else local --
   //                          used for the boundary tiles once the halo has arrived (no read-modify-write pass)
-  template <class P, int recon, bool dagger, KernelType kt, bool part = true>
+  template <class P, int recon, bool dagger, KernelType kt, bool part = true, bool pretwist = false>
   B2_HD void wilson_hops(typename P::real *acc, const DslashArgs<P, recon> &arg, const int *x, int x_cb, int parity)
   {
     using real = typename P::real;
@@ -326,8 +362,8 @@ namespace b200
         const bool ghost = (x[d] + 1 >= g.X[d]) && arg.comm_dim[d];
         real r[12];
         if constexpr (kt == K_INTERIOR) {
-          hop_add<P, recon, dagger, true, part>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d, preload ? &raw[2 * d] : nullptr,
-                                                ghost ? (real)0 : (real)1);
+          hop_add<P, recon, dagger, true, part, Cache::STREAM, pretwist>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d,
+                                                                         preload ? &raw[2 * d] : nullptr, ghost ? (real)0 : (real)1);
         } else if constexpr (kt == K_EXTERIOR_ALL) {
           if (ghost) {
             hop_ghost<P, recon, true>(r, arg, x, x_cb, parity, d);
@@ -353,8 +389,8 @@ namespace b200
         const bool ghost = (x[d] - 1 < 0) && arg.comm_dim[d];
         real r[12];
         if constexpr (kt == K_INTERIOR) {
-          hop_add<P, recon, dagger, false, part>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d,
-                                                 preload ? &raw[2 * d + 1] : nullptr, ghost ? (real)0 : (real)1);
+          hop_add<P, recon, dagger, false, part, Cache::STREAM, pretwist>(acc, arg, arg.in[1 - parity], x, x_cb, parity, d,
+                                                                          preload ? &raw[2 * d + 1] : nullptr, ghost ? (real)0 : (real)1);
         } else if constexpr (kt == K_EXTERIOR_ALL) {
           if (ghost) {
             hop_ghost<P, recon, false>(r, arg, x, x_cb, parity, d);
@@ -401,17 +437,26 @@ namespace b200
     real acc[24];
 #pragma unroll
     for (int i = 0; i < 24; i++) acc[i] = 0;
-    wilson_hops<P, recon, dagger, K_INTERIOR, part>(acc, arg, x, x_cb, parity);
+    wilson_hops<P, recon, dagger, K_INTERIOR, part, op == OP_TM_PC_PRE>(acc, arg, x, x_cb, parity);
 
     const bool complete = part ? site_is_interior(arg, x) : true;
     if constexpr (op == OP_CLOVER_PC) {
       if (complete) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
     }
+    if constexpr (op == OP_TM_PC) {
+      if (complete) twist_apply(acc, arg.a, arg.twist_b()); // a (1 + i b gamma5) D in
+    }
     if constexpr (xpay) {
       real xv[24];
       arg.x[parity].template load<Cache::STREAM>(xv, x_cb);
       if constexpr (op == OP_CLOVER) clover_apply_site<P, false>(xv, arg.A, x_cb, parity);
-      if (op != OP_CLOVER_PC || complete) {
+      if constexpr (op == OP_TM) twist_apply(xv, (real)1, arg.twist_b()); // (1 + i b gamma5) x + a D in
+      if constexpr (op == OP_TM_PC || op == OP_TM_PC_PRE) { // `a` is the rotation's scale here: plain x + ...
+        if (complete) {
+#pragma unroll
+          for (int i = 0; i < 24; i++) acc[i] = xv[i] + acc[i];
+        }
+      } else if (op != OP_CLOVER_PC || complete) {
 #pragma unroll
         for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
       }
@@ -433,12 +478,14 @@ namespace b200
     for (int i = 0; i < 24; i++) acc[i] = 0;
     wilson_hops<P, recon, dagger, K_FULL>(acc, arg, x, x_cb, parity);
     if constexpr (op == OP_CLOVER_PC) clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+    if constexpr (op == OP_TM_PC) twist_apply(acc, arg.a, arg.twist_b());
     if constexpr (xpay) {
       real xv[24];
       arg.x[parity].template load<Cache::STREAM>(xv, x_cb);
       if constexpr (op == OP_CLOVER) clover_apply_site<P, false>(xv, arg.A, x_cb, parity);
+      if constexpr (op == OP_TM) twist_apply(xv, (real)1, arg.twist_b());
 #pragma unroll
-      for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
+      for (int i = 0; i < 24; i++) acc[i] = xv[i] + (op == OP_TM_PC ? acc[i] : arg.a * acc[i]);
     }
     arg.out[parity].save(acc, x_cb);
   }
@@ -611,15 +658,18 @@ namespace b200
     wilson_hops<P, recon, dagger, K_EXTERIOR_ALL>(acc, arg, x, x_cb, parity);
     real partial[24];
     arg.out[parity].template load<Cache::STREAM>(partial, x_cb);
-    if constexpr (op == OP_CLOVER_PC) {
+    if constexpr (op == OP_CLOVER_PC || op == OP_TM_PC) {
 #pragma unroll
       for (int i = 0; i < 24; i++) acc[i] += partial[i];
-      clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+      if constexpr (op == OP_CLOVER_PC)
+        clover_apply_site<P, true>(acc, arg.A, x_cb, parity);
+      else
+        twist_apply(acc, arg.a, arg.twist_b());
       if constexpr (xpay) {
         real xv[24];
         arg.x[parity].template load<Cache::STREAM>(xv, x_cb);
 #pragma unroll
-        for (int i = 0; i < 24; i++) acc[i] = xv[i] + arg.a * acc[i];
+        for (int i = 0; i < 24; i++) acc[i] = xv[i] + (op == OP_TM_PC ? acc[i] : arg.a * acc[i]);
       }
     } else {
 #pragma unroll

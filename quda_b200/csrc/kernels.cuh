@@ -524,6 +524,14 @@ namespace b200
       else
         return xp ? launch_config<P, recon, false, true, OP_CLOVER_PC>(rq, arg) :
                     launch_config<P, recon, false, false, OP_CLOVER_PC>(rq, arg);
+    case OP_TM: // xpay form only
+      return dg ? launch_config<P, recon, true, true, OP_TM>(rq, arg) : launch_config<P, recon, false, true, OP_TM>(rq, arg);
+    case OP_TM_PC:
+      if (dg && !rq.asymmetric) // symmetric dagger: the rotation acts on the neighbour spinors before the hop
+        return xp ? launch_config<P, recon, true, true, OP_TM_PC_PRE>(rq, arg) :
+                    launch_config<P, recon, true, false, OP_TM_PC_PRE>(rq, arg);
+      if (dg) return launch_config<P, recon, true, false, OP_TM_PC>(rq, arg); // asymmetric dagger (never xpay)
+      return xp ? launch_config<P, recon, false, true, OP_TM_PC>(rq, arg) : launch_config<P, recon, false, false, OP_TM_PC>(rq, arg);
     }
     return set_error(B200_ERR_INVALID, "unknown op %d", rq.op);
   }

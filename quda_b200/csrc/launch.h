@@ -18,6 +18,8 @@ namespace b200
   struct LaunchRequest {
     int op, kernel, reconstruct, dagger, xpay, parity, n_parity;
     int X[4], tile[4];
+    double b;       // twisted mass: twist factor as passed by the caller (the dagger sign flip happens in fill_args)
+    int asymmetric; // twisted-mass preconditioned: asymmetric variant
     int march_t; // > 0: every CTA walks `march_t` consecutive time slices with its (x,y,z) tile (L1 reuse of the slices)
     double a;
     b200_spinor out, in, x;
@@ -128,6 +130,8 @@ namespace b200
     arg.n_parity = rq.n_parity;
     arg.parity = rq.parity;
     arg.a = (typename P::real)rq.a;
+    arg.A = CloverView<P> {};
+    arg.A.diagonal = (typename P::real)(rq.dagger ? -rq.b : rq.b); // twist_b(); dslash_twisted_mass.cuh:27: "if dagger flip the twist"
     if (rq.out.volume_cb != g.volume_cb || rq.in.volume_cb != g.volume_cb)
       return set_error(B200_ERR_INVALID, "spinor volume_cb (%d/%d) does not match lattice (%d)", rq.out.volume_cb,
                        rq.in.volume_cb, g.volume_cb);
@@ -151,7 +155,7 @@ namespace b200
     m.t_bound_cb = (g.X[3] - 1) * g.X[0] * g.X[1] * g.X[2] / 2;
     m.volume_cb = g.volume_cb;
     arg.U.init(rq.U.gauge, rq.U.parity_stride_bytes, rq.U.stride, m);
-    if (rq.op != OP_WILSON) fill_clover(arg.A, rq.A, g.volume_cb);
+    if (rq.op == OP_CLOVER || rq.op == OP_CLOVER_PC) fill_clover(arg.A, rq.A, g.volume_cb);
     arg.threads_ext[0] = 0;
     for (int d = 0; d < 4; d++) {
       arg.comm_dim[d] = rq.halo.comm_dim[d] ? 1 : 0;
@@ -285,9 +289,21 @@ namespace b200
       return set_error(B200_ERR_INVALID, "out/in site subsets differ or are invalid (%d/%d)", a->out.n_parity, a->in.n_parity);
     if (a->out.n_parity == 1 && a->parity != 0 && a->parity != 1)
       return set_error(B200_ERR_INVALID, "parity %d invalid for single-parity fields", a->parity);
-    if (a->op != B200_OP_WILSON && a->op != B200_OP_CLOVER && a->op != B200_OP_CLOVER_PC)
-      return set_error(B200_ERR_INVALID, "unknown op %d", a->op);
-    if (a->op != B200_OP_WILSON && !a->A.clover) return set_error(B200_ERR_INVALID, "clover operator without clover field");
+    if (a->op < B200_OP_WILSON || a->op > B200_OP_TWISTED_MASS_PC) return set_error(B200_ERR_INVALID, "unknown op %d", a->op);
+    const bool clover_op = a->op == B200_OP_CLOVER || a->op == B200_OP_CLOVER_PC;
+    if (clover_op && !a->A.clover) return set_error(B200_ERR_INVALID, "clover operator without clover field");
+    bool any_comm_tm = false;
+    for (int d = 0; d < 4; d++) any_comm_tm |= (a->halo.comm_dim[d] != 0);
+    if (a->op == B200_OP_TWISTED_MASS && a->a == 0.0)
+      return set_error(B200_ERR_INVALID, "Twisted-mass operator only defined for xpay=true (a != 0)"); // lib/dslash_twisted_mass.cu
+    if (a->op == B200_OP_TWISTED_MASS_PC) { // lib/dslash_twisted_mass_preconditioned.cu:41-43
+      if (a->asymmetric && !a->dagger) return set_error(B200_ERR_INVALID, "asymmetric operator only defined for dagger");
+      if (a->asymmetric && a->x.v) return set_error(B200_ERR_INVALID, "asymmetric operator not defined for xpay");
+      if (a->out.n_parity != 1) return set_error(B200_ERR_INVALID, "Preconditioned twisted-mass operator not defined nParity=2");
+      if (a->dagger && !a->asymmetric && any_comm_tm)
+        return set_error(B200_ERR_UNSUPPORTED, "symmetric preconditioned twisted-mass dagger on a partitioned lattice needs the "
+                                               "twist in the pack kernel: not built");
+    }
     if (a->op == B200_OP_CLOVER_PC && a->out.n_parity != 1)
       return set_error(B200_ERR_INVALID, "preconditioned clover operator only defined on single-parity fields");
     if (a->op == B200_OP_CLOVER_PC && a->a != 0.0 && a->dagger)
@@ -298,8 +314,10 @@ namespace b200
     rq.kernel = a->kernel;
     rq.reconstruct = a->U.reconstruct;
     rq.dagger = a->dagger ? 1 : 0;
-    rq.xpay = (a->a != 0.0) ? 1 : 0;
+    rq.xpay = (a->op == B200_OP_TWISTED_MASS_PC) ? (a->x.v != nullptr) : (a->a != 0.0);
     rq.a = a->a;
+    rq.b = a->b;
+    rq.asymmetric = a->asymmetric ? 1 : 0;
     rq.parity = a->parity;
     rq.n_parity = a->out.n_parity;
     for (int d = 0; d < 4; d++) rq.X[d] = a->X[d];
@@ -363,7 +381,7 @@ namespace b200
     rq.x = x;
     bool any_comm = false;
     for (int d = 0; d < 4; d++) any_comm |= (a->halo.comm_dim[d] != 0);
-    batched = !any_comm && a->kernel == B200_KERNEL_AUTO;
+    batched = !any_comm && a->kernel == B200_KERNEL_AUTO && a->op <= B200_OP_CLOVER_PC;
     return 0;
   }
 

@@ -99,7 +99,7 @@ class Halo:
 
 
 def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=None, kernel=L.KERNEL_AUTO, tile=None,
-           stream=None, backend=None):
+           stream=None, backend=None, b=0.0, asymmetric=False):
     be = backend or cuda_backend()
     multi = isinstance(out, (list, tuple))  # the reference's cvector_ref batch: sources sharing U (and A)
     if multi:
@@ -117,6 +117,7 @@ def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=No
     args.parity = 0 if parity == QUDA_INVALID_PARITY else parity
     args.dagger = int(bool(dagger))
     args.a = float(a)
+    args.b, args.asymmetric = float(b), int(bool(asymmetric))
     args.out, args.in_ = out.desc(), in_.desc()
     if x is not None:
         args.x = x.desc()
@@ -149,6 +150,19 @@ def ApplyWilsonClover(out, in_, U, A, a, x, parity, dagger, comm_override=None, 
 def ApplyWilsonCloverPreconditioned(out, in_, U, A, a, x, parity, dagger, comm_override=None, halo=None, **kw):
     """out = A^-1 D in (a == 0) or x + a A^-1 D in.  Reference: lib/dslash_wilson_clover_preconditioned.cu:13-27."""
     _apply(L.OP_CLOVER_PC, out, in_, U, a, x, parity, dagger, comm_override, A=A, halo=halo, **kw)
+
+
+def ApplyTwistedMass(out, in_, U, a, b, x, parity, dagger, comm_override=None, halo=None, **kw):
+    """out = a D in + (1 + i b gamma5) x (xpay form only; b is negated for dagger).
+    Reference: include/dslash_quda.h:363-365, include/kernels/dslash_twisted_mass.cuh:33-70."""
+    _apply(L.OP_TWISTED_MASS, out, in_, U, a, x, parity, dagger, comm_override, halo=halo, b=b, **kw)
+
+
+def ApplyTwistedMassPreconditioned(out, in_, U, a, b, xpay, x, parity, dagger, asymmetric, comm_override=None, halo=None, **kw):
+    """out = a (1 + i b gamma5) D in [+ x]; for dagger without `asymmetric`: out = D^dagger a (1 - i b gamma5) in [+ x].
+    Reference: include/dslash_quda.h:403-406, include/kernels/dslash_twisted_mass_preconditioned.cuh:121-175."""
+    _apply(L.OP_TWISTED_MASS_PC, out, in_, U, a, x if xpay else None, parity, dagger, comm_override, halo=halo, b=b,
+           asymmetric=asymmetric, **kw)
 
 
 def ApplyClover(out, in_, A, inverse, parity, stream=None, backend=None):

@@ -8,10 +8,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200_LIB lets the tuning tools load an alternative build of the same library (e.g. another occupancy target)
 LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libquda_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DOUBLE, SINGLE, HALF = 8, 4, 2
-OP_WILSON, OP_CLOVER, OP_CLOVER_PC = 0, 1, 2
+OP_WILSON, OP_CLOVER, OP_CLOVER_PC, OP_TWISTED_MASS, OP_TWISTED_MASS_PC = 0, 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_INTERIOR, KERNEL_EXTERIOR, KERNEL_INTERIOR_TILES, KERNEL_BOUNDARY_TILES = 0, 1, 2, 3, 4
 
 
@@ -43,6 +43,7 @@ class Halo(C.Structure):
 class DslashArgs(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("op", C.c_int), ("kernel", C.c_int), ("precision", C.c_int),
                 ("X", C.c_int * 4), ("parity", C.c_int), ("dagger", C.c_int), ("a", C.c_double),
+                ("b", C.c_double), ("asymmetric", C.c_int),
                 ("out", Spinor), ("in_", Spinor), ("x", Spinor), ("U", Gauge), ("A", Clover), ("halo", Halo),
                 ("tile", C.c_int * 4), ("stream", C.c_void_p)]
 

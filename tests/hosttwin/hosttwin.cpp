@@ -135,6 +135,12 @@ namespace b200
     case OP_CLOVER_PC:
       if (dg) { if (xp) GO(true, true, OP_CLOVER_PC); else GO(true, false, OP_CLOVER_PC); }
       else { if (xp) GO(false, true, OP_CLOVER_PC); else GO(false, false, OP_CLOVER_PC); }
+    case OP_TM:
+      if (dg) GO(true, true, OP_TM); else GO(false, true, OP_TM);
+    case OP_TM_PC:
+      if (dg && !rq.asymmetric) { if (xp) GO(true, true, OP_TM_PC_PRE); else GO(true, false, OP_TM_PC_PRE); }
+      if (dg) GO(true, false, OP_TM_PC);
+      if (xp) GO(false, true, OP_TM_PC); else GO(false, false, OP_TM_PC);
     }
 #undef GO
     return set_error(B200_ERR_INVALID, "unknown op");

@@ -62,6 +62,73 @@ def check_clover(mem, be, prec, recon, compressed, dynamic, X=(4, 4, 6, 4)):
         assert_close(ref, P.to_host(out), prec, tolr, "clover-pc xpay")
 
 
+def check_twisted_mass(mem, be, prec, recon, X=(4, 6, 4, 8), comm_dim=None):
+    """Degenerate twisted mass: ApplyTwistedMass / ApplyTwistedMassPreconditioned and their composition into the
+    even-odd preconditioned operator for all four matpc types (lib/dirac_twisted_mass.cpp:47-237) against the oracle's
+    tm_dslash / tm_mat / tm_matpc (tests/host_reference/wilson_dslash_reference.cpp:139-315)."""
+    P = Problem(X, prec, recon, mem)
+    kappa, mu = 0.12195, 0.1
+    s, xs = P.spinor(seed=41), P.spinor(seed=42)
+    f64 = np.float64
+    b_tw = 2 * mu * kappa                 # direct twist
+    a_inv = -2.0 * kappa * mu             # inverse twist
+    scale = 1.0 / (1.0 + a_inv * a_inv)
+
+    def halo_for(field, in_parity, dagger):
+        if comm_dim is None:
+            return None
+        h = self_halo(P, mem, comm_dim)
+        self_exchange(P, h, field, in_parity, dagger, be)
+        return h
+
+    for parity, dagger in itertools.product((0, 1), (0, 1)):
+        din = P.to_dev(s)
+        # ApplyTwistedMass: a D in + (1 + i b gamma5) x
+        out = P.empty()
+        D.ApplyTwistedMass(out, din, P.U, -kappa, b_tw, P.to_dev(xs), parity, dagger, halo=halo_for(din, 1 - parity, dagger),
+                           backend=be)
+        ref = oracle.twist_gamma5(xs, kappa, mu, dagger).astype(f64) - kappa * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(f64)
+        assert_close(ref, P.to_host(out), prec, recon, f"ApplyTwistedMass p={parity} dag={dagger}")
+        # ApplyTwistedMassPreconditioned as DiracTwistedMassPC::Dslash / DslashXpay call it
+        for matpc in range(4):
+            asym = matpc >= 2 and dagger
+            if comm_dim is not None and dagger and not asym:
+                continue  # needs the twist in the pack kernel (rejected with B200_ERR_UNSUPPORTED, checked elsewhere)
+            out = P.empty()
+            D.ApplyTwistedMassPreconditioned(out, din, P.U, scale, a_inv, False, None, parity, dagger, asym,
+                                             halo=halo_for(din, 1 - parity, dagger), backend=be)
+            ref = oracle.tm_dslash(P.gauge, s, X, kappa, mu, parity, dagger, matpc).astype(f64)
+            assert_close(ref, P.to_host(out), prec, recon, f"tm_dslash matpc={matpc} p={parity} dag={dagger}")
+            if not asym:
+                k = -kappa * kappa
+                out = P.empty()
+                D.ApplyTwistedMassPreconditioned(out, din, P.U, k * scale, a_inv, True, P.to_dev(xs), parity, dagger, False,
+                                                 halo=halo_for(din, 1 - parity, dagger), backend=be)
+                assert_close(xs.astype(f64) + k * ref, P.to_host(out), prec, recon, f"tm_dslash xpay matpc={matpc} dag={dagger}")
+    if comm_dim is not None:
+        return
+    # composition: DiracTwistedMassPC::M
+    for matpc, dagger in itertools.product(range(4), (0, 1)):
+        this = 0 if matpc in (0, 2) else 1
+        other = 1 - this
+        asym = matpc >= 2 and dagger
+        din, tmp, out = P.to_dev(s), P.empty(), P.empty()
+        D.ApplyTwistedMassPreconditioned(tmp, din, P.U, scale, a_inv, False, None, other, dagger, asym, backend=be)
+        k2 = -kappa * kappa
+        if matpc < 2:
+            D.ApplyTwistedMassPreconditioned(out, tmp, P.U, k2 * scale, a_inv, True, din, this, dagger, False, backend=be)
+        else:
+            D.ApplyTwistedMass(out, tmp, P.U, k2, b_tw, din, this, dagger, backend=be)
+        ref = oracle.tm_matpc(P.gauge, s, X, kappa, mu, matpc, dagger)
+        assert_close(ref, P.to_host(out), prec, recon, f"tm_matpc matpc={matpc} dag={dagger}")
+    # full operator through full fields
+    full = P.spinor(seed=43, nparity=2)
+    for dagger in (0, 1):
+        out, inp = P.empty(2), P.to_dev(full, 2)
+        D.ApplyTwistedMass(out, inp, P.U, -kappa, b_tw, inp, D.QUDA_INVALID_PARITY, dagger, backend=be)
+        assert_close(oracle.tm_mat(P.gauge, full, X, kappa, mu, dagger), P.to_host(out), prec, recon, "tm_mat")
+
+
 def check_multi_rhs(mem, be, prec, recon, n_src, op="wilson", xpay=False, dagger=0, X=(4, 6, 4, 8), nparity=1, comm_dim=None,
                     tile=None):
     """The reference's cvector_ref form: n_src sources sharing U (and A) in one call.  Every source is checked against

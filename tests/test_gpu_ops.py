@@ -104,3 +104,14 @@ def test_multi_rhs_cta_flavour_clover_and_full(monkeypatch):
     ops.check_multi_rhs(CudaMem, None, 4, 12, 3, op="clover_pc", xpay=True)
     ops.check_multi_rhs(CudaMem, None, 2, 12, 3, op="clover", xpay=True, tile=(2, 2, 1, 1))
     ops.check_multi_rhs(CudaMem, None, 4, 12, 4, xpay=True, nparity=2, tile=(2, 2, 2, 2))
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (4, 8), (2, 12)])
+def test_twisted_mass(prec, recon):
+    """degenerate twisted mass (ApplyTwistedMass / ApplyTwistedMassPreconditioned + the DiracTwistedMassPC composition,
+    all four matpc types x dagger) against the oracle's tm_dslash / tm_mat / tm_matpc"""
+    ops.check_twisted_mass(CudaMem, None, prec, recon)
+
+
+def test_twisted_mass_partitioned():
+    ops.check_twisted_mass(CudaMem, None, 4, 12, X=(4, 4, 4, 4), comm_dim=(1, 0, 1, 1))

@@ -98,3 +98,24 @@ def test_compare_spinor_metric():
     b[7] += 3e-6 * np.abs(a).max()
     lvl, dev, fails = oracle.compare_spinor(a, b)
     assert lvl == 5 and fails[5] == 1 and fails[4] == 0
+
+
+@pytest.mark.parametrize("X", DIMS[:3])
+@pytest.mark.parametrize("prec", [8, 4])
+def test_twisted_mass_operators_bit_identical(X, prec):
+    """twist_gamma5 / tm_dslash / tm_mat / tm_matpc (wilson_dslash_reference.cpp:139-315), singlet flavour, all four
+    matpc types, both parities, dagger"""
+    R = oracle.Reference(X)
+    g = oracle.random_gauge(X, prec, seed=137)
+    s = oracle.random_spinor(X, prec, seed=21)
+    full = oracle.random_spinor(X, prec, seed=22, nparity=2)
+    kappa, mu = 0.12195, 0.1
+    for dagger in (0, 1):
+        for inverse in (False, True):
+            assert np.array_equal(R.twist_gamma5(s, kappa, mu, dagger, inverse), oracle.twist_gamma5(s, kappa, mu, dagger, inverse))
+        for matpc in range(4):
+            for parity in (0, 1):
+                assert np.array_equal(R.tm_dslash(g, s, kappa, mu, parity, dagger, matpc),
+                                      oracle.tm_dslash(g, s, X, kappa, mu, parity, dagger, matpc))
+            assert np.array_equal(R.tm_matpc(g, s, kappa, mu, matpc, dagger), oracle.tm_matpc(g, s, X, kappa, mu, matpc, dagger))
+        assert np.array_equal(R.tm_mat(g, full, kappa, mu, dagger), oracle.tm_mat(g, full, X, kappa, mu, dagger))

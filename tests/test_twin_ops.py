@@ -124,3 +124,33 @@ def test_multi_rhs_cta_flavour_clover_and_full(monkeypatch):
     ops.check_multi_rhs(HostMem, be, 4, 12, 3, op="clover_pc", xpay=True)
     ops.check_multi_rhs(HostMem, be, 2, 12, 3, op="clover", xpay=True, tile=(2, 2, 1, 1))
     ops.check_multi_rhs(HostMem, be, 4, 12, 4, xpay=True, nparity=2, tile=(2, 2, 2, 2))
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 18), (8, 12), (4, 12), (4, 8), (2, 18), (2, 12)])
+def test_twisted_mass(prec, recon):
+    """degenerate twisted mass: ApplyTwistedMass / ApplyTwistedMassPreconditioned + the PC operator composition"""
+    ops.check_twisted_mass(HostMem, twin_backend(), prec, recon)
+
+
+@pytest.mark.parametrize("comm_dim", [(0, 0, 0, 1), (1, 1, 1, 1)])
+@pytest.mark.parametrize("prec", [8, 2])
+def test_twisted_mass_partitioned(prec, comm_dim):
+    ops.check_twisted_mass(HostMem, twin_backend(), prec, 12, X=(4, 4, 4, 4), comm_dim=comm_dim)
+
+
+def test_twisted_mass_argument_checks():
+    from common import Problem
+    from quda_b200 import dslash as D
+    from quda_b200.lib import B200Error
+    be = twin_backend()
+    P = Problem((4, 4, 4, 4), 4, 12, HostMem)
+    s, out = P.to_dev(P.spinor(seed=1)), P.empty()
+    with pytest.raises(B200Error, match="only defined for xpay"):
+        D.ApplyTwistedMass(out, s, P.U, 0.0, 0.1, s, 0, 0, backend=be)
+    with pytest.raises(B200Error, match="only defined for dagger"):
+        D.ApplyTwistedMassPreconditioned(out, s, P.U, 1.0, 0.1, False, None, 0, 0, True, backend=be)
+    with pytest.raises(B200Error, match="not defined for xpay"):
+        D.ApplyTwistedMassPreconditioned(out, s, P.U, 1.0, 0.1, True, P.to_dev(P.spinor(seed=2)), 0, 1, True, backend=be)
+    h = ops.self_halo(P, HostMem, (0, 0, 0, 1))
+    with pytest.raises(B200Error, match="pack kernel"):
+        D.ApplyTwistedMassPreconditioned(out, s, P.U, 1.0, 0.1, False, None, 0, 1, False, halo=h, backend=be)
