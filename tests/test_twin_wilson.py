@@ -53,3 +53,18 @@ def test_time_marching_launch(monkeypatch, prec, recon, march):
     import ops
     monkeypatch.setenv("B200_MARCH_T", str(march))
     ops.check_xpay_fullfield(HostMem, twin_backend(), prec, recon, X=(4, 4, 4, 6))
+
+
+@pytest.mark.parametrize("X", [(2, 2, 2, 2), (2, 4, 2, 6), (4, 2, 2, 2), (16, 2, 4, 2)])
+@pytest.mark.parametrize("prec,recon", [(8, 12), (4, 8), (2, 18)])
+def test_degenerate_extents(X, prec, recon):
+    """smallest legal lattices: extent 2 makes the forward and the backward neighbour the same site (and X0 = 2 leaves one
+    checkerboard site per row); anisotropy + periodic t exercise the other u0 branch of the reconstruction"""
+    be = twin_backend()
+    P = Problem(X, prec, recon, HostMem, anisotropy=2.38, antiperiodic_t=False)
+    for parity, dagger in ((0, 0), (1, 1)):
+        s, xs = P.spinor(seed=7 + parity), P.spinor(seed=9)
+        out = P.empty()
+        D.ApplyWilson(out, P.to_dev(s), P.U, -0.1, P.to_dev(xs), parity, dagger, backend=be)
+        ref = xs.astype(np.float64) - 0.1 * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
+        assert_close(ref, P.to_host(out), prec, recon, f"X={X} parity={parity}")
