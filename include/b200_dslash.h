@@ -147,6 +147,12 @@ int b200_dslash_apply_multi(const b200_dslash_args *args, int n_src, const b200_
 int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_clover *A, int precision, int inverse,
                       int parity, void *stream);
 
+/* replaces quda::ApplyTwistGamma(out, in, 4, kappa, mu, 0, dagger, type) for the singlet flavour (include/dslash_quda.h:883,
+ * include/kernels/dslash_gamma_helper.cuh:55-62): out = a (1 + i b gamma5) in on one parity, with
+ * direct: b = 2 kappa mu, a = 1;  inverse: b = -2 kappa mu, a = 1 / (1 + b^2);  dagger negates b.  out may alias in. */
+int b200_twist_gamma5(const b200_spinor *out, const b200_spinor *in, int precision, double kappa, double mu, int dagger,
+                      int inverse, void *stream);
+
 /* replaces quda::PackGhost (include/dslash_quda.h:919; lib/dslash_pack2.cu:55-425): spin-project the boundary
  * sites of `in` (parity 1-parity... see b200_pack_args) and store 12-real half spinors into the send targets,
  * which may be local buffers or peer-GPU ghost buffers mapped over NVLink. */
@@ -246,7 +252,9 @@ typedef struct {
 
 typedef struct b200_dirac_s b200_dirac; /* opaque */
 
-typedef enum { B200_DIRAC_WILSON = 0, B200_DIRAC_WILSONPC = 1, B200_DIRAC_CLOVER = 2, B200_DIRAC_CLOVERPC = 3 } b200_dirac_type;
+typedef enum { B200_DIRAC_WILSON = 0, B200_DIRAC_WILSONPC = 1, B200_DIRAC_CLOVER = 2, B200_DIRAC_CLOVERPC = 3,
+               B200_DIRAC_TWISTED_MASS = 4, B200_DIRAC_TWISTED_MASSPC = 5 /* singlet flavour, lib/dirac_twisted_mass.cpp */
+} b200_dirac_type;
 typedef enum { B200_MATPC_EVEN_EVEN = 0, B200_MATPC_ODD_ODD = 1, B200_MATPC_EVEN_EVEN_ASYMMETRIC = 2,
                B200_MATPC_ODD_ODD_ASYMMETRIC = 3 } b200_matpc_type;
 typedef enum { B200_APPLY_M = 0, B200_APPLY_MDAG = 1, B200_APPLY_MDAGM = 2, B200_APPLY_DSLASH = 3,
@@ -256,6 +264,8 @@ typedef enum { B200_APPLY_M = 0, B200_APPLY_MDAG = 1, B200_APPLY_MDAGM = 2, B200
  * descriptors are copied; the fields they point to stay owned by the caller and must outlive the operator. */
 int b200_dirac_create(b200_dirac **op, int type, int precision, const int X[4], const b200_gauge *U, const b200_clover *A,
                       const b200_clover *Ainv, double kappa, int matpc_type, b200_comm *comm, void *stream);
+/* twisted-mass operators: the twist mass mu (DiracParam::mu); 0 after creation */
+int b200_dirac_set_twist(b200_dirac *op, double mu);
 int b200_dirac_destroy(b200_dirac *op);
 /* M / Mdag / MdagM act on full fields (unpreconditioned types) or single-parity fields (PC types);
  * DSLASH / DSLASH_XPAY take the destination parity, x and k as Dirac::Dslash[Xpay] do. */

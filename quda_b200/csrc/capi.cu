@@ -131,6 +131,42 @@ int b200_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", precision);
 }
 
+// a, b of out = a (1 + i b gamma5) in for the singlet twist (dslash_gamma_helper.cuh:55-62)
+static void twist_coefficients(double &a, double &b, double kappa, double mu, int dagger, int inverse)
+{
+  if (!inverse) {
+    b = 2.0 * kappa * mu;
+    a = 1.0;
+  } else {
+    b = -2.0 * kappa * mu;
+    a = 1.0 / (1.0 + b * b);
+  }
+  if (dagger) b = -b;
+}
+
+int b200_twist_gamma5(const b200_spinor *out, const b200_spinor *in, int precision, double kappa, double mu, int dagger,
+                      int inverse, void *stream)
+{
+  if (!out || !in || !out->v || !in->v) return set_error(B200_ERR_INVALID, "b200_twist_gamma5: null argument");
+  if (int rc = require_device()) return rc;
+  if (out->n_parity != 1 || in->n_parity != 1 || out->volume_cb != in->volume_cb)
+    return set_error(B200_ERR_INVALID, "b200_twist_gamma5 acts on single-parity fields of equal volume");
+  TwistRequest rq;
+  rq.out = out->v;
+  rq.out_norm = out->norm;
+  rq.in = in->v;
+  rq.in_norm = in->norm;
+  rq.volume_cb = out->volume_cb;
+  twist_coefficients(rq.a, rq.b, kappa, mu, dagger, inverse);
+  rq.stream = stream;
+  switch (precision) {
+  case B200_DOUBLE: return launch_twist_precision<PrecF64>(rq);
+  case B200_SINGLE: return launch_twist_precision<PrecF32>(rq);
+  case B200_HALF: return launch_twist_precision<PrecH16>(rq);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", precision);
+}
+
 int b200_copy_spinor(const b200_spinor *native, int native_precision, void *host_order, int host_precision, int to_native,
                      void *stream)
 {

@@ -157,9 +157,12 @@ namespace b200
       abi_ok(b200_pack_ghost(&a));
     }
 
+    // `b`, `asymmetric`: twisted mass only; with_x: 1 / 0 force x on / off (the twisted-mass preconditioned operator's
+    // xpay flag), -1 = the Wilson convention (x iff a != 0)
     static void apply(int op, ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, const CloverField *A,
                       bool inverse_field, double a, const ColorSpinorField &x, int parity, bool dagger,
-                      const int *comm_override, CommContext *comm, void *stream)
+                      const int *comm_override, CommContext *comm, void *stream, double b = 0.0, bool asymmetric = false,
+                      int with_x = -1)
     {
       b200_dslash_args args;
       memset(&args, 0, sizeof(args));
@@ -173,7 +176,9 @@ namespace b200
       args.a = a;
       args.out = out.desc();
       args.in = in.desc();
-      if (a != 0.0) args.x = x.desc();
+      if (with_x < 0 ? a != 0.0 : with_x != 0) args.x = x.desc();
+      args.b = b;
+      args.asymmetric = asymmetric ? 1 : 0;
       args.U = U.g;
       if (A) args.A = (inverse_field && A->has_inverse()) ? A->cinv : A->c;
       bool part = false;
@@ -224,6 +229,28 @@ namespace b200
                                          bool dagger, const int *comm_override, CommContext *comm, void *stream)
     {
       apply(B200_OP_CLOVER_PC, out, in, U, &A, true, a, x, parity, dagger, comm_override, comm, stream);
+    }
+
+    void ApplyTwistedMass(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a, double b,
+                          const ColorSpinorField &x, int parity, bool dagger, const int *comm_override, CommContext *comm,
+                          void *stream)
+    {
+      apply(B200_OP_TWISTED_MASS, out, in, U, nullptr, false, a, x, parity, dagger, comm_override, comm, stream, b);
+    }
+
+    void ApplyTwistedMassPreconditioned(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a,
+                                        double b, bool xpay, const ColorSpinorField &x, int parity, bool dagger,
+                                        bool asymmetric, const int *comm_override, CommContext *comm, void *stream)
+    {
+      apply(B200_OP_TWISTED_MASS_PC, out, in, U, nullptr, false, a, x, parity, dagger, comm_override, comm, stream, b,
+            asymmetric, xpay ? 1 : 0);
+    }
+
+    void ApplyTwistGamma(ColorSpinorField &out, const ColorSpinorField &in, double kappa, double mu, bool dagger, bool inverse,
+                         void *stream)
+    {
+      b200_spinor o = out.desc(), i = in.desc();
+      abi_ok(b200_twist_gamma5(&o, &i, in.precision, kappa, mu, dagger, inverse, stream));
     }
 
     void ApplyClover(ColorSpinorField &out, const ColorSpinorField &in, const CloverField &A, bool inverse, int parity,
@@ -487,6 +514,8 @@ namespace b200
       if (type == "wilsonpc") return new DiracWilsonPC(p);
       if (type == "clover") return new DiracClover(p);
       if (type == "cloverpc") return new DiracCloverPC(p);
+      if (type == "twistedmass") return new DiracTwistedMass(p);
+      if (type == "twistedmasspc") return new DiracTwistedMassPC(p);
       throw Error("Dirac::create: unsupported operator type '" + type + "'");
     }
 
@@ -688,6 +717,109 @@ namespace b200
       DiracWilson::DslashXpay(tmp, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
       auto xo = x.parity_view(other_parity);
       CloverInv(xo, tmp, other_parity);
+    }
+
+    // --- twisted mass, singlet flavour (lib/dirac_twisted_mass.cpp:9-317)
+    DiracTwistedMass::DiracTwistedMass(const DiracParam &p) : DiracWilson(p), mu(p.mu) { }
+    void DiracTwistedMass::Twist(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      ApplyTwistGamma(out, in, kappa, mu, dagger, false, stream);
+    }
+    void DiracTwistedMass::Dslash(ColorSpinorField &, const ColorSpinorField &, int) const
+    {
+      // the reference routes this to ApplyTwistedMass with a = 0, which it does not instantiate (:47-59)
+      throw Error("DiracTwistedMass::Dslash: twisted-mass operator only defined for xpay=true");
+    }
+    void DiracTwistedMass::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                                      double k) const
+    {
+      check_parity_spinor(in, out);
+      ApplyTwistedMass(out, in, *gauge, k, 2 * mu * kappa, x, parity, dagger, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracTwistedMass::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      check_full_spinor(out, in);
+      // -kappa D in + (1 + i 2 mu kappa gamma5) in, one parity at a time (the halo exchange works per parity)
+      auto oe = out.Even(), oo = out.Odd();
+      DiracTwistedMass::DslashXpay(oe, in.Odd(), 0, in.Even(), -kappa);
+      DiracTwistedMass::DslashXpay(oo, in.Even(), 1, in.Odd(), -kappa);
+    }
+    void DiracTwistedMass::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      FieldTmp tmp(in, in.n_parity);
+      M(tmp, in);
+      Mdag(out, tmp);
+    }
+
+    void DiracTwistedMassPC::TwistInv(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      ApplyTwistGamma(out, in, kappa, mu, dagger, true, stream);
+    }
+    void DiracTwistedMassPC::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
+    {
+      check_parity_spinor(in, out);
+      const double a = -2.0 * kappa * mu; // inverse twist
+      const double b = 1.0 / (1.0 + a * a);
+      const bool asymmetric = !symmetric && dagger;
+      ApplyTwistedMassPreconditioned(out, in, *gauge, b, a, false, in, parity, dagger, asymmetric, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracTwistedMassPC::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                                        double k) const
+    {
+      check_parity_spinor(in, out);
+      const double a = -2.0 * kappa * mu;
+      const double b = k / (1.0 + a * a);
+      const bool asymmetric = !symmetric && dagger;
+      ApplyTwistedMassPreconditioned(out, in, *gauge, b, a, true, x, parity, dagger, asymmetric, commDim, comm, stream);
+      dslash_applications++;
+    }
+    void DiracTwistedMassPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      const double kappa2 = -kappa * kappa;
+      FieldTmp tmp(in, 1);
+      Dslash(tmp, in, other_parity);
+      if (symmetric)
+        DslashXpay(out, tmp, this_parity, in, kappa2);
+      else
+        DiracTwistedMass::DslashXpay(out, tmp, this_parity, in, kappa2);
+    }
+    void DiracTwistedMassPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      FieldTmp tmp(in, 1); // extra temporary because of the symmetric dagger operator
+      M(tmp, in);
+      Mdag(out, tmp);
+    }
+    void DiracTwistedMassPC::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
+                                     QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) {
+        src = b;
+        sol = x;
+        return;
+      }
+      src = x.parity_view(other_parity);
+      sol = x.parity_view(this_parity);
+      FieldTmp tmp(b, 1);
+      if (symmetric) { // src = A_ee^-1 (b_e + k D_eo A_oo^-1 b_o)
+        TwistInv(src, b.parity_view(other_parity));
+        DiracWilson::DslashXpay(tmp, src, this_parity, b.parity_view(this_parity), kappa);
+        TwistInv(src, tmp);
+      } else { // src = b_e + k D_eo A_oo^-1 b_o
+        TwistInv(tmp, b.parity_view(other_parity));
+        DiracWilson::DslashXpay(src, tmp, this_parity, b.parity_view(this_parity), kappa);
+      }
+    }
+    void DiracTwistedMassPC::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
+    {
+      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
+      check_full_spinor(x, b);
+      FieldTmp tmp(b, 1);
+      // x_o = A_oo^-1 (b_o + k D_oe x_e)
+      DiracWilson::DslashXpay(tmp, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
+      auto xo = x.parity_view(other_parity);
+      TwistInv(xo, tmp);
     }
 
     // ------------------------------------------------------------------ CG (normal equations) with reliable updates

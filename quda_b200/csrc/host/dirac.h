@@ -105,6 +105,15 @@ namespace b200
                                          bool dagger, const int *comm_override, CommContext *comm, void *stream = nullptr);
     void ApplyClover(ColorSpinorField &out, const ColorSpinorField &in, const CloverField &A, bool inverse, int parity,
                      void *stream = nullptr);
+    // degenerate twisted mass (include/dslash_quda.h:363-406,883)
+    void ApplyTwistedMass(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a, double b,
+                          const ColorSpinorField &x, int parity, bool dagger, const int *comm_override, CommContext *comm,
+                          void *stream = nullptr);
+    void ApplyTwistedMassPreconditioned(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a,
+                                        double b, bool xpay, const ColorSpinorField &x, int parity, bool dagger,
+                                        bool asymmetric, const int *comm_override, CommContext *comm, void *stream = nullptr);
+    void ApplyTwistGamma(ColorSpinorField &out, const ColorSpinorField &in, double kappa, double mu, bool dagger, bool inverse,
+                         void *stream = nullptr);
 
     // ---- blas on native-order fields of equal precision (fp64 / fp32); reductions accumulate in double
     namespace blas
@@ -128,6 +137,7 @@ namespace b200
       const GaugeField *gauge = nullptr;
       const CloverField *clover = nullptr;
       double kappa = 0.0;
+      double mu = 0.0; // twisted mass
       QudaMatPCType matpcType = QUDA_MATPC_EVEN_EVEN;
       bool dagger = false;
       int commDim[4] = {1, 1, 1, 1};
@@ -166,7 +176,8 @@ namespace b200
       void flipDagger() const { dagger = !dagger; }
       long long DslashApplications() const { return dslash_applications; }
       CommContext *Comm() const { return comm; }
-      static Dirac *create(const std::string &type, const DiracParam &p); // "wilson", "wilsonpc", "clover", "cloverpc"
+      // "wilson", "wilsonpc", "clover", "cloverpc", "twistedmass", "twistedmasspc"
+      static Dirac *create(const std::string &type, const DiracParam &p);
     };
 
     class DiracWilson : public Dirac
@@ -218,6 +229,39 @@ namespace b200
       void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override; // A^-1 D
       void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
                       double k) const override; // x + k A^-1 D in
+      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
+      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
+      void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
+                   QudaSolutionType) const override;
+      void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const override;
+    };
+
+    // ---- degenerate (singlet) twisted mass, lib/dirac_twisted_mass.cpp
+    class DiracTwistedMass : public DiracWilson
+    {
+    protected:
+      double mu;
+
+    public:
+      explicit DiracTwistedMass(const DiracParam &p);
+      void setMu(double m) { mu = m; }
+      void Twist(ColorSpinorField &out, const ColorSpinorField &in) const; // (1 + i 2 kappa mu gamma5) in
+      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override;
+      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                      double k) const override; // k D in + (1 + i 2 mu kappa gamma5) x
+      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
+      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
+    };
+
+    class DiracTwistedMassPC : public DiracTwistedMass
+    {
+    public:
+      using DiracTwistedMass::DiracTwistedMass;
+      bool pc() const override { return true; }
+      void TwistInv(ColorSpinorField &out, const ColorSpinorField &in) const;
+      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override; // A^-1 D / D^dag A^-dag
+      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
+                      double k) const override;
       void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
       void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
       void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,

@@ -100,10 +100,20 @@ int b200_dirac_create(b200_dirac **out, int type, int precision, const int X[4],
     p.matpcType = (QudaMatPCType)matpc_type;
     p.comm = h->has_comm ? &h->comm : nullptr;
     p.stream = stream;
-    static const char *names[] = {"wilson", "wilsonpc", "clover", "cloverpc"};
-    if (type < 0 || type > 3) throw Error("b200_dirac_create: unknown operator type");
+    static const char *names[] = {"wilson", "wilsonpc", "clover", "cloverpc", "twistedmass", "twistedmasspc"};
+    if (type < 0 || type > 5) throw Error("b200_dirac_create: unknown operator type");
     h->op.reset(Dirac::create(names[type], p));
     *out = h.release();
+  });
+}
+
+int b200_dirac_set_twist(b200_dirac *op, double mu)
+{
+  return guarded([&] {
+    if (!op) throw Error("b200_dirac_set_twist: null operator");
+    auto *tm = dynamic_cast<DiracTwistedMass *>(op->op.get());
+    if (!tm) throw Error("b200_dirac_set_twist: not a twisted-mass operator");
+    tm->setMu(mu);
   });
 }
 

@@ -179,6 +179,19 @@ namespace b200
     out.save(v, x_cb);
   }
 
+  // site-local twisted-mass rotation out = a (1 + i b gamma5) in (ApplyTwistGamma, dslash_gamma_helper.cuh)
+  template <class P>
+  __global__ void __launch_bounds__(256) twist_gamma5_kernel(SpinorView<P> out, SpinorView<P> in, int volume_cb,
+                                                             typename P::real a, typename P::real b)
+  {
+    const int x_cb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x_cb >= volume_cb) return;
+    typename P::real v[24];
+    in.template load<Cache::STREAM>(v, x_cb);
+    twist_apply(v, a, b);
+    out.save(v, x_cb);
+  }
+
   // Halo packing: one thread per (dim, face, face site); spin-project the boundary site and store the 12-real
   // half spinor to the destination face buffer (local, or a peer GPU's ghost buffer mapped over NVLink).
   // Face 0 (x[d] == 0) feeds the backward neighbour's forward hop, which uses P(d, dagger ? + : -);
@@ -561,6 +574,17 @@ namespace b200
       clover_apply_kernel<P, false><<<blocks, 128, 0, s>>>(out, in, A, rq.volume_cb, rq.parity);
     count_launch();
     return check_cuda(cudaGetLastError(), "clover launch");
+  }
+
+  template <class P> int launch_twist_precision(const TwistRequest &rq)
+  {
+    SpinorView<P> out, in;
+    fill_spinor(out, rq.out, rq.out_norm, rq.volume_cb);
+    fill_spinor(in, rq.in, rq.in_norm, rq.volume_cb);
+    twist_gamma5_kernel<P><<<(rq.volume_cb + 255) / 256, 256, 0, (cudaStream_t)rq.stream>>>(out, in, rq.volume_cb, (typename P::real)rq.a,
+                                                                                          (typename P::real)rq.b);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "twist launch");
   }
 
   template <class P> int launch_pack_precision(const PackRequest &rq)

@@ -50,6 +50,13 @@ namespace b200
     void *stream;
   };
 
+  struct TwistRequest {
+    void *out, *out_norm, *in, *in_norm;
+    int volume_cb;
+    double a, b; // out = a (in + b i gamma5 in)
+    void *stream;
+  };
+
   struct CopyRequest {
     void *native, *native_norm, *host;
     int volume_cb, host_precision, to_native;
@@ -479,6 +486,7 @@ namespace b200
   template <class P> int launch_precision(const LaunchRequest &rq);
   template <class P> int launch_mrhs_precision(const MrhsRequest &rq);
   template <class P> int launch_clover_precision(const CloverRequest &rq);
+  template <class P> int launch_twist_precision(const TwistRequest &rq);
   template <class P> int launch_pack_precision(const PackRequest &rq);
   template <class P> int launch_copy_precision(const CopyRequest &rq);
   template <class P> int launch_gauge_copy_precision(const GaugeCopyRequest &rq);

@@ -6,11 +6,13 @@ import ctypes as C
 from . import lib as L
 
 MATPC_EVEN_EVEN, MATPC_ODD_ODD, MATPC_EVEN_EVEN_ASYMMETRIC, MATPC_ODD_ODD_ASYMMETRIC = 0, 1, 2, 3
-_TYPES = {"wilson": L.DIRAC_WILSON, "wilsonpc": L.DIRAC_WILSONPC, "clover": L.DIRAC_CLOVER, "cloverpc": L.DIRAC_CLOVERPC}
+_TYPES = {"wilson": L.DIRAC_WILSON, "wilsonpc": L.DIRAC_WILSONPC, "clover": L.DIRAC_CLOVER, "cloverpc": L.DIRAC_CLOVERPC,
+          "twistedmass": L.DIRAC_TWISTED_MASS, "twistedmasspc": L.DIRAC_TWISTED_MASSPC}
 
 
 class Dirac:
-    def __init__(self, kind, U, kappa, clover=None, clover_inv=None, matpc_type=MATPC_EVEN_EVEN, comm=None, stream=None):
+    def __init__(self, kind, U, kappa, clover=None, clover_inv=None, matpc_type=MATPC_EVEN_EVEN, comm=None, stream=None,
+                 mu=0.0):
         self.lib = L.load()
         self.kind, self.U, self.clover, self.clover_inv, self.comm = kind, U, clover, clover_inv, comm  # keep fields alive
         self.prec = U.prec
@@ -24,6 +26,8 @@ class Dirac:
                                            C.byref(ai) if ai is not None else None, float(kappa), int(matpc_type),
                                            C.byref(comm) if comm is not None else None, stream))
         self.h = h
+        if kind.startswith("twistedmass"):
+            L.check(self.lib.b200_dirac_set_twist(self.h, float(mu)))
 
     def __del__(self):
         try:

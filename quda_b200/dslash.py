@@ -172,6 +172,14 @@ def ApplyClover(out, in_, A, inverse, parity, stream=None, backend=None):
     be.call("clover_apply", C.byref(o), C.byref(i), C.byref(c), out.prec, int(bool(inverse)), parity, stream)
 
 
+def ApplyTwistGamma(out, in_, kappa, mu, dagger, inverse, stream=None, backend=None):
+    """out = a (1 + i b gamma5) in on one parity: the singlet twist (inverse=False) or its inverse.
+    Reference: include/dslash_quda.h:883 (d = 4, epsilon = 0), include/kernels/dslash_gamma_helper.cuh:55-62."""
+    be = backend or cuda_backend()
+    o, i = out.desc(), in_.desc()
+    be.call("twist_gamma5", C.byref(o), C.byref(i), out.prec, float(kappa), float(mu), int(bool(dagger)), int(bool(inverse)), stream)
+
+
 def PackGhost(dst, in_, parity, dagger, comm_dim, stream=None, backend=None):
     """Spin-project the faces of `in_` (sites of `parity`) into dst[d][face] (local or peer ghost buffers).
     Reference: lib/dslash_pack2.cu:55-425."""

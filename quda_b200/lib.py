@@ -76,7 +76,7 @@ class SolverParam(C.Structure):
 
 
 MAX_MULTI_RHS = 16
-DIRAC_WILSON, DIRAC_WILSONPC, DIRAC_CLOVER, DIRAC_CLOVERPC = 0, 1, 2, 3
+DIRAC_WILSON, DIRAC_WILSONPC, DIRAC_CLOVER, DIRAC_CLOVERPC, DIRAC_TWISTED_MASS, DIRAC_TWISTED_MASSPC = 0, 1, 2, 3, 4, 5
 APPLY_M, APPLY_MDAG, APPLY_MDAGM, APPLY_DSLASH, APPLY_DSLASH_XPAY = 0, 1, 2, 3, 4
 
 
@@ -89,6 +89,9 @@ def declare(lib, prefix="b200"):
     f.restype = C.c_int
     f = getattr(lib, prefix + "_clover_apply")
     f.argtypes = [C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(Clover), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    f.restype = C.c_int
+    f = getattr(lib, prefix + "_twist_gamma5")
+    f.argtypes = [C.POINTER(Spinor), C.POINTER(Spinor), C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
     f.restype = C.c_int
     f = getattr(lib, prefix + "_pack_ghost")
     f.argtypes, f.restype = [C.POINTER(PackArgs)], C.c_int
@@ -131,6 +134,7 @@ def load():
                                           C.c_void_p]
         lib.b200_dirac_create.restype = C.c_int
         lib.b200_dirac_destroy.argtypes, lib.b200_dirac_destroy.restype = [C.c_void_p], C.c_int
+        lib.b200_dirac_set_twist.argtypes, lib.b200_dirac_set_twist.restype = [C.c_void_p, C.c_double], C.c_int
         lib.b200_dirac_apply.argtypes = [C.c_void_p, C.c_int, C.POINTER(Spinor), C.POINTER(Spinor), C.c_int,
                                          C.POINTER(Spinor), C.c_double, C.c_int]
         lib.b200_dirac_apply.restype = C.c_int
@@ -154,9 +158,9 @@ def check(rc, lib=None, prefix="b200"):
         raise B200Error(f"{prefix} error {rc}: {msg}")
 
 
-EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_dslash_apply_multi", "b200_clover_apply", "b200_pack_ghost", "b200_ghost_face_bytes",
+EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_dslash_apply_multi", "b200_clover_apply", "b200_twist_gamma5", "b200_pack_ghost", "b200_ghost_face_bytes",
                     "b200_copy_spinor", "b200_copy_gauge", "b200_copy_clover", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
-                    "b200_dirac_create", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",
+                    "b200_dirac_create", "b200_dirac_set_twist", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",
                     "b200_dirac_reconstruct", "b200_invert_cg",
                     "b200_last_error", "b200_abi_version", "b200_launch_count", "b200_reset_launch_count"]

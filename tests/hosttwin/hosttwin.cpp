@@ -319,6 +319,20 @@ namespace b200
 
 using namespace b200;
 
+template <class P> static int run_twist(const b200_spinor *out, const b200_spinor *in, double a, double b)
+{
+  SpinorView<P> o, i;
+  fill_spinor(o, out->v, out->norm, out->volume_cb);
+  fill_spinor(i, in->v, in->norm, in->volume_cb);
+  for (int x_cb = 0; x_cb < out->volume_cb; x_cb++) {
+    typename P::real v[24];
+    i.load(v, x_cb);
+    twist_apply(v, (typename P::real)a, (typename P::real)b);
+    o.save(v, x_cb);
+  }
+  return 0;
+}
+
 extern "C" {
 const char *twin_last_error(void) { return g_err; }
 
@@ -369,6 +383,19 @@ int twin_clover_apply(const b200_spinor *out, const b200_spinor *in, const b200_
   case B200_DOUBLE: return run_clover<PrecF64>(out, in, A, inverse, parity);
   case B200_SINGLE: return run_clover<PrecF32>(out, in, A, inverse, parity);
   case B200_HALF: return run_clover<PrecH16>(out, in, A, inverse, parity);
+  }
+  return -1;
+}
+
+int twin_twist_gamma5(const b200_spinor *out, const b200_spinor *in, int precision, double kappa, double mu, int dagger, int inverse, void *)
+{
+  double a, b; // capi.cu::twist_coefficients
+  if (!inverse) { b = 2.0 * kappa * mu; a = 1.0; } else { b = -2.0 * kappa * mu; a = 1.0 / (1.0 + b * b); }
+  if (dagger) b = -b;
+  switch (precision) {
+  case B200_DOUBLE: return run_twist<PrecF64>(out, in, a, b);
+  case B200_SINGLE: return run_twist<PrecF32>(out, in, a, b);
+  case B200_HALF: return run_twist<PrecH16>(out, in, a, b);
   }
   return -1;
 }

@@ -107,6 +107,11 @@ def check_twisted_mass(mem, be, prec, recon, X=(4, 6, 4, 8), comm_dim=None):
                 assert_close(xs.astype(f64) + k * ref, P.to_host(out), prec, recon, f"tm_dslash xpay matpc={matpc} dag={dagger}")
     if comm_dim is not None:
         return
+    # ApplyTwistGamma: the site-local rotation and its inverse
+    for dagger, inverse in itertools.product((0, 1), (False, True)):
+        out = P.empty()
+        D.ApplyTwistGamma(out, P.to_dev(s), kappa, mu, dagger, inverse, backend=be)
+        assert_close(oracle.twist_gamma5(s, kappa, mu, dagger, inverse), P.to_host(out), prec, 18, f"twist dag={dagger} inv={inverse}")
     # composition: DiracTwistedMassPC::M
     for matpc, dagger in itertools.product(range(4), (0, 1)):
         this = 0 if matpc in (0, 2) else 1

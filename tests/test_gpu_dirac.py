@@ -135,3 +135,58 @@ def test_partitioned_operators_through_cpp_layer():
     op.M(out, P.to_dev(full, 2))
     assert_close(oracle.wil_mat(P.gauge, full, X, KAPPA, 0), P.to_host(out), 8, 12, "partitioned wilson M")
     assert not ex.timed_out()
+
+
+# The C++ twisted-mass operator classes were written after the last GPU session of round 1; their building blocks
+# (ApplyTwistedMass*, ApplyTwistGamma) are covered by tests/test_gpu_ops.py::test_twisted_mass, the classes themselves wait
+# for their first run on hardware: B200_EXPERIMENTAL=1.
+_experimental = pytest.mark.skipif(not __import__("os").environ.get("B200_EXPERIMENTAL"),
+                                   reason="first hardware run pending, enable with B200_EXPERIMENTAL=1")
+MU = 0.1
+
+
+@_experimental
+@pytest.mark.parametrize("prec", [8, 4])
+def test_twisted_mass_mat_and_matpc(prec):
+    """DiracTwistedMass / DiracTwistedMassPC (lib/dirac_twisted_mass.cpp) against tm_mat / tm_matpc"""
+    X = (4, 6, 4, 8)
+    P = Problem(X, prec, 12, CudaMem)
+    full = P.spinor(seed=3, nparity=2)
+    op = DR.Dirac("twistedmass", P.U, KAPPA, mu=MU)
+    for dagger in (0, 1):
+        out = P.empty(2)
+        op.M(out, P.to_dev(full, 2), dagger=dagger)
+        assert_close(oracle.tm_mat(P.gauge, full, X, KAPPA, MU, dagger), P.to_host(out), prec, 12, "twisted-mass M")
+    s = P.spinor(seed=4)
+    for matpc in range(4):
+        pc = DR.Dirac("twistedmasspc", P.U, KAPPA, matpc_type=matpc, mu=MU)
+        for dagger in (0, 1):
+            out = P.empty()
+            pc.M(out, P.to_dev(s), dagger=dagger)
+            ref = oracle.tm_matpc(P.gauge, s, X, KAPPA, MU, matpc, dagger)
+            assert_close(ref, P.to_host(out), prec, 12, f"twisted-mass Mpc type={matpc} dag={dagger}")
+
+
+@_experimental
+@pytest.mark.parametrize("matpc", [DR.MATPC_EVEN_EVEN, DR.MATPC_ODD_ODD_ASYMMETRIC])
+def test_cg_twisted_mass_full_system(matpc):
+    """prepare -> CG on MpcdagMpc -> reconstruct for the twisted-mass operator, verified with the oracle's tm_mat"""
+    from quda_b200 import dslash as D
+    X = (8, 8, 8, 8)
+    P = Problem(X, 8, 18, CudaMem)
+    pc = DR.Dirac("twistedmasspc", P.U, KAPPA, matpc_type=matpc, mu=MU)
+    b = P.spinor(seed=77, nparity=2)
+    bdev, xdev = P.to_dev(b, 2), P.empty(2)
+    src_p, sol_p = pc.prepare(xdev, bdev)
+    pb = xdev.parity_bytes
+    src = D.ColorSpinorField(xdev.buf[src_p * pb:(src_p + 1) * pb], X, 8)
+    sol = D.ColorSpinorField(xdev.buf[sol_p * pb:(sol_p + 1) * pb], X, 8)
+    rhs = P.empty()
+    pc.Mdag(rhs, src)
+    sol.buf.zero_()
+    res = DR.invert_cg(pc, None, sol, rhs, tol=1e-10, maxiter=2000)
+    pc.reconstruct(xdev, bdev)
+    x = P.to_host(xdev)
+    Mx = oracle.tm_mat(P.gauge, x, X, KAPPA, MU, 0)
+    true_res = np.linalg.norm(Mx.ravel() - b.ravel()) / np.linalg.norm(b.ravel())
+    assert res.iter < 2000 and true_res < 1e-8, (res.iter, true_res)
