@@ -56,6 +56,20 @@ def test_no_cpu_fallback_without_gpu():
     rc = lib.b200_dslash_apply(C.byref(args))
     assert rc == -4  # B200_ERR_NO_DEVICE
     assert b"no CPU path" in lib.b200_last_error()
+    # every compute entry point refuses the same way (none of them can reach a host code path)
+    import numpy as np
+    buf = np.zeros(64, dtype=np.uint8)
+    sp = L.Spinor(buf.ctypes.data, None, 0, 1, 1)
+    sps = (L.Spinor * 2)(sp, sp)
+    cl = L.Clover(buf.ctypes.data, 0, 1, 1, 1.0, 1.0)
+    assert lib.b200_dslash_apply_multi(C.byref(args), 2, sps, sps, None) == -4
+    assert lib.b200_clover_apply(C.byref(sp), C.byref(sp), C.byref(cl), 4, 0, 0, None) == -4
+    assert lib.b200_twist_gamma5(C.byref(sp), C.byref(sp), 4, 0.1, 0.1, 0, 0, None) == -4
+    assert lib.b200_copy_spinor(C.byref(sp), 4, buf.ctypes.data, 4, 1, None) == -4
+    pa = L.PackArgs()
+    pa.abi_version = L.ABI_VERSION
+    pa.in_ = sp
+    assert lib.b200_pack_ghost(C.byref(pa)) == -4
 
 
 def test_ghost_face_bytes():
