@@ -5,6 +5,10 @@
 
 #include "launch.h"
 
+#ifndef B2_TMA_DEFAULT
+#define B2_TMA_DEFAULT 0
+#endif
+
 namespace b200
 {
   static thread_local char g_err[512] = "";
@@ -39,6 +43,19 @@ namespace b200
     return 0;
   }
 
+  // B200_TMA=0|1|2 selects the TMA-staged marching kernel (2: fail instead of falling back when a shape is not served);
+  // B200_TMA_TILE="ty tz", B200_TMA_GRID, B200_TMA_LINKS tune it.  Read on every call (a handful of getenv lookups) so
+  // that tests and tuning scripts can switch between calls.
+  static void tma_knobs(LaunchRequest &rq)
+  {
+    const char *e = getenv("B200_TMA");
+    rq.tma = e ? atoi(e) : B2_TMA_DEFAULT;
+    if (!rq.tma) return;
+    if ((e = getenv("B200_TMA_TILE"))) sscanf(e, "%d %d", &rq.tma_ty, &rq.tma_tz);
+    if ((e = getenv("B200_TMA_GRID"))) rq.tma_grid = atoi(e);
+    if ((e = getenv("B200_TMA_LINKS"))) rq.tma_link_slots = atoi(e);
+  }
+
 } // namespace b200
 
 using namespace b200;
@@ -64,6 +81,13 @@ int b200_dslash_apply(const b200_dslash_args *a)
   if (int rc = make_request(rq, a, nothing_to_do)) return rc;
   if (nothing_to_do) return B200_SUCCESS;
   if (const char *e = getenv("B200_MARCH_T")) rq.march_t = atoi(e); // experimental: time-marching CTAs (kernels.cuh)
+  tma_knobs(rq);
+  if (rq.tma && rq.kernel == B200_KERNEL_AUTO && a->precision != B200_HALF) {
+    // TMA-staged marching kernel (tma_kernel.cuh) for the shapes it serves; anything else falls through
+    const int rc = a->precision == B200_DOUBLE ? launch_tma_precision<PrecF64>(rq) : launch_tma_precision<PrecF32>(rq);
+    if (rc != kTmaSkip) return rc;
+    if (rq.tma > 1) return set_error(B200_ERR_UNSUPPORTED, "B200_TMA=2: shape not served by the TMA kernel");
+  }
   switch (a->precision) {
   case B200_DOUBLE: return launch_precision<PrecF64>(rq);
   case B200_SINGLE: return launch_precision<PrecF32>(rq);

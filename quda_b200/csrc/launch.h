@@ -21,6 +21,8 @@ namespace b200
     double b;       // twisted mass: twist factor as passed by the caller (the dagger sign flip happens in fill_args)
     int asymmetric; // twisted-mass preconditioned: asymmetric variant
     int march_t; // > 0: every CTA walks `march_t` consecutive time slices with its (x,y,z) tile (L1 reuse of the slices)
+    int tma;     // 1: unpartitioned single-source requests go to the TMA-staged marching kernel when it serves the shape
+    int tma_ty, tma_tz, tma_grid, tma_link_slots; // tuning overrides of that kernel (0: built-in choice)
     double a;
     b200_spinor out, in, x;
     b200_gauge U;
@@ -334,6 +336,8 @@ namespace b200
       default_tile(rq.tile, a->precision, a->X);
     }
     rq.march_t = 0;
+    rq.tma = 0;
+    rq.tma_ty = rq.tma_tz = rq.tma_grid = rq.tma_link_slots = 0;
     rq.out = a->out;
     rq.in = a->in;
     rq.x = a->x;
@@ -484,6 +488,8 @@ namespace b200
   }
 
   template <class P> int launch_precision(const LaunchRequest &rq);
+  constexpr int kTmaSkip = -4242; // "this request is not served by the TMA kernel": the caller uses the gather kernel
+  template <class P> int launch_tma_precision(const LaunchRequest &rq); // tma_kernel.cuh; kTmaSkip if not served
   template <class P> int launch_mrhs_precision(const MrhsRequest &rq);
   template <class P> int launch_clover_precision(const CloverRequest &rq);
   template <class P> int launch_twist_precision(const TwistRequest &rq);

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "../../quda_b200/csrc/launch.h"
+#include "tma_emu.h"
 
 namespace b200
 {
@@ -33,6 +34,11 @@ namespace b200
     if (int e = make_tile_map(tm, threads, rq.tile, g, 128)) return e;
     const bool partitioned = arg.threads_ext[4] > 0;
     long visited = 0;
+    if (rq.tma && !partitioned && rq.kernel == B200_KERNEL_AUTO) { // capi.cu: TMA-staged marching kernel where it serves the shape
+      const int rc = tma_emu_launch<P, recon, dagger, xpay, op>(rq, arg);
+      if (rc != kTmaSkip) return rc;
+      if (rq.tma > 1) return set_error(B200_ERR_UNSUPPORTED, "B200_TMA=2: shape not served by the TMA kernel");
+    }
     // walk the SAME launch grids as kernels.cuh::launch_config (tile boxes, slab table, block / thread decomposition)
     auto walk_box = [&](auto site_fn) {
 #pragma omp parallel for collapse(2) reduction(+ : visited)
@@ -343,6 +349,10 @@ int twin_dslash_apply(const b200_dslash_args *a)
   if (int rc = make_request(rq, a, nothing)) return rc;
   if (nothing) return 0;
   if (const char *e = getenv("B200_MARCH_T")) rq.march_t = atoi(e);
+  if (const char *e = getenv("B200_TMA")) rq.tma = atoi(e); // (read on every call: tests toggle it)
+  if (const char *e = getenv("B200_TMA_TILE")) sscanf(e, "%d %d", &rq.tma_ty, &rq.tma_tz);
+  if (const char *e = getenv("B200_TMA_GRID")) rq.tma_grid = atoi(e);
+  if (const char *e = getenv("B200_TMA_LINKS")) rq.tma_link_slots = atoi(e);
   switch (a->precision) {
   case B200_DOUBLE: return run_precision<PrecF64>(rq);
   case B200_SINGLE: return run_precision<PrecF32>(rq);
