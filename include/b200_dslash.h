@@ -271,6 +271,10 @@ int b200_dirac_destroy(b200_dirac *op);
  * DSLASH / DSLASH_XPAY take the destination parity, x and k as Dirac::Dslash[Xpay] do. */
 int b200_dirac_apply(b200_dirac *op, int what, const b200_spinor *out, const b200_spinor *in, int parity,
                      const b200_spinor *x, double k, int dagger);
+/* Halo health check: B200_SUCCESS if no halo wait has given up since the last check on this exchange, an error (flag
+ * cleared) otherwise; synchronises `stream`.  Kernels waiting for a neighbour's faces give up after ~10 s of SM clocks so
+ * that a lost peer can never hang the GPU; b200_invert_cg checks by itself, other callers check at their sync points. */
+int b200_comm_check(b200_comm *comm, void *stream);
 /* Dirac::prepare / Dirac::reconstruct for a full-system solve through the preconditioned operator: src_parity /
  * sol_parity receive which parity block of x holds the preconditioned source / solution. */
 int b200_dirac_prepare(b200_dirac *op, const b200_spinor *x, const b200_spinor *b, int *src_parity, int *sol_parity);
@@ -284,6 +288,7 @@ typedef struct {
   int reliable_updates;
   double true_res;  /* out: |b - A x| / |b| recomputed in the precise operator */
   double secs, gflops;
+  int host_syncs;   /* out: stream synchronisations during the solve (~1 per iteration, one iteration behind the GPU) */
 } b200_solver_param;
 /* CG on MdagM x = b (x, b in the precise operator's precision; sloppy may equal precise) */
 int b200_invert_cg(b200_dirac *precise, b200_dirac *sloppy, const b200_spinor *x, const b200_spinor *b, b200_solver_param *param);

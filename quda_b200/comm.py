@@ -109,7 +109,8 @@ class HaloExchange:
         self.grid, self.X, self.prec, self.n_parity, self.mode = grid, [int(v) for v in X], prec, n_parity, mode
         self.backend, self.dist = backend, dist
         self.comm_dim = grid.comm_dim() if mode != "self" else [1, 1, 1, 1]
-        self.seq = 0
+        self._comm_struct = None
+        self._seq = 0
         self.face_bytes = [n_parity * F.ghost_parity_bytes(X, prec, d) for d in range(4)]
         # slab layout: [buf 0|1][d][dir] ghost regions (256-byte aligned), then flags[2][4][2] (u32), counters[8], timeout
         self.off = {}
@@ -130,7 +131,9 @@ class HaloExchange:
         self.slab_bytes = (o + 255) // 256 * 256
         # solver scalars: "callback" = torch.distributed all-reduce from the host (validated default);
         # "nvlink" = the mailbox kernel over peer memory (needs every rank mapped, world <= 16)
-        self.allreduce_mode = os.environ.get("B200_ALLREDUCE", "callback")
+        # solver scalars: "nvlink" = device-side all-reduce through peer-mapped mailboxes inside the reduction kernels (no
+        # host round trip); "callback" = torch.distributed all_reduce from the host (two stream syncs per CG iteration)
+        self.allreduce_mode = os.environ.get("B200_ALLREDUCE", "nvlink")
         self.send_off = None
         if mode in ("p2p", "self"):
             self._init_device_slab()
@@ -178,6 +181,20 @@ class HaloExchange:
         self.slab = torch.zeros(self.slab_bytes, dtype=torch.uint8, device="cuda")
         self.send = torch.zeros(self.slab_bytes, dtype=torch.uint8, device="cuda")
         self.base = self.slab.data_ptr()
+
+    # The exchange counter is ONE number shared by every layer that drives this exchange: once a b200_comm block exists
+    # (comm_struct()), the C++ operators advance its `seq` field in place and the Python-level schedule reads / advances the
+    # very same field, so mixing Dirac objects with apply_wilson_distributed can never reuse a sequence number.
+    @property
+    def seq(self):
+        return int(self._comm_struct.seq) if self._comm_struct is not None else self._seq
+
+    @seq.setter
+    def seq(self, v):
+        if self._comm_struct is not None:
+            self._comm_struct.seq = int(v)
+        else:
+            self._seq = int(v)
 
     def pack_stream(self, stream=None):
         """side stream on which the pack kernel runs concurrently with the interior kernel"""
@@ -300,6 +317,8 @@ class HaloExchange:
         c.block_counter = self.base + self.counter_off
         c.timeout_flag = self.base + self.timeout_off
         c.seq = self.seq
+        if self._comm_struct is not None:
+            c.reduce_seq = self._comm_struct.reduce_seq
         if self.mode == "p2p":
             c.pack_stream = self.pack_stream().cuda_stream
         if self.mode == "p2p" and g.size > 1:

@@ -44,7 +44,8 @@ namespace b200
   }
 
   // B200_TMA=0|1|2 selects the TMA-staged marching kernel (2: fail instead of falling back when a shape is not served);
-  // B200_TMA_TILE="ty tz", B200_TMA_GRID, B200_TMA_LINKS tune it.  Read on every call (a handful of getenv lookups) so
+  // B200_TMA_TILE="ty tz", B200_TMA_GRID, B200_TMA_LINKS (n shared-memory stages, -1 register
+  // stream), B200_TMA_L2PF (L2 prefetch look-ahead in items, -1 off), B200_TMA_PREFETCH, B200_TMA_RINGS="centre halo" tune it.  Read on every call (a handful of getenv lookups) so
   // that tests and tuning scripts can switch between calls.
   static void tma_knobs(LaunchRequest &rq)
   {
@@ -54,6 +55,9 @@ namespace b200
     if ((e = getenv("B200_TMA_TILE"))) sscanf(e, "%d %d", &rq.tma_ty, &rq.tma_tz);
     if ((e = getenv("B200_TMA_GRID"))) rq.tma_grid = atoi(e);
     if ((e = getenv("B200_TMA_LINKS"))) rq.tma_link_slots = atoi(e);
+    if ((e = getenv("B200_TMA_PREFETCH"))) rq.tma_prefetch = atoi(e);
+    if ((e = getenv("B200_TMA_L2PF"))) rq.tma_l2_prefetch = atoi(e);
+    if ((e = getenv("B200_TMA_RINGS"))) sscanf(e, "%d %d", &rq.tma_center_slots, &rq.tma_halo_slots);
   }
 
 } // namespace b200

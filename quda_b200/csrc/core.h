@@ -46,7 +46,10 @@ namespace b200
   // Global-memory access policy hooks.  On the device these become cache-hinted PTX; on the host plain loads.
   // STREAM: read-once data (gauge links, clover) -- do not allocate in L1, evict-first in L2.
   // REUSE : neighbour spinors -- default caching (L1 + L2) so the 8-fold neighbour reuse is served on chip.
-  enum class Cache { REUSE, STREAM };
+  // COHERENT: data another agent may write while this kernel is resident (ghost slabs filled by peer GPUs over NVLink,
+  //            fields a kernel updates in place): ordinary coherent loads that do not allocate in L1 -- never the
+  //            non-coherent (.nc) path, which requires the data to be read-only for the kernel's lifetime.
+  enum class Cache { REUSE, STREAM, COHERENT };
 
   template <Cache c, typename V> B2_HD V ld(const V *p)
   {
@@ -54,7 +57,12 @@ namespace b200
     static_assert(sizeof(V) == 16 || sizeof(V) == 8 || sizeof(V) == 4, "vector width");
     if constexpr (sizeof(V) == 16) {
       uint4 r;
-      if constexpr (c == Cache::STREAM) {
+      if constexpr (c == Cache::COHERENT) {
+        asm volatile("ld.relaxed.sys.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                     : "l"(p)
+                     : "memory");
+      } else if constexpr (c == Cache::STREAM) {
 #ifdef B2_L2_HINTS
         // read-once data: additionally ask L2 to evict these lines first so they do not displace neighbour spinors
         unsigned long long pol;
@@ -72,14 +80,19 @@ namespace b200
       return *reinterpret_cast<V *>(&r);
     } else if constexpr (sizeof(V) == 8) {
       uint2 r;
-      if constexpr (c == Cache::STREAM)
+      if constexpr (c == Cache::COHERENT)
+        asm volatile("ld.relaxed.sys.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+      else if constexpr (c == Cache::STREAM)
         asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
       else
         asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
       return *reinterpret_cast<V *>(&r);
     } else {
       unsigned r;
-      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+      if constexpr (c == Cache::COHERENT)
+        asm volatile("ld.relaxed.sys.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+      else
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
       return *reinterpret_cast<V *>(&r);
     }
 #else
@@ -362,10 +375,10 @@ namespace b200
       }
     }
 
-    B2_HD float load_norm(int x_cb) const
+    template <Cache c = Cache::REUSE> B2_HD float load_norm(int x_cb) const
     {
       if constexpr (P::fixed)
-        return ld<Cache::REUSE>(norm + x_cb);
+        return ld<c>(norm + x_cb);
       else
         return 1.0f;
     }
@@ -375,7 +388,7 @@ namespace b200
     {
       load_planes<0, 24 / P::Ns, c>(out, x_cb);
       if constexpr (P::fixed) {
-        const float n = load_norm(x_cb);
+        const float n = load_norm<c == Cache::COHERENT ? Cache::COHERENT : Cache::REUSE>(x_cb);
 #pragma unroll
         for (int i = 0; i < 24; i++) out[i] *= n;
       }
@@ -431,11 +444,11 @@ namespace b200
       const V *base = reinterpret_cast<const V *>(v);
 #pragma unroll
       for (int i = 0; i < 12 / N; i++) {
-        const V t = ld<Cache::STREAM>(base + (size_t)i * face_cb + idx);
+        const V t = ld<Cache::COHERENT>(base + (size_t)i * face_cb + idx); // written by the neighbour while we are resident
         vec_to_real(out + i * N, t);
       }
       if constexpr (P::fixed) {
-        const float n = ld<Cache::STREAM>(norm + idx);
+        const float n = ld<Cache::COHERENT>(norm + idx);
 #pragma unroll
         for (int i = 0; i < 12; i++) out[i] *= n;
       }

@@ -657,7 +657,7 @@ namespace b200
     for (int i = 0; i < 24; i++) acc[i] = 0;
     wilson_hops<P, recon, dagger, K_EXTERIOR_ALL>(acc, arg, x, x_cb, parity);
     real partial[24];
-    arg.out[parity].template load<Cache::STREAM>(partial, x_cb);
+    arg.out[parity].template load<Cache::COHERENT>(partial, x_cb); // read-modify-write of `out`: not the .nc path
     if constexpr (op == OP_CLOVER_PC || op == OP_TM_PC) {
 #pragma unroll
       for (int i = 0; i < 24; i++) acc[i] += partial[i];

@@ -1,9 +1,10 @@
-// Implementation of the host-side operator / blas / solver mirror (see dirac.h for the reference citations).
+// Implementation of the host-side operator / blas / solver layer (design notes and reference citations: dirac.h).
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <cuda_runtime.h>
 
 #include "dirac.h"
@@ -21,6 +22,7 @@ namespace b200
     {
       if (rc != B200_SUCCESS) throw Error(b200_last_error());
     }
+    static cudaStream_t cs(void *s) { return static_cast<cudaStream_t>(s); }
 
     // ------------------------------------------------------------------ fields
     static size_t parity_bytes_of(const int *X, int precision)
@@ -53,7 +55,7 @@ namespace b200
 
     ColorSpinorField ColorSpinorField::parity_view(int p) const
     {
-      if (n_parity != 2) throw Error("parity_view of a single-parity field");
+      if (n_parity != 2) throw Error("parity_view needs a full (two-parity) field");
       ColorSpinorField f = wrap(static_cast<char *>(v) + p * parity_bytes, X, precision, 1);
       f.owned = owned;
       return f;
@@ -70,46 +72,68 @@ namespace b200
       return s;
     }
 
-    // Field temporaries (reference: getFieldTmp / lib/field_cache.cpp): operators need a scratch field per application;
-    // cudaMalloc per call would serialise the stream, so released temporaries are parked in a free list and reused.
+    // Scratch fields: an operator application needs one or two temporaries; cudaMalloc per call would serialise the
+    // device, so released temporaries are parked and reused -- per stream, because a parked buffer may still be read by
+    // kernels queued on the stream that used it last.
     namespace
     {
-      struct TmpPool {
-        std::vector<ColorSpinorField> free_list;
-        ColorSpinorField get(const int *X, int precision, int n_parity)
+      struct ScratchPool {
+        std::multimap<void *, ColorSpinorField> parked; // keyed by stream
+        ColorSpinorField get(void *stream, const int *X, int precision, int n_parity)
         {
-          for (size_t i = 0; i < free_list.size(); i++) {
-            auto &f = free_list[i];
+          auto range = parked.equal_range(stream);
+          for (auto it = range.first; it != range.second; ++it) {
+            const ColorSpinorField &f = it->second;
             if (f.precision == precision && f.n_parity == n_parity && f.X[0] == X[0] && f.X[1] == X[1] && f.X[2] == X[2]
                 && f.X[3] == X[3]) {
               ColorSpinorField r = f;
-              free_list.erase(free_list.begin() + i);
+              parked.erase(it);
               return r;
             }
           }
           return ColorSpinorField::create(X, precision, n_parity);
         }
-        void put(const ColorSpinorField &f) { free_list.push_back(f); }
+        void put(void *stream, const ColorSpinorField &f) { parked.emplace(stream, f); }
       };
-      TmpPool &pool()
+      ScratchPool &pool()
       {
-        static TmpPool p;
+        static ScratchPool p;
         return p;
       }
-      struct FieldTmp {
+      struct Scratch {
+        void *stream;
         ColorSpinorField f;
-        FieldTmp(const ColorSpinorField &like, int n_parity) : f(pool().get(like.X, like.precision, n_parity)) { }
-        ~FieldTmp() { pool().put(f); }
+        Scratch(void *stream_, const ColorSpinorField &like, int n_parity) :
+          stream(stream_), f(pool().get(stream_, like.X, like.precision, n_parity))
+        {
+        }
+        ~Scratch() { pool().put(stream, f); }
         operator ColorSpinorField &() { return f; }
       };
+
+      // fork / join events of the two-stream halo schedule, one pair per halo context
+      struct StreamEvents {
+        cudaEvent_t fork = nullptr, join = nullptr;
+      };
+      StreamEvents &events_of(CommContext *c)
+      {
+        static std::map<CommContext *, StreamEvents> m;
+        StreamEvents &e = m[c];
+        if (!e.fork) {
+          cuda_ok(cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming), "event");
+          cuda_ok(cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming), "event");
+        }
+        return e;
+      }
     } // namespace
 
     // ------------------------------------------------------------------ Apply*
-    static void halo_fill(b200_halo &h, const int *comm_override, const CommContext *comm)
+    static void halo_fill(b200_halo &h, const int *comm_override, CommContext *comm)
     {
       memset(&h, 0, sizeof(h));
       if (!comm) return;
-      const int b = comm->seq & 1;
+      const unsigned seq = comm->seq();
+      const int b = seq & 1;
       for (int d = 0; d < 4; d++) {
         h.comm_dim[d] = comm->comm_dim[d] && (!comm_override || comm_override[d]);
         for (int dir = 0; dir < 2; dir++) {
@@ -117,7 +141,7 @@ namespace b200
           h.wait_flag[d][dir] = h.comm_dim[d] ? comm->recv_flag[b][d][dir] : nullptr;
         }
       }
-      h.seq = comm->seq;
+      h.seq = seq;
       h.timeout_flag = comm->timeout_flag;
     }
 
@@ -125,8 +149,8 @@ namespace b200
     static void exchange_start(const ColorSpinorField &in, int in_parity, bool dagger, const int *comm_override,
                                CommContext *comm, void *stream)
     {
-      comm->seq++;
-      const int b = comm->seq & 1;
+      const unsigned seq = ++comm->seq();
+      const int b = seq & 1;
       b200_pack_args a;
       memset(&a, 0, sizeof(a));
       a.abi_version = B200_ABI_VERSION;
@@ -143,13 +167,12 @@ namespace b200
       a.dagger = dagger;
       a.in = in.desc();
       a.block_counter = comm->block_counter;
-      a.seq = comm->seq;
+      a.seq = seq;
       if (comm->pack_stream && comm->pack_stream != stream) {
         // fork: the pack kernel runs on its own stream, concurrently with the interior tiles (joined in apply())
-        static cudaEvent_t fork_ev = nullptr;
-        if (!fork_ev) cuda_ok(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming), "event");
-        cuda_ok(cudaEventRecord(fork_ev, (cudaStream_t)stream), "record");
-        cuda_ok(cudaStreamWaitEvent((cudaStream_t)comm->pack_stream, fork_ev, 0), "wait");
+        StreamEvents &ev = events_of(comm);
+        cuda_ok(cudaEventRecord(ev.fork, cs(stream)), "record");
+        cuda_ok(cudaStreamWaitEvent(cs(comm->pack_stream), ev.fork, 0), "wait");
         a.stream = comm->pack_stream;
       } else {
         a.stream = stream;
@@ -164,6 +187,8 @@ namespace b200
                       const int *comm_override, CommContext *comm, void *stream, double b = 0.0, bool asymmetric = false,
                       int with_x = -1)
     {
+      if (in.precision != U.precision)
+        throw Error("spinor precision " + std::to_string(in.precision) + " does not match the gauge field's " + std::to_string(U.precision));
       b200_dslash_args args;
       memset(&args, 0, sizeof(args));
       args.abi_version = B200_ABI_VERSION;
@@ -185,14 +210,14 @@ namespace b200
       if (comm)
         for (int d = 0; d < 4; d++) part |= (comm->comm_dim[d] && (!comm_override || comm_override[d]));
       if (part) {
-        if (in.n_parity != 1) throw Error("partitioned full-field Dslash: apply per parity (Dirac::M does)");
+        if (in.n_parity != 1) throw Error("a partitioned Dslash works on one parity at a time");
         exchange_start(in, 1 - parity, dagger, comm_override, comm, stream);
       }
       halo_fill(args.halo, comm_override, part ? comm : nullptr);
       const bool two_streams = part && comm->pack_stream && comm->pack_stream != stream;
       if (two_streams) {
-        // side stream (behind the pack kernel): boundary tiles -- they depend only on the halo, not on the interior
-        // launch; main stream: the interior tiles.  Both halves write disjoint sites.
+        // side stream (behind the pack kernel): boundary sites -- they depend only on the halo, not on the interior
+        // launch; main stream: the interior.  Both halves write disjoint sites.
         args.kernel = B200_KERNEL_BOUNDARY_TILES;
         args.stream = comm->pack_stream;
         abi_ok(b200_dslash_apply(&args));
@@ -200,10 +225,9 @@ namespace b200
         args.stream = stream;
         abi_ok(b200_dslash_apply(&args));
         // join: `out` is complete, and `in` may be overwritten, only after the side stream has drained
-        static cudaEvent_t join_ev = nullptr;
-        if (!join_ev) cuda_ok(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming), "event");
-        cuda_ok(cudaEventRecord(join_ev, (cudaStream_t)comm->pack_stream), "record");
-        cuda_ok(cudaStreamWaitEvent((cudaStream_t)stream, join_ev, 0), "wait");
+        StreamEvents &ev = events_of(comm);
+        cuda_ok(cudaEventRecord(ev.join, cs(comm->pack_stream)), "record");
+        cuda_ok(cudaStreamWaitEvent(cs(stream), ev.join, 0), "wait");
       } else {
         args.stream = stream;
         abi_ok(b200_dslash_apply(&args));
@@ -261,41 +285,29 @@ namespace b200
       abi_ok(b200_clover_apply(&o, &i, &c, in.precision, inverse, parity, stream));
     }
 
-    // ------------------------------------------------------------------ blas
+    bool halo_timed_out(CommContext *comm, void *stream)
+    {
+      if (!comm || !comm->timeout_flag) return false;
+      int flag = 0;
+      cuda_ok(cudaMemcpyAsync(&flag, comm->timeout_flag, sizeof(int), cudaMemcpyDeviceToHost, cs(stream)), "memcpy(timeout flag)");
+      cuda_ok(cudaStreamSynchronize(cs(stream)), "sync");
+      if (flag) cuda_ok(cudaMemsetAsync(comm->timeout_flag, 0, sizeof(int), cs(stream)), "memset(timeout flag)");
+      return flag != 0;
+    }
+
+    // ------------------------------------------------------------------ blas + reductions
     namespace blas
     {
       static long long g_flops = 0;
       long long flops() { return g_flops; }
 
-      static double *reduce_buf()
-      {
-        static double *d = nullptr;
-        if (!d) cuda_ok(cudaMalloc(&d, 4 * sizeof(double)), "cudaMalloc(reduce)");
-        return d;
-      }
+      constexpr int kBlocks = 148 * 4, kThreads = 256, kMaxVals = 2;
 
-      template <typename T> __device__ __forceinline__ double blk_sum(double v, double *out)
-      {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        __shared__ double s[32];
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0) s[w] = v;
-        __syncthreads();
-        if (w == 0) {
-          v = l < (blockDim.x >> 5) ? s[l] : 0.0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-          if (l == 0) atomicAdd(out, v);
-        }
-        return v;
-      }
+      // device-resident scalars of a solve (read by the update kernels, written by the reduction finalisers)
+      enum Scalar { S_R2 = 0, S_R2_OLD = 1, S_PAP = 2, S_ALPHA = 3, S_BETA = 4, S_RAW0 = 5, S_RAW1 = 6, S_COUNT = 8 };
+      enum Finish { FIN_RAW = 0, FIN_PAP = 1, FIN_R2 = 2 };
 
-      // ---- NVLink mailbox all-reduce of up to 4 doubles (b200_comm::reduce_peer).  One warp: lane r < n_ranks pushes this
-      // rank's partial sums into its slot of rank r's mailbox and raises the slot's sequence number, then waits for
-      // rank r's contribution in the local mailbox; lane 0 adds the contributions in rank order (identical on every
-      // rank).  Slots are double buffered by the parity of `seq`: a rank can only be one reduction ahead of the
-      // slowest one, because finishing reduction k needs everybody's contribution to k.
+      // NVLink mailboxes of the all-reduce (b200_comm::reduce_peer): slot [parity of seq][source rank] in every rank's box
       struct ReduceSlot {
         double v[4];
         unsigned seq;
@@ -304,61 +316,151 @@ namespace b200
       static_assert(sizeof(ReduceSlot) == B200_REDUCE_SLOT_BYTES, "mailbox slot layout");
       struct ReducePeers {
         ReduceSlot *box[B200_MAX_RANKS];
+        int rank, n_ranks;
+        unsigned seq;
+        int *timeout_flag;
       };
 
-      __global__ void mailbox_allreduce_kernel(double *__restrict__ val, int n, ReducePeers peers, int rank, int n_ranks,
-                                               unsigned seq, int *timeout_flag)
+      // per-stream reduction workspace
+      struct Workspace {
+        double *partials = nullptr; // [kBlocks][kMaxVals]
+        unsigned *ticket = nullptr;
+        double *scalars = nullptr;  // [S_COUNT] on the device
+        double *host = nullptr;     // pinned + mapped: [ring][S_COUNT], written by the finalisers
+        double *host_dev = nullptr; // device alias of `host`
+        cudaEvent_t ev[8] = {};
+        unsigned long long ring = 0;
+      };
+      static Workspace &workspace(void *stream)
       {
-        __shared__ double part[B200_MAX_RANKS][4];
+        static std::map<void *, Workspace> m;
+        Workspace &w = m[stream];
+        if (!w.partials) {
+          cuda_ok(cudaMalloc(&w.partials, sizeof(double) * kBlocks * kMaxVals), "cudaMalloc(reduce)");
+          cuda_ok(cudaMalloc(&w.ticket, sizeof(unsigned)), "cudaMalloc(reduce)");
+          cuda_ok(cudaMemset(w.ticket, 0, sizeof(unsigned)), "memset");
+          cuda_ok(cudaMalloc(&w.scalars, sizeof(double) * S_COUNT), "cudaMalloc(reduce)");
+          cuda_ok(cudaMemset(w.scalars, 0, sizeof(double) * S_COUNT), "memset");
+          cuda_ok(cudaHostAlloc(&w.host, sizeof(double) * 8 * S_COUNT, cudaHostAllocMapped), "cudaHostAlloc(reduce)");
+          cuda_ok(cudaHostGetDevicePointer(&w.host_dev, w.host, 0), "cudaHostGetDevicePointer");
+          for (auto &e : w.ev) cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+        }
+        return w;
+      }
+
+      // Second stage of every reduction, run by the block that arrives last: sum the per-block partial sums in block
+      // order (fixed -> bit-reproducible), all-reduce over the ranks through the NVLink mailboxes in rank order, derive
+      // the CG scalars and publish everything to the host mirror.
+      template <int NV>
+      __device__ void finish_reduction(const double *acc_block, double *partials, unsigned *ticket, double *S, double *host_out,
+                                       int fin, ReducePeers peers)
+      {
+        __shared__ double sh[kThreads][kMaxVals];
+        __shared__ bool is_last;
+        __shared__ double part[B200_MAX_RANKS][kMaxVals];
         const int t = threadIdx.x;
-        const int b = seq & 1;
-        if (t < n_ranks) {
-          ReduceSlot *dst = peers.box[t] + b * B200_MAX_RANKS + rank;
-          for (int i = 0; i < n; i++) dst->v[i] = val[i];
-          __threadfence_system();
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->seq), "r"(seq) : "memory");
-          const ReduceSlot *src = peers.box[rank] + b * B200_MAX_RANKS + t;
-          const long long t0 = clock64();
-          for (;;) {
-            unsigned got;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(&src->seq) : "memory");
-            if ((int)(got - seq) >= 0) break;
-            if (clock64() - t0 > 4000000000LL) { // ~2 s: a lost peer must never hang the GPU
-              if (timeout_flag) *timeout_flag = 1;
-              break;
-            }
-            __nanosleep(50);
-          }
-          for (int i = 0; i < n; i++) part[t][i] = *reinterpret_cast<const volatile double *>(&src->v[i]);
+        if (t == 0) {
+          for (int i = 0; i < NV; i++) partials[blockIdx.x * kMaxVals + i] = acc_block[i];
+          __threadfence();
+          is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
         }
         __syncthreads();
-        if (t == 0) {
-          for (int i = 0; i < n; i++) {
-            double acc = 0;
-            for (int r = 0; r < n_ranks; r++) acc += part[r][i];
-            val[i] = acc;
+        if (!is_last) return;
+        __threadfence();
+        double a[kMaxVals] = {0, 0};
+        for (int b = t; b < (int)gridDim.x; b += kThreads)
+          for (int i = 0; i < NV; i++) a[i] += __ldcg(partials + b * kMaxVals + i);
+        for (int i = 0; i < NV; i++) sh[t][i] = a[i];
+        __syncthreads();
+        for (int s = kThreads / 2; s > 0; s >>= 1) {
+          if (t < s)
+            for (int i = 0; i < NV; i++) sh[t][i] += sh[t + s][i];
+          __syncthreads();
+        }
+        if (peers.n_ranks > 1) {
+          const int b = peers.seq & 1;
+          if (t < peers.n_ranks) {
+            ReduceSlot *dst = peers.box[t] + b * B200_MAX_RANKS + peers.rank;
+            for (int i = 0; i < NV; i++) dst->v[i] = sh[0][i];
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->seq), "r"(peers.seq) : "memory");
+            const ReduceSlot *src = peers.box[peers.rank] + b * B200_MAX_RANKS + t;
+            const long long t0 = clock64();
+            for (;;) {
+              unsigned got;
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(&src->seq) : "memory");
+              if ((int)(got - peers.seq) >= 0) break;
+              if (clock64() - t0 > 20000000000LL) { // ~10 s: a lost peer must never hang the GPU
+                if (peers.timeout_flag) *peers.timeout_flag = 1;
+                break;
+              }
+              __nanosleep(40);
+            }
+            for (int i = 0; i < NV; i++) part[t][i] = *reinterpret_cast<const volatile double *>(&src->v[i]);
           }
+          __syncthreads();
+          if (t == 0)
+            for (int i = 0; i < NV; i++) {
+              double s = 0;
+              for (int r = 0; r < peers.n_ranks; r++) s += part[r][i];
+              sh[0][i] = s;
+            }
+        }
+        if (t == 0) {
+          const double v0 = sh[0][0];
+          if (fin == FIN_PAP) {
+            S[S_PAP] = v0;
+            S[S_ALPHA] = S[S_R2] / v0;
+          } else if (fin == FIN_R2) {
+            const double old = S[S_R2];
+            S[S_R2_OLD] = old;
+            S[S_R2] = v0;
+            S[S_BETA] = v0 / old;
+          }
+          S[S_RAW0] = v0;
+          if (NV > 1) S[S_RAW1] = sh[0][1];
+          if (host_out) {
+            for (int i = 0; i < S_COUNT; i++) host_out[i] = S[i];
+            __threadfence_system();
+          }
+          *ticket = 0;
         }
       }
 
-      // sum `n` device doubles over all ranks in place (stream-ordered); false if this CommContext has no mailboxes
-      static bool device_allreduce(double *val, int n, CommContext *comm)
+      __device__ __forceinline__ double warp_sum(double v)
       {
-        if (!comm || comm->n_ranks < 2) return false;
-        if (n > 4 || comm->n_ranks > B200_MAX_RANKS) throw Error("mailbox all-reduce: too many values / ranks");
-        ReducePeers peers;
-        for (int r = 0; r < B200_MAX_RANKS; r++) peers.box[r] = reinterpret_cast<ReduceSlot *>(comm->reduce_peer[r]);
-        comm->reduce_seq++;
-        mailbox_allreduce_kernel<<<1, 32>>>(val, n, peers, comm->rank, comm->n_ranks, comm->reduce_seq, comm->timeout_flag);
-        cuda_ok(cudaGetLastError(), "all-reduce launch");
-        return true;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        return v;
+      }
+      // per-block sum of per-thread values, in a fixed order (warp tree, then warps in index order)
+      __device__ __forceinline__ double block_sum(double v, double *warp_buf)
+      {
+        v = warp_sum(v);
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) warp_buf[w] = v;
+        __syncthreads();
+        double s = 0;
+        if (threadIdx.x == 0)
+          for (int i = 0; i < kThreads / 32; i++) s += warp_buf[i];
+        __syncthreads();
+        return s;
       }
 
-      // y = a x + b y (+ optional z update), optional reduction of |y|^2 or <x,y>; one template keeps it compact
+      struct ReduceArgs {
+        double *partials;
+        unsigned *ticket;
+        double *S;
+        double *host_out;
+        int fin;
+        ReducePeers peers;
+      };
+
+      // y = a x + b y with an optional reduction over the result (R_NORM_Y) or <x, y> (R_DOT_XY)
       enum { R_NONE = 0, R_NORM_Y = 1, R_DOT_XY = 2 };
       template <typename Tx, typename Ty, int R>
-      __global__ void axpby_kernel(double a, const Tx *__restrict__ x, double b, Ty *__restrict__ y, size_t n, double *red,
-                                   bool write)
+      __global__ void __launch_bounds__(kThreads) axpby_kernel(double a, const Tx *__restrict__ x, double b, Ty *__restrict__ y,
+                                                               size_t n, bool write, ReduceArgs ra)
       {
         double acc = 0;
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -368,50 +470,127 @@ namespace b200
           if (R == R_NORM_Y) acc += (write ? (double)(Ty)r * (double)(Ty)r : yv * yv);
           if (R == R_DOT_XY) acc += xv * yv;
         }
-        if (R != R_NONE) blk_sum<double>(acc, red);
-      }
-
-      template <typename T>
-      __global__ void axpyZpbx_kernel(double a, T *__restrict__ p, T *__restrict__ x, const T *__restrict__ r, double b, size_t n)
-      {
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-          const double pv = p[i];
-          x[i] = (T)((double)x[i] + a * pv);
-          p[i] = (T)((double)r[i] + b * pv);
+        if (R != R_NONE) {
+          __shared__ double wb[kThreads / 32];
+          const double s = block_sum(acc, wb);
+          finish_reduction<1>(&s, ra.partials, ra.ticket, ra.S, ra.host_out, ra.fin, ra.peers);
         }
       }
 
+      // ---- the three kernels of a CG iteration; alpha and beta come from the device scalars
+      // r -= alpha Ap ; |r|^2   (finaliser: r2_old <- r2, r2 <- |r|^2, beta <- r2 / r2_old)
+      template <typename T>
+      __global__ void __launch_bounds__(kThreads) cg_update_r_kernel(T *__restrict__ r, const T *__restrict__ Ap, size_t n, ReduceArgs ra)
+      {
+        const double alpha = ra.S[S_ALPHA];
+        double acc = 0;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+          const T v = (T)((double)r[i] - alpha * (double)Ap[i]);
+          r[i] = v;
+          acc += (double)v * (double)v;
+        }
+        __shared__ double wb[kThreads / 32];
+        const double s = block_sum(acc, wb);
+        finish_reduction<1>(&s, ra.partials, ra.ticket, ra.S, ra.host_out, ra.fin, ra.peers);
+      }
+      // x += alpha p ; p = r + beta p   (the reference's axpyZpbx, lib/inv_cg_quda.cpp:389)
+      template <typename T>
+      __global__ void __launch_bounds__(kThreads) cg_update_xp_kernel(T *__restrict__ x, T *__restrict__ p, const T *__restrict__ r,
+                                                                      size_t n, const double *__restrict__ S)
+      {
+        const double alpha = S[S_ALPHA], beta = S[S_BETA];
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+          const double pv = p[i];
+          x[i] = (T)((double)x[i] + alpha * pv);
+          p[i] = (T)((double)r[i] + beta * pv);
+        }
+      }
+      // after a reliable update: p += r_new - r_old ; r_old <- r_new   (keeps p = r + beta p_old with the true residual)
+      template <typename T>
+      __global__ void __launch_bounds__(kThreads) cg_replace_r_kernel(T *__restrict__ p, T *__restrict__ r, const T *__restrict__ r_new, size_t n)
+      {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+          const T rn = r_new[i];
+          p[i] = (T)((double)p[i] + ((double)rn - (double)r[i]));
+          r[i] = rn;
+        }
+      }
+      __global__ void set_scalar_kernel(double *S, int idx, double v) { S[idx] = v; }
+
       static void check_pair(const ColorSpinorField &x, const ColorSpinorField &y)
       {
-        if (x.Length() != y.Length()) throw Error("blas: field length mismatch");
-        if (x.precision == B200_HALF || y.precision == B200_HALF) throw Error("blas: block-float half fields not supported");
+        if (x.Length() != y.Length()) throw Error("blas: operands differ in length");
+        if (x.precision == B200_HALF || y.precision == B200_HALF) throw Error("blas: half-precision (block-float) fields are not supported");
       }
 
-      template <int R>
-      static double run(double a, const ColorSpinorField &x, double b, ColorSpinorField &y, bool write, CommContext *comm)
+      static ReducePeers peers_of(CommContext *comm)
+      {
+        ReducePeers p;
+        memset(&p, 0, sizeof(p));
+        p.n_ranks = 1;
+        if (comm && comm->mailboxes()) {
+          if (comm->n_ranks > B200_MAX_RANKS) throw Error("NVLink all-reduce: more ranks than mailbox slots");
+          for (int r = 0; r < B200_MAX_RANKS; r++) p.box[r] = reinterpret_cast<ReduceSlot *>(comm->reduce_peer[r]);
+          p.rank = comm->rank;
+          p.n_ranks = comm->n_ranks;
+          p.seq = ++comm->reduce_seq();
+          p.timeout_flag = comm->timeout_flag;
+        }
+        return p;
+      }
+
+      // reduction launch bookkeeping: where the finaliser writes, and the event the host may wait on
+      struct Pending {
+        Workspace *w;
+        int slot;
+      };
+      static ReduceArgs reduce_args(const Exec &ex, int fin, Pending &pend)
+      {
+        Workspace &w = workspace(ex.stream);
+        pend.w = &w;
+        pend.slot = (int)(w.ring++ & 7);
+        ReduceArgs ra;
+        ra.partials = w.partials;
+        ra.ticket = w.ticket;
+        ra.S = w.scalars;
+        ra.host_out = w.host_dev + pend.slot * S_COUNT;
+        ra.fin = fin;
+        ra.peers = peers_of(ex.comm);
+        return ra;
+      }
+      static void mark(const Exec &ex, const Pending &p) { cuda_ok(cudaEventRecord(p.w->ev[p.slot], cs(ex.stream)), "record"); }
+      // wait for a reduction launched earlier and return the host mirror of the device scalars as of that launch;
+      // multi-rank sums without NVLink mailboxes go through the host callback here
+      static const double *await(const Exec &ex, const Pending &p, bool need_host_allreduce, double *scratch)
+      {
+        cuda_ok(cudaEventSynchronize(p.w->ev[p.slot]), "event sync");
+        const double *h = p.w->host + p.slot * S_COUNT;
+        if (!need_host_allreduce) return h;
+        memcpy(scratch, h, sizeof(double) * S_COUNT);
+        ex.comm->allreduce_sum(&scratch[S_RAW0], 1, ex.comm->user);
+        return scratch;
+      }
+      static bool host_allreduce(const Exec &ex) { return ex.comm && !ex.comm->mailboxes() && ex.comm->allreduce_sum; }
+
+      template <int R> static double run(double a, const ColorSpinorField &x, double b, ColorSpinorField &y, bool write, const Exec &ex)
       {
         check_pair(x, y);
-        if (x.precision != y.precision) throw Error("blas: mixed-precision operands (use blas::copy to convert)");
+        if (x.precision != y.precision) throw Error("blas: operands differ in precision (convert with blas::copy)");
         const size_t n = x.Length();
-        double *red = reduce_buf();
-        if (R != R_NONE) cuda_ok(cudaMemsetAsync(red, 0, sizeof(double)), "memset");
-        const int threads = 256, blocks = 148 * 8;
-        if (x.precision == 8 && y.precision == 8)
-          axpby_kernel<double, double, R><<<blocks, threads>>>(a, (const double *)x.v, b, (double *)y.v, n, red, write);
-        else if (x.precision == 4 && y.precision == 4)
-          axpby_kernel<float, float, R><<<blocks, threads>>>(a, (const float *)x.v, b, (float *)y.v, n, red, write);
-        else if (x.precision == 8 && y.precision == 4)
-          axpby_kernel<double, float, R><<<blocks, threads>>>(a, (const double *)x.v, b, (float *)y.v, n, red, write);
+        Pending pend {};
+        ReduceArgs ra {};
+        if (R != R_NONE) ra = reduce_args(ex, FIN_RAW, pend);
+        cudaStream_t s = cs(ex.stream);
+        if (x.precision == 8)
+          axpby_kernel<double, double, R><<<kBlocks, kThreads, 0, s>>>(a, (const double *)x.v, b, (double *)y.v, n, write, ra);
         else
-          axpby_kernel<float, double, R><<<blocks, threads>>>(a, (const float *)x.v, b, (double *)y.v, n, red, write);
+          axpby_kernel<float, float, R><<<kBlocks, kThreads, 0, s>>>(a, (const float *)x.v, b, (float *)y.v, n, write, ra);
         cuda_ok(cudaGetLastError(), "blas launch");
         g_flops += 3 * (long long)n;
         if (R == R_NONE) return 0.0;
-        double h = 0;
-        const bool on_device = device_allreduce(red, 1, comm); // NVLink mailboxes if wired, else the host callback
-        cuda_ok(cudaMemcpy(&h, red, sizeof(double), cudaMemcpyDeviceToHost), "memcpy(reduce)");
-        if (!on_device && comm && comm->allreduce_sum) comm->allreduce_sum(&h, 1, comm->user);
-        return h;
+        mark(ex, pend);
+        double scratch[S_COUNT];
+        return await(ex, pend, host_allreduce(ex), scratch)[S_RAW0];
       }
 
       // Precision conversion has to go through the site/component map: the native order of fp64 fields is planes of 2
@@ -432,68 +611,226 @@ namespace b200
         for (int r = 0; r < 24; r++) d[((size_t)(r / Nd) * volume_cb + x) * Nd + r % Nd] = (Td)v[r];
       }
 
-      void copy(ColorSpinorField &dst, const ColorSpinorField &src)
+      void copy(ColorSpinorField &dst, const ColorSpinorField &src, const Exec &ex)
       {
         check_pair(src, dst);
-        if (dst.n_parity != src.n_parity) throw Error("copy: site subsets differ");
+        if (dst.n_parity != src.n_parity) throw Error("blas::copy: fields cover different site subsets");
         if (src.precision == dst.precision) {
-          cuda_ok(cudaMemcpyAsync(dst.v, src.v, src.Bytes(), cudaMemcpyDeviceToDevice), "copy");
+          if (dst.v != src.v) cuda_ok(cudaMemcpyAsync(dst.v, src.v, src.Bytes(), cudaMemcpyDeviceToDevice, cs(ex.stream)), "copy");
           return;
         }
         const int vcb = src.VolumeCB();
         dim3 grid((vcb + 127) / 128, src.n_parity);
         const size_t se = (size_t)24 * vcb, de = (size_t)24 * vcb;
         if (src.precision == 8)
-          convert_kernel<double, 2, float, 4><<<grid, 128>>>((const double *)src.v, (float *)dst.v, vcb, se, de);
+          convert_kernel<double, 2, float, 4><<<grid, 128, 0, cs(ex.stream)>>>((const double *)src.v, (float *)dst.v, vcb, se, de);
         else
-          convert_kernel<float, 4, double, 2><<<grid, 128>>>((const float *)src.v, (double *)dst.v, vcb, se, de);
+          convert_kernel<float, 4, double, 2><<<grid, 128, 0, cs(ex.stream)>>>((const float *)src.v, (double *)dst.v, vcb, se, de);
         cuda_ok(cudaGetLastError(), "convert launch");
       }
-      void zero(ColorSpinorField &x) { cuda_ok(cudaMemsetAsync(x.v, 0, x.Bytes()), "memset"); }
-      void ax(double a, ColorSpinorField &x) { run<R_NONE>(0.0, x, a, x, true, nullptr); }
-      void axpy(double a, const ColorSpinorField &x, ColorSpinorField &y) { run<R_NONE>(a, x, 1.0, y, true, nullptr); }
-      void xpay(const ColorSpinorField &x, double a, ColorSpinorField &y) { run<R_NONE>(1.0, x, a, y, true, nullptr); }
-      void axpby(double a, const ColorSpinorField &x, double b, ColorSpinorField &y) { run<R_NONE>(a, x, b, y, true, nullptr); }
-      double norm2(const ColorSpinorField &x, CommContext *comm)
+      void zero(ColorSpinorField &x, const Exec &ex) { cuda_ok(cudaMemsetAsync(x.v, 0, x.Bytes(), cs(ex.stream)), "memset"); }
+      void ax(double a, ColorSpinorField &x, const Exec &ex) { run<R_NONE>(0.0, x, a, x, true, ex); }
+      void axpy(double a, const ColorSpinorField &x, ColorSpinorField &y, const Exec &ex) { run<R_NONE>(a, x, 1.0, y, true, ex); }
+      void xpay(const ColorSpinorField &x, double a, ColorSpinorField &y, const Exec &ex) { run<R_NONE>(1.0, x, a, y, true, ex); }
+      void axpby(double a, const ColorSpinorField &x, double b, ColorSpinorField &y, const Exec &ex) { run<R_NONE>(a, x, b, y, true, ex); }
+      double norm2(const ColorSpinorField &x, const Exec &ex)
       {
-        return run<R_NORM_Y>(0.0, x, 1.0, const_cast<ColorSpinorField &>(x), false, comm);
+        return run<R_NORM_Y>(0.0, x, 1.0, const_cast<ColorSpinorField &>(x), false, ex);
       }
-      double reDotProduct(const ColorSpinorField &x, const ColorSpinorField &y, CommContext *comm)
+      double reDotProduct(const ColorSpinorField &x, const ColorSpinorField &y, const Exec &ex)
       {
-        return run<R_DOT_XY>(0.0, x, 1.0, const_cast<ColorSpinorField &>(y), false, comm);
+        return run<R_DOT_XY>(0.0, x, 1.0, const_cast<ColorSpinorField &>(y), false, ex);
       }
-      double axpyNorm(double a, const ColorSpinorField &x, ColorSpinorField &y, CommContext *comm)
+      double axpyNorm(double a, const ColorSpinorField &x, ColorSpinorField &y, const Exec &ex) { return run<R_NORM_Y>(a, x, 1.0, y, true, ex); }
+      double xmyNorm(const ColorSpinorField &x, ColorSpinorField &y, const Exec &ex) { return run<R_NORM_Y>(1.0, x, -1.0, y, true, ex); }
+
+      // ---- CG iteration pieces (used by invertCG below)
+      static void set_scalar(const Exec &ex, int idx, double v)
       {
-        return run<R_NORM_Y>(a, x, 1.0, y, true, comm);
+        set_scalar_kernel<<<1, 1, 0, cs(ex.stream)>>>(workspace(ex.stream).scalars, idx, v);
+        cuda_ok(cudaGetLastError(), "scalar launch");
       }
-      double xmyNorm(const ColorSpinorField &x, ColorSpinorField &y, CommContext *comm)
+      // <p, Ap> -> pAp, alpha = r2 / pAp (device)
+      static Pending cg_dot(const ColorSpinorField &p, const ColorSpinorField &Ap, const Exec &ex)
       {
-        return run<R_NORM_Y>(1.0, x, -1.0, y, true, comm);
-      }
-      void axpyZpbx(double a, ColorSpinorField &p, ColorSpinorField &x, const ColorSpinorField &r, double b)
-      {
-        check_pair(p, x);
-        check_pair(p, r);
-        if (p.precision != x.precision || p.precision != r.precision) throw Error("axpyZpbx: mixed precision");
+        check_pair(p, Ap);
+        Pending pend {};
+        ReduceArgs ra = reduce_args(ex, FIN_PAP, pend);
         const size_t n = p.Length();
         if (p.precision == 8)
-          axpyZpbx_kernel<double><<<148 * 8, 256>>>(a, (double *)p.v, (double *)x.v, (const double *)r.v, b, n);
+          axpby_kernel<double, double, R_DOT_XY><<<kBlocks, kThreads, 0, cs(ex.stream)>>>(0.0, (const double *)p.v, 1.0, (double *)Ap.v, n, false, ra);
         else
-          axpyZpbx_kernel<float><<<148 * 8, 256>>>(a, (float *)p.v, (float *)x.v, (const float *)r.v, b, n);
+          axpby_kernel<float, float, R_DOT_XY><<<kBlocks, kThreads, 0, cs(ex.stream)>>>(0.0, (const float *)p.v, 1.0, (float *)Ap.v, n, false, ra);
+        cuda_ok(cudaGetLastError(), "blas launch");
+        g_flops += 2 * (long long)n;
+        mark(ex, pend);
+        return pend;
+      }
+      static Pending cg_update_r(ColorSpinorField &r, const ColorSpinorField &Ap, const Exec &ex)
+      {
+        check_pair(r, Ap);
+        Pending pend {};
+        ReduceArgs ra = reduce_args(ex, FIN_R2, pend);
+        const size_t n = r.Length();
+        if (r.precision == 8)
+          cg_update_r_kernel<double><<<kBlocks, kThreads, 0, cs(ex.stream)>>>((double *)r.v, (const double *)Ap.v, n, ra);
+        else
+          cg_update_r_kernel<float><<<kBlocks, kThreads, 0, cs(ex.stream)>>>((float *)r.v, (const float *)Ap.v, n, ra);
+        cuda_ok(cudaGetLastError(), "blas launch");
+        g_flops += 4 * (long long)n;
+        mark(ex, pend);
+        return pend;
+      }
+      static void cg_update_xp(ColorSpinorField &x, ColorSpinorField &p, const ColorSpinorField &r, const Exec &ex)
+      {
+        check_pair(x, p);
+        const size_t n = p.Length();
+        const double *S = workspace(ex.stream).scalars;
+        if (p.precision == 8)
+          cg_update_xp_kernel<double><<<kBlocks, kThreads, 0, cs(ex.stream)>>>((double *)x.v, (double *)p.v, (const double *)r.v, n, S);
+        else
+          cg_update_xp_kernel<float><<<kBlocks, kThreads, 0, cs(ex.stream)>>>((float *)x.v, (float *)p.v, (const float *)r.v, n, S);
         cuda_ok(cudaGetLastError(), "blas launch");
         g_flops += 4 * (long long)n;
       }
+      static void cg_replace_r(ColorSpinorField &p, ColorSpinorField &r, const ColorSpinorField &r_new, const Exec &ex)
+      {
+        check_pair(p, r_new);
+        const size_t n = p.Length();
+        if (p.precision == 8)
+          cg_replace_r_kernel<double><<<kBlocks, kThreads, 0, cs(ex.stream)>>>((double *)p.v, (double *)r.v, (const double *)r_new.v, n);
+        else
+          cg_replace_r_kernel<float><<<kBlocks, kThreads, 0, cs(ex.stream)>>>((float *)p.v, (float *)r.v, (const float *)r_new.v, n);
+        cuda_ok(cudaGetLastError(), "blas launch");
+        g_flops += 2 * (long long)n;
+      }
     } // namespace blas
 
-    // ------------------------------------------------------------------ Dirac
-    Dirac::Dirac(const DiracParam &p) :
-      gauge(p.gauge), kappa(p.kappa), matpcType(p.matpcType), dagger(p.dagger), comm(p.comm), stream(p.stream)
+    // ------------------------------------------------------------------ the even-odd operator
+    Dirac::Dirac(SiteTerm term_, bool schur_, const DiracParam &p) :
+      gauge(p.gauge), clover(p.clover), kappa(p.kappa), mu(p.mu), matpcType(p.matpcType), dagger(p.dagger), comm(p.comm),
+      stream(p.stream), term(term_), schur(schur_)
     {
-      if (!gauge) throw Error("Dirac: gauge field missing");
+      if (!gauge) throw Error("operator needs a gauge field");
+      if (term == SiteTerm::Clover) {
+        if (!clover) throw Error("clover operator needs a clover field");
+        if (schur && !clover->has_inverse() && !clover->c.dynamic_inverse)
+          throw Error("even-odd preconditioned clover operator needs A^-1 (a static inverse field or dynamic_inverse)");
+      }
       for (int d = 0; d < 4; d++) commDim[d] = p.commDim[d];
       symmetric = (matpcType == QUDA_MATPC_EVEN_EVEN || matpcType == QUDA_MATPC_ODD_ODD);
       this_parity = (matpcType == QUDA_MATPC_EVEN_EVEN || matpcType == QUDA_MATPC_EVEN_EVEN_ASYMMETRIC) ? 0 : 1;
       other_parity = 1 - this_parity;
+    }
+
+    Dirac *Dirac::create(const std::string &type, const DiracParam &p)
+    {
+      if (type == "wilson") return new Dirac(SiteTerm::Identity, false, p);
+      if (type == "wilsonpc") return new Dirac(SiteTerm::Identity, true, p);
+      if (type == "clover") return new Dirac(SiteTerm::Clover, false, p);
+      if (type == "cloverpc") return new Dirac(SiteTerm::Clover, true, p);
+      if (type == "twistedmass") return new Dirac(SiteTerm::Twist, false, p);
+      if (type == "twistedmasspc") return new Dirac(SiteTerm::Twist, true, p);
+      throw Error("no operator of type '" + type + "' in this engine");
+    }
+
+    static void need_single_parity(const ColorSpinorField &a, const ColorSpinorField &b)
+    {
+      if (a.n_parity != 1 || b.n_parity != 1) throw Error("this operation acts on single-parity fields");
+      if (a.v == b.v) throw Error("input and output must be different fields");
+    }
+    static void need_full(const ColorSpinorField &a, const ColorSpinorField &b)
+    {
+      if (a.n_parity != 2 || b.n_parity != 2) throw Error("this operation acts on full (two-parity) fields");
+    }
+
+    // One Dslash launch: out = [x +] k * (site-term fused in the epilogue) D in
+    //   Fuse::None     : out = D in                | x + k D in
+    //   Fuse::A        : out = A x + k D in        (always with x)
+    //   Fuse::AinvPost : out = A^-1 D in           | x + k A^-1 D in
+    // For the identity site term all three coincide with the Wilson form.
+    void Dirac::hop(ColorSpinorField &out, const ColorSpinorField &in, int parity, Fuse f, const ColorSpinorField *x, double k) const
+    {
+      need_single_parity(in, out);
+      const ColorSpinorField &xf = x ? *x : in;
+      const double a = x ? k : 0.0;
+      if (term == SiteTerm::Identity || f == Fuse::None) {
+        ApplyWilson(out, in, *gauge, a, xf, parity, dagger, commDim, comm, stream);
+      } else if (term == SiteTerm::Clover) {
+        if (f == Fuse::A) {
+          if (!x) throw Error("A x + k D in needs x");
+          ApplyWilsonClover(out, in, *gauge, *clover, a, xf, parity, dagger, commDim, comm, stream);
+        } else {
+          ApplyWilsonCloverPreconditioned(out, in, *gauge, *clover, a, xf, parity, dagger, commDim, comm, stream);
+        }
+      } else { // twist: A = 1 + i 2 kappa mu gamma5, A^-1 = (1 - i 2 kappa mu gamma5) / (1 + (2 kappa mu)^2)
+        if (f == Fuse::A) {
+          if (!x) throw Error("the twisted-mass Dslash exists only in its xpay form");
+          ApplyTwistedMass(out, in, *gauge, a, 2 * mu * kappa, xf, parity, dagger, commDim, comm, stream);
+        } else {
+          const double tw = -2.0 * kappa * mu;
+          const double nrm = 1.0 / (1.0 + tw * tw);
+          const bool asym = !symmetric && dagger;
+          ApplyTwistedMassPreconditioned(out, in, *gauge, x ? k * nrm : nrm, tw, x != nullptr, xf, parity, dagger, asym, commDim, comm, stream);
+        }
+      }
+      dslash_applications++;
+    }
+
+    // out = A in or A^-1 in on one parity
+    void Dirac::site(ColorSpinorField &out, const ColorSpinorField &in, int parity, bool inverse) const
+    {
+      switch (term) {
+      case SiteTerm::Identity: blas::copy(out, in, exec()); break;
+      case SiteTerm::Clover: ApplyClover(out, in, *clover, inverse, parity, stream); break;
+      case SiteTerm::Twist: ApplyTwistGamma(out, in, kappa, mu, dagger, inverse, stream); break;
+      }
+    }
+
+    void Dirac::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
+    {
+      if (term == SiteTerm::Twist && !schur) throw Error("the unpreconditioned twisted-mass Dslash exists only in its xpay form");
+      hop(out, in, parity, schur ? Fuse::AinvPost : Fuse::None, nullptr, 0.0);
+    }
+
+    void Dirac::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x, double k) const
+    {
+      hop(out, in, parity, schur ? Fuse::AinvPost : Fuse::A, &x, k);
+    }
+
+    void Dirac::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    {
+      if (!schur) {
+        // out_p = A_p in_p - kappa D in_{1-p}
+        need_full(out, in);
+        const bool one_launch = term != SiteTerm::Twist && !(comm && comm->partitioned());
+        if (one_launch) { // both parities in one launch (full-field kernel)
+          if (term == SiteTerm::Identity)
+            ApplyWilson(out, in, *gauge, -kappa, in, QUDA_INVALID_PARITY, dagger, commDim, comm, stream);
+          else
+            ApplyWilsonClover(out, in, *gauge, *clover, -kappa, in, QUDA_INVALID_PARITY, dagger, commDim, comm, stream);
+          dslash_applications += 2;
+        } else {
+          for (int p = 0; p < 2; p++) {
+            auto o = out.parity_view(p);
+            const auto x = in.parity_view(p);
+            hop(o, in.parity_view(1 - p), p, Fuse::A, &x, -kappa);
+          }
+        }
+        return;
+      }
+      // Schur complement on `this_parity`
+      const double k2 = -kappa * kappa;
+      Scratch tmp(stream, in, 1);
+      if (term == SiteTerm::Clover && symmetric && dagger) {
+        // (1 - k^2 A^-1 D A^-1 D)^dagger = 1 - k^2 D^dagger A^-1 D^dagger A^-1   (A hermitian)
+        site(out, in, this_parity, true);
+        hop(tmp, out, other_parity, Fuse::AinvPost, nullptr, 0.0);
+        hop(out, tmp, this_parity, Fuse::None, &in, k2);
+      } else {
+        hop(tmp, in, other_parity, Fuse::AinvPost, nullptr, 0.0);
+        hop(out, tmp, this_parity, symmetric ? Fuse::AinvPost : Fuse::A, &in, k2);
+      }
     }
 
     void Dirac::Mdag(ColorSpinorField &out, const ColorSpinorField &in) const
@@ -508,407 +845,218 @@ namespace b200
       flipDagger();
     }
 
-    Dirac *Dirac::create(const std::string &type, const DiracParam &p)
+    void Dirac::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
     {
-      if (type == "wilson") return new DiracWilson(p);
-      if (type == "wilsonpc") return new DiracWilsonPC(p);
-      if (type == "clover") return new DiracClover(p);
-      if (type == "cloverpc") return new DiracCloverPC(p);
-      if (type == "twistedmass") return new DiracTwistedMass(p);
-      if (type == "twistedmasspc") return new DiracTwistedMassPC(p);
-      throw Error("Dirac::create: unsupported operator type '" + type + "'");
-    }
-
-    static void check_parity_spinor(const ColorSpinorField &a, const ColorSpinorField &b)
-    {
-      if (a.n_parity != 1 || b.n_parity != 1) throw Error("ColorSpinorFields are not single parity");
-      if (a.v == b.v) throw Error("Aliasing pointers");
-    }
-    static void check_full_spinor(const ColorSpinorField &a, const ColorSpinorField &b)
-    {
-      if (a.n_parity != 2 || b.n_parity != 2) throw Error("ColorSpinorFields are not full fields");
-    }
-
-    // --- Wilson (lib/dirac_wilson.cpp:21-104)
-    void DiracWilson::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
-    {
-      check_parity_spinor(in, out);
-      ApplyWilson(out, in, *gauge, 0.0, in, parity, dagger, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracWilson::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                                 double k) const
-    {
-      check_parity_spinor(in, out);
-      ApplyWilson(out, in, *gauge, k, x, parity, dagger, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracWilson::M(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      check_full_spinor(out, in);
-      if (comm && comm->partitioned()) { // halo exchange works per parity
-        auto oe = out.Even(), oo = out.Odd();
-        DiracWilson::DslashXpay(oe, in.Odd(), 0, in.Even(), -kappa);
-        DiracWilson::DslashXpay(oo, in.Even(), 1, in.Odd(), -kappa);
-      } else {
-        ApplyWilson(out, in, *gauge, -kappa, in, QUDA_INVALID_PARITY, dagger, commDim, comm, stream);
-        dslash_applications += 2;
-      }
-    }
-    void DiracWilson::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      FieldTmp tmp(in, in.n_parity);
+      Scratch tmp(stream, in, in.n_parity);
       M(tmp, in);
       Mdag(out, tmp);
     }
-    void DiracWilson::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                              QudaSolutionType st) const
-    {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION)
-        throw Error("Preconditioned solution requires a preconditioned solve_type");
-      src = b;
-      sol = x;
-    }
-    void DiracWilson::reconstruct(ColorSpinorField &, const ColorSpinorField &, QudaSolutionType) const { }
 
-    // --- WilsonPC (lib/dirac_wilson.cpp:106-163)
-    void DiracWilsonPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
+    // Full-system solve through the Schur complement: M x = b  <=>  M_pc x_e = src, x_o from x_e.
+    //   symmetric : src = A_e^-1 (b_e + k D_eo A_o^-1 b_o)       asymmetric : src = b_e + k D_eo A_o^-1 b_o
+    // The preconditioned source is built in the other-parity half of x, the solution lives in the this-parity half.
+    void Dirac::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
+                        QudaSolutionType st) const
     {
-      const double kappa2 = -kappa * kappa;
-      FieldTmp tmp(in, 1);
-      if (!symmetric) throw Error("MatPCType not valid for DiracWilsonPC");
-      Dslash(tmp, in, other_parity);
-      DslashXpay(out, tmp, this_parity, in, kappa2);
-    }
-    void DiracWilsonPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      FieldTmp tmp(in, 1);
-      M(tmp, in);
-      Mdag(out, tmp);
-    }
-    void DiracWilsonPC::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                                QudaSolutionType st) const
-    {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) {
+      const bool pc_solution = (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION);
+      if (!schur) {
+        if (pc_solution) throw Error("a preconditioned solution type needs an even-odd preconditioned operator");
         src = b;
         sol = x;
         return;
       }
-      // src = b_e + k D_eo b_o (stored in x_o), solution in x_e
-      auto xo = x.parity_view(other_parity);
-      DslashXpay(xo, b.parity_view(other_parity), this_parity, b.parity_view(this_parity), kappa);
-      src = xo;
-      sol = x.parity_view(this_parity);
-    }
-    void DiracWilsonPC::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
-    {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
-      check_full_spinor(x, b);
-      auto xo = x.parity_view(other_parity);
-      DslashXpay(xo, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
-    }
-
-    // --- Clover (lib/dirac_clover.cpp:36-100)
-    DiracClover::DiracClover(const DiracParam &p) : DiracWilson(p), clover(p.clover)
-    {
-      if (!clover) throw Error("DiracClover: clover field missing");
-    }
-    void DiracClover::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                                 double k) const
-    {
-      check_parity_spinor(in, out);
-      ApplyWilsonClover(out, in, *gauge, *clover, k, x, parity, dagger, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracClover::Clover(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
-    {
-      ApplyClover(out, in, *clover, false, parity, stream);
-    }
-    void DiracClover::M(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      check_full_spinor(out, in);
-      if (comm && comm->partitioned()) {
-        auto oe = out.Even(), oo = out.Odd();
-        DiracClover::DslashXpay(oe, in.Odd(), 0, in.Even(), -kappa);
-        DiracClover::DslashXpay(oo, in.Even(), 1, in.Odd(), -kappa);
-      } else {
-        ApplyWilsonClover(out, in, *gauge, *clover, -kappa, in, QUDA_INVALID_PARITY, dagger, commDim, comm, stream);
-        dslash_applications += 2;
-      }
-    }
-    void DiracClover::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      check_full_spinor(out, in);
-      FieldTmp tmp(in, 2);
-      M(tmp, in);
-      Mdag(out, tmp);
-    }
-
-    // --- CloverPC (lib/dirac_clover.cpp:118-258)
-    DiracCloverPC::DiracCloverPC(const DiracParam &p) : DiracClover(p)
-    {
-      if (!clover->has_inverse() && !clover->c.dynamic_inverse) throw Error("Clover inverse required for DiracCloverPC");
-    }
-    void DiracCloverPC::CloverInv(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
-    {
-      ApplyClover(out, in, *clover, true, parity, stream);
-    }
-    void DiracCloverPC::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
-    {
-      check_parity_spinor(in, out);
-      ApplyWilsonCloverPreconditioned(out, in, *gauge, *clover, 0.0, in, parity, dagger, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracCloverPC::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                                   double k) const
-    {
-      check_parity_spinor(in, out);
-      ApplyWilsonCloverPreconditioned(out, in, *gauge, *clover, k, x, parity, dagger, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracCloverPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      const double kappa2 = -kappa * kappa;
-      FieldTmp tmp(in, 1);
-      if (!symmetric) {
-        Dslash(tmp, in, other_parity);                                   // A^-1 D
-        DiracClover::DslashXpay(out, tmp, this_parity, in, kappa2);      // A x - k^2 D
-      } else if (!dagger) {
-        Dslash(tmp, in, other_parity);
-        DslashXpay(out, tmp, this_parity, in, kappa2);                   // x - k^2 A^-1 D (A^-1 D)
-      } else {
-        CloverInv(out, in, this_parity);                                 // 1 - D^+ A^-1 D^+ A^-1
-        Dslash(tmp, out, other_parity);
-        DiracWilson::DslashXpay(out, tmp, this_parity, in, kappa2);
-      }
-    }
-    void DiracCloverPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      FieldTmp tmp(in, 1);
-      M(tmp, in);
-      Mdag(out, tmp);
-    }
-    void DiracCloverPC::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                                QudaSolutionType st) const
-    {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) {
+      if (pc_solution) {
         src = b;
         sol = x;
         return;
       }
+      need_full(x, b);
       src = x.parity_view(other_parity);
       sol = x.parity_view(this_parity);
-      FieldTmp tmp(b, 1);
-      if (symmetric) { // src = A_ee^-1 (b_e + k D_eo A_oo^-1 b_o)
-        CloverInv(src, b.parity_view(other_parity), other_parity);
-        DiracWilson::DslashXpay(tmp, src, this_parity, b.parity_view(this_parity), kappa);
-        CloverInv(src, tmp, this_parity);
-      } else { // src = b_e + k D_eo A_oo^-1 b_o
-        CloverInv(tmp, b.parity_view(other_parity), other_parity);
-        DiracWilson::DslashXpay(src, tmp, this_parity, b.parity_view(this_parity), kappa);
-      }
-    }
-    void DiracCloverPC::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
-    {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
-      check_full_spinor(x, b);
-      FieldTmp tmp(b, 1);
-      // x_o = A_oo^-1 (b_o + k D_oe x_e)
-      DiracWilson::DslashXpay(tmp, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
-      auto xo = x.parity_view(other_parity);
-      CloverInv(xo, tmp, other_parity);
-    }
-
-    // --- twisted mass, singlet flavour (lib/dirac_twisted_mass.cpp:9-317)
-    DiracTwistedMass::DiracTwistedMass(const DiracParam &p) : DiracWilson(p), mu(p.mu) { }
-    void DiracTwistedMass::Twist(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      ApplyTwistGamma(out, in, kappa, mu, dagger, false, stream);
-    }
-    void DiracTwistedMass::Dslash(ColorSpinorField &, const ColorSpinorField &, int) const
-    {
-      // the reference routes this to ApplyTwistedMass with a = 0, which it does not instantiate (:47-59)
-      throw Error("DiracTwistedMass::Dslash: twisted-mass operator only defined for xpay=true");
-    }
-    void DiracTwistedMass::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                                      double k) const
-    {
-      check_parity_spinor(in, out);
-      ApplyTwistedMass(out, in, *gauge, k, 2 * mu * kappa, x, parity, dagger, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracTwistedMass::M(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      check_full_spinor(out, in);
-      // -kappa D in + (1 + i 2 mu kappa gamma5) in, one parity at a time (the halo exchange works per parity)
-      auto oe = out.Even(), oo = out.Odd();
-      DiracTwistedMass::DslashXpay(oe, in.Odd(), 0, in.Even(), -kappa);
-      DiracTwistedMass::DslashXpay(oo, in.Even(), 1, in.Odd(), -kappa);
-    }
-    void DiracTwistedMass::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      FieldTmp tmp(in, in.n_parity);
-      M(tmp, in);
-      Mdag(out, tmp);
-    }
-
-    void DiracTwistedMassPC::TwistInv(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      ApplyTwistGamma(out, in, kappa, mu, dagger, true, stream);
-    }
-    void DiracTwistedMassPC::Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const
-    {
-      check_parity_spinor(in, out);
-      const double a = -2.0 * kappa * mu; // inverse twist
-      const double b = 1.0 / (1.0 + a * a);
-      const bool asymmetric = !symmetric && dagger;
-      ApplyTwistedMassPreconditioned(out, in, *gauge, b, a, false, in, parity, dagger, asymmetric, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracTwistedMassPC::DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                                        double k) const
-    {
-      check_parity_spinor(in, out);
-      const double a = -2.0 * kappa * mu;
-      const double b = k / (1.0 + a * a);
-      const bool asymmetric = !symmetric && dagger;
-      ApplyTwistedMassPreconditioned(out, in, *gauge, b, a, true, x, parity, dagger, asymmetric, commDim, comm, stream);
-      dslash_applications++;
-    }
-    void DiracTwistedMassPC::M(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      const double kappa2 = -kappa * kappa;
-      FieldTmp tmp(in, 1);
-      Dslash(tmp, in, other_parity);
-      if (symmetric)
-        DslashXpay(out, tmp, this_parity, in, kappa2);
-      else
-        DiracTwistedMass::DslashXpay(out, tmp, this_parity, in, kappa2);
-    }
-    void DiracTwistedMassPC::MdagM(ColorSpinorField &out, const ColorSpinorField &in) const
-    {
-      FieldTmp tmp(in, 1); // extra temporary because of the symmetric dagger operator
-      M(tmp, in);
-      Mdag(out, tmp);
-    }
-    void DiracTwistedMassPC::prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                                     QudaSolutionType st) const
-    {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) {
-        src = b;
-        sol = x;
+      const auto b_this = b.parity_view(this_parity), b_other = b.parity_view(other_parity);
+      if (term == SiteTerm::Identity) {
+        hop(src, b_other, this_parity, Fuse::None, &b_this, kappa);
         return;
       }
-      src = x.parity_view(other_parity);
-      sol = x.parity_view(this_parity);
-      FieldTmp tmp(b, 1);
-      if (symmetric) { // src = A_ee^-1 (b_e + k D_eo A_oo^-1 b_o)
-        TwistInv(src, b.parity_view(other_parity));
-        DiracWilson::DslashXpay(tmp, src, this_parity, b.parity_view(this_parity), kappa);
-        TwistInv(src, tmp);
-      } else { // src = b_e + k D_eo A_oo^-1 b_o
-        TwistInv(tmp, b.parity_view(other_parity));
-        DiracWilson::DslashXpay(src, tmp, this_parity, b.parity_view(this_parity), kappa);
+      Scratch tmp(stream, b, 1);
+      if (symmetric) {
+        site(src, b_other, other_parity, true);
+        hop(tmp, src, this_parity, Fuse::None, &b_this, kappa);
+        site(src, tmp, this_parity, true);
+      } else {
+        site(tmp, b_other, other_parity, true);
+        hop(src, tmp, this_parity, Fuse::None, &b_this, kappa);
       }
     }
-    void DiracTwistedMassPC::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
+
+    // x_o = A_o^-1 (b_o + k D_oe x_e)
+    void Dirac::reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType st) const
     {
-      if (st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
-      check_full_spinor(x, b);
-      FieldTmp tmp(b, 1);
-      // x_o = A_oo^-1 (b_o + k D_oe x_e)
-      DiracWilson::DslashXpay(tmp, x.parity_view(this_parity), other_parity, b.parity_view(other_parity), kappa);
-      auto xo = x.parity_view(other_parity);
-      TwistInv(xo, tmp);
+      if (!schur || st == QUDA_MATPC_SOLUTION || st == QUDA_MATPCDAG_MATPC_SOLUTION) return;
+      need_full(x, b);
+      auto x_other = x.parity_view(other_parity);
+      const auto x_this = x.parity_view(this_parity), b_other = b.parity_view(other_parity);
+      if (term == SiteTerm::Identity) {
+        hop(x_other, x_this, other_parity, Fuse::None, &b_other, kappa);
+        return;
+      }
+      Scratch tmp(stream, b, 1);
+      hop(tmp, x_this, other_parity, Fuse::None, &b_other, kappa);
+      site(x_other, tmp, other_parity, true);
     }
 
     // ------------------------------------------------------------------ CG (normal equations) with reliable updates
+    // Same recurrences and reliable-update criterion as the reference's CG (lib/inv_cg_quda.cpp:237-420), restructured so
+    // that no iteration waits for the host: pAp, r2, alpha, beta live on the device (written by the reduction
+    // finalisers, read by the next update kernel); the host reads r2 of iteration k-1 while the GPU runs iteration k and
+    // takes its convergence / reliable-update decisions one iteration late.  A late reliable update repairs the search
+    // direction with p += r_true - r_sloppy, which restores p = r_true + beta p_old exactly.
     void invertCG(const Dirac &mat, const Dirac &matSloppy, ColorSpinorField &x, const ColorSpinorField &b, SolverParam &param)
     {
       using namespace blas;
-      CommContext *comm = mat.Comm();
+      const Exec ex = mat.exec();
+      if (matSloppy.Stream() != mat.Stream()) throw Error("precise and sloppy operators must share a stream");
       const auto t0 = std::chrono::steady_clock::now();
       const long long flops0 = blas::flops();
       const long long ds0 = mat.DslashApplications() + matSloppy.DslashApplications();
       const bool mixed = (&mat != &matSloppy);
-      const int sp = mixed ? 4 : x.precision; // sloppy precision
-      if (mixed && x.precision != 8) throw Error("mixed-precision CG expects a double-precision solution field");
+      const int sp = matSloppy.Precision();
+      if (x.precision != mat.Precision() || b.precision != mat.Precision()) throw Error("x and b must have the precise operator's precision");
+      if (sp != 8 && sp != 4) throw Error("the sloppy operator must be double or single precision");
+      if (mixed && sp > x.precision) throw Error("the sloppy operator is more precise than the precise one");
+      const bool host_ar = host_allreduce(ex);
+      int syncs = 0;
 
       auto r = ColorSpinorField::create(x.X, x.precision, x.n_parity);  // high-precision residual
       auto y = ColorSpinorField::create(x.X, x.precision, x.n_parity);  // high-precision accumulated solution
       auto tmp = ColorSpinorField::create(x.X, x.precision, x.n_parity);
-      auto rS = mixed ? ColorSpinorField::create(x.X, sp, x.n_parity) : r;
+      const bool same_prec = sp == x.precision;
+      auto rS = same_prec ? r : ColorSpinorField::create(x.X, sp, x.n_parity);
       auto xS = ColorSpinorField::create(x.X, sp, x.n_parity);
       auto p = ColorSpinorField::create(x.X, sp, x.n_parity);
       auto Ap = ColorSpinorField::create(x.X, sp, x.n_parity);
+      auto tS = same_prec ? tmp : ColorSpinorField::create(x.X, sp, x.n_parity); // sloppy-precision staging
 
-      const double b2 = norm2(b, comm);
+      const double b2 = norm2(b, ex);
+      syncs++;
       if (b2 == 0.0) {
-        zero(x);
+        zero(x, ex);
         param.iter = 0;
         param.true_res = 0.0;
         return;
       }
       // r = b - A x
       mat.MdagM(tmp, x);
-      copy(r, b);
-      axpy(-1.0, tmp, r);
-      double r2 = norm2(r, comm);
-      copy(y, x);
-      if (mixed) copy(rS, r);
-      zero(xS);
-      copy(p, rS);
+      copy(r, b, ex);
+      double r2 = axpyNorm(-1.0, tmp, r, ex);
+      syncs++;
+      copy(y, x, ex);
+      if (!same_prec) copy(rS, r, ex);
+      zero(xS, ex);
+      copy(p, rS, ex);
+      set_scalar(ex, S_R2, r2);
       const double stop = param.tol * param.tol * b2;
       double rNorm = std::sqrt(r2), r0Norm = rNorm, maxrx = rNorm, maxrr = rNorm;
       int k = 0;
       param.reliable_updates = 0;
       const bool verbose = getenv("B200_CG_VERBOSE") != nullptr;
       if (verbose) fprintf(stderr, "[cg] b2=%g r2=%g stop=%g mixed=%d\n", b2, r2, stop, (int)mixed);
-      while (r2 > stop && k < param.maxiter) {
-        matSloppy.MdagM(Ap, p);
-        const double pAp = reDotProduct(p, Ap, comm);
-        const double alpha = r2 / pAp;
-        const double r2_old = r2;
-        r2 = axpyNorm(-alpha, Ap, rS, comm);
-        rNorm = std::sqrt(r2);
+
+      // fold the sloppy solution into y, recompute the true residual in high precision, repair the recursion
+      auto reliable_update = [&]() {
+        copy(tmp, xS, ex);
+        axpy(1.0, tmp, y, ex);
+        zero(xS, ex);
+        mat.MdagM(tmp, y);
+        copy(r, b, ex);
+        const double r2_true = axpyNorm(-1.0, tmp, r, ex);
+        syncs++;
+        copy(tS, r, ex);             // the true residual in the sloppy precision
+        cg_replace_r(p, rS, tS, ex); // p += r_true - rS ; rS = r_true
+        set_scalar(ex, S_R2, r2_true);
+        param.reliable_updates++;
+        return r2_true;
+      };
+      // convergence / reliable-update decision on a residual norm; returns true if the recursion was restarted
+      bool done = false;
+      auto decide = [&](double r2_seen) {
+        rNorm = std::sqrt(r2_seen);
         if (rNorm > maxrx) maxrx = rNorm;
         if (rNorm > maxrr) maxrr = rNorm;
-        const bool update = mixed && ((rNorm < param.delta * maxrx && r0Norm <= maxrx) || (rNorm < param.delta * r0Norm && r0Norm <= maxrr) || r2 <= stop);
-        if (!update) {
-          const double beta = r2 / r2_old;
-          axpyZpbx(alpha, p, xS, rS, beta); // xS += alpha p ; p = rS + beta p
-        } else {
-          axpy(alpha, p, xS);
-          // reliable update: fold the sloppy solution into y, recompute the true residual in high precision
-          copy(tmp, xS);
-          axpy(1.0, tmp, y);
-          mat.MdagM(tmp, y);
-          copy(r, b);
-          r2 = axpyNorm(-1.0, tmp, r, comm);
-          copy(rS, r);
-          zero(xS);
-          // keep the search direction conjugate as far as precision allows: p = r + beta p
-          const double beta = r2 / r2_old;
-          xpay(rS, beta, p);
+        const bool converged = r2_seen <= stop;
+        const bool update = !same_prec
+          && ((rNorm < param.delta * maxrx && r0Norm <= maxrx) || (rNorm < param.delta * r0Norm && r0Norm <= maxrr) || converged);
+        if (verbose && (k < 10 || k % 20 == 0 || update)) fprintf(stderr, "[cg] k=%d r2=%g update=%d\n", k, r2_seen, (int)update);
+        if (update) {
+          r2 = reliable_update();
           rNorm = std::sqrt(r2);
           maxrr = maxrx = r0Norm = rNorm;
-          param.reliable_updates++;
+          if (r2 <= stop) done = true;
+          return true;
         }
+        if (converged) done = true;
+        return false;
+      };
+
+      Pending prev {};
+      bool have_prev = false;
+      double scratch[S_COUNT];
+      while (!done && k < param.maxiter) {
+        matSloppy.MdagM(Ap, p);
+        Pending pd = cg_dot(p, Ap, ex);
+        if (host_ar) { // no NVLink mailboxes: every global sum goes through the host callback (two syncs per iteration)
+          const double pAp = await(ex, pd, true, scratch)[S_RAW0];
+          syncs++;
+          set_scalar(ex, S_PAP, pAp);
+          set_scalar(ex, S_ALPHA, r2 / pAp);
+        }
+        Pending pr = cg_update_r(rS, Ap, ex);
+        if (host_ar) {
+          const double r2_new = await(ex, pr, true, scratch)[S_RAW0];
+          syncs++;
+          set_scalar(ex, S_R2_OLD, r2);
+          set_scalar(ex, S_R2, r2_new);
+          set_scalar(ex, S_BETA, r2_new / r2);
+          r2 = r2_new;
+        }
+        cg_update_xp(xS, p, rS, ex);
         k++;
-        if (verbose && (k < 10 || k % 20 == 0 || update))
-          fprintf(stderr, "[cg] k=%d r2=%g pAp=%g alpha=%g update=%d\n", k, r2, pAp, alpha, (int)update);
+        if (host_ar) {
+          decide(r2);
+          continue;
+        }
+        // the host follows one iteration behind: while the GPU runs iteration k it looks at the residual of k - 1
+        bool restarted = false;
+        if (have_prev) {
+          r2 = await(ex, prev, false, scratch)[S_R2];
+          syncs++;
+          restarted = decide(r2);
+        }
+        if (restarted) {
+          have_prev = false; // the pending residual belongs to the recursion before the restart
+        } else {
+          prev = pr;
+          have_prev = true;
+        }
       }
       // x = y + xS
-      copy(tmp, xS);
-      axpy(1.0, tmp, y);
-      copy(x, y);
+      if (same_prec) {
+        axpy(1.0, xS, y, ex);
+      } else {
+        copy(tmp, xS, ex);
+        axpy(1.0, tmp, y, ex);
+      }
+      copy(x, y, ex);
       // true residual
       mat.MdagM(tmp, x);
-      copy(r, b);
-      const double tr2 = axpyNorm(-1.0, tmp, r, comm);
-      cuda_ok(cudaDeviceSynchronize(), "sync");
+      copy(r, b, ex);
+      const double tr2 = axpyNorm(-1.0, tmp, r, ex);
+      syncs++;
+      cuda_ok(cudaStreamSynchronize(cs(ex.stream)), "sync");
+      if (halo_timed_out(ex.comm, ex.stream)) throw Error("a halo wait timed out during the solve: the result is not valid");
       param.iter = k;
       param.true_res = std::sqrt(tr2 / b2);
+      param.host_syncs = syncs;
       param.secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       const long long nds = mat.DslashApplications() + matSloppy.DslashApplications() - ds0;
       const double fl = (double)(blas::flops() - flops0) + (double)nds * 1320.0 * x.VolumeCB();

@@ -1,12 +1,16 @@
-// Host-side C++ mirror of the reference's operator layer for the Wilson / Wilson-clover family:
-//   ApplyWilson / ApplyWilsonClover / ApplyWilsonCloverPreconditioned / ApplyClover   (include/dslash_quda.h:83-811)
-//   DiracWilson, DiracWilsonPC, DiracClover, DiracCloverPC                          (include/dirac_quda.h, lib/dirac_wilson.cpp,
-//                                                                                    lib/dirac_clover.cpp)
-//   blas:: axpy/xpay/.../norm2/cDotProduct and CG with reliable updates             (lib/blas_quda.cu, lib/reduce_quda.cu,
-//                                                                                    lib/inv_cg_quda.cpp)
-// Same names, argument meaning and error behaviour (errors throw b200::host::Error, the analogue of errorQuda);
-// everything bottoms out in the C ABI of include/b200_dslash.h.  Fields are non-owning views unless created with
-// ColorSpinorField::create (device memory from cudaMalloc).
+// Host-side C++ layer above the C ABI for the Wilson / Wilson-clover / twisted-mass family: what a QUDA caller reaches
+// through Dirac::M / MdagM / prepare / reconstruct and invertQuda's CG.
+//   reference surface   include/dslash_quda.h:83-811 (Apply*), include/dirac_quda.h (Dirac* classes),
+//                       lib/blas_quda.cu + lib/reduce_quda.cu (blas), lib/inv_cg_quda.cpp:63-420 (CG, reliable updates)
+// Design (not a mirror of the reference's class tree):
+//   * ONE operator class.  An even-odd operator is described by its site term A (identity, clover, twist) and whether it
+//     is the full matrix or the Schur complement; M / Mdag / prepare / reconstruct are short sequences of two
+//     primitives -- `hop` (a Dslash launch with the site term fused into its epilogue) and `site` (A or A^-1 alone).
+//   * Everything runs on the operator's stream: Dslash, blas, reductions, the NVLink all-reduce.  Reductions are
+//     two-stage and summed in a fixed order (bit-reproducible); their results stay on the device -- the CG scalars
+//     (alpha, beta) are computed there and consumed by the next kernel, the host only follows one iteration behind to
+//     decide convergence / reliable updates, so no iteration waits for a host round trip.
+// Errors throw b200::host::Error (the analogue of errorQuda); everything bottoms out in include/b200_dslash.h.
 #pragma once
 
 #include <array>
@@ -47,15 +51,20 @@ namespace b200
       void *recv_flag[2][4][2] = {};
       int *block_counter = nullptr;
       int *timeout_flag = nullptr;
-      unsigned seq = 0;
+      unsigned *seq_shared = nullptr; // the ONE exchange counter all operators on this exchange advance (b200_comm::seq)
+      unsigned seq_local = 0;         // used when seq_shared is null
       void *pack_stream = nullptr; // cudaStream_t for the pack kernels (nullptr: same stream as the Dslash)
       void (*allreduce_sum)(double *data, int n, void *user) = nullptr; // nullptr: single rank
       void *user = nullptr;
       // NVLink mailbox all-reduce (b200_comm::reduce_peer); n_ranks == 0: use the callback
       int rank = 0, n_ranks = 0;
       void *reduce_peer[B200_MAX_RANKS] = {};
-      unsigned reduce_seq = 0;
+      unsigned *reduce_seq_shared = nullptr;
+      unsigned reduce_seq_local = 0;
       bool partitioned() const { return comm_dim[0] || comm_dim[1] || comm_dim[2] || comm_dim[3]; }
+      unsigned &seq() { return seq_shared ? *seq_shared : seq_local; }
+      unsigned &reduce_seq() { return reduce_seq_shared ? *reduce_seq_shared : reduce_seq_local; }
+      bool mailboxes() const { return n_ranks >= 2 && reduce_peer[0] != nullptr; }
     };
 
     class ColorSpinorField
@@ -93,7 +102,8 @@ namespace b200
       bool has_inverse() const { return cinv.clover != nullptr; }
     };
 
-    // ---- the drop-in entry points (reference: include/dslash_quda.h)
+    // ---- the drop-in entry points (reference: include/dslash_quda.h); on a partitioned lattice they own the halo
+    // exchange exactly as the reference's do (pack + remote write on the side stream, interior, boundary)
     void ApplyWilson(ColorSpinorField &out, const ColorSpinorField &in, const GaugeField &U, double a,
                      const ColorSpinorField &x, int parity, bool dagger, const int *comm_override, CommContext *comm,
                      void *stream = nullptr);
@@ -115,21 +125,26 @@ namespace b200
     void ApplyTwistGamma(ColorSpinorField &out, const ColorSpinorField &in, double kappa, double mu, bool dagger, bool inverse,
                          void *stream = nullptr);
 
-    // ---- blas on native-order fields of equal precision (fp64 / fp32); reductions accumulate in double
+    // where blas kernels and reductions run: the operator's stream and (for global sums) its halo context
+    struct Exec {
+      void *stream = nullptr;
+      CommContext *comm = nullptr;
+    };
+
+    // ---- blas on native-order fields (fp64 / fp32); reductions accumulate in double, in a fixed order
     namespace blas
     {
-      void copy(ColorSpinorField &dst, const ColorSpinorField &src); // precision conversion allowed (8 <-> 4)
-      void zero(ColorSpinorField &x);
-      void ax(double a, ColorSpinorField &x);
-      void axpy(double a, const ColorSpinorField &x, ColorSpinorField &y);            // y += a x
-      void xpay(const ColorSpinorField &x, double a, ColorSpinorField &y);            // y = x + a y
-      void axpby(double a, const ColorSpinorField &x, double b, ColorSpinorField &y); // y = a x + b y
-      double norm2(const ColorSpinorField &x, CommContext *comm);
-      double reDotProduct(const ColorSpinorField &x, const ColorSpinorField &y, CommContext *comm);
-      double axpyNorm(double a, const ColorSpinorField &x, ColorSpinorField &y, CommContext *comm); // y += a x ; |y|^2
-      double xmyNorm(const ColorSpinorField &x, ColorSpinorField &y, CommContext *comm);            // y = x - y ; |y|^2
-      // p = r + beta p ; x += alpha p_old fused as in the reference's axpyZpbx (lib/inv_cg_quda.cpp:389)
-      void axpyZpbx(double a, ColorSpinorField &p, ColorSpinorField &x, const ColorSpinorField &r, double b);
+      void copy(ColorSpinorField &dst, const ColorSpinorField &src, const Exec &ex); // precision conversion allowed (8 <-> 4)
+      void zero(ColorSpinorField &x, const Exec &ex);
+      void ax(double a, ColorSpinorField &x, const Exec &ex);
+      void axpy(double a, const ColorSpinorField &x, ColorSpinorField &y, const Exec &ex);            // y += a x
+      void xpay(const ColorSpinorField &x, double a, ColorSpinorField &y, const Exec &ex);            // y = x + a y
+      void axpby(double a, const ColorSpinorField &x, double b, ColorSpinorField &y, const Exec &ex); // y = a x + b y
+      // the reductions below synchronise the stream (they return the global sum to the host)
+      double norm2(const ColorSpinorField &x, const Exec &ex);
+      double reDotProduct(const ColorSpinorField &x, const ColorSpinorField &y, const Exec &ex);
+      double axpyNorm(double a, const ColorSpinorField &x, ColorSpinorField &y, const Exec &ex); // y += a x ; |y|^2
+      double xmyNorm(const ColorSpinorField &x, ColorSpinorField &y, const Exec &ex);            // y = x - y ; |y|^2
       long long flops();
     } // namespace blas
 
@@ -145,131 +160,56 @@ namespace b200
       void *stream = nullptr;
     };
 
+    // site term of the even-odd operator  M = [[A_e, -kappa D_eo], [-kappa D_oe, A_o]]
+    enum class SiteTerm { Identity, Clover, Twist };
+
     class Dirac
     {
-    protected:
       const GaugeField *gauge;
-      double kappa;
+      const CloverField *clover;
+      double kappa, mu;
       QudaMatPCType matpcType;
       mutable bool dagger;
       int commDim[4];
       CommContext *comm;
       void *stream;
-      bool symmetric;
+      SiteTerm term;
+      bool schur;           // operator acts on one parity (Schur complement of the even-odd decomposition)
+      bool symmetric;       // Schur form 1 - k^2 A^-1 D A^-1 D (else A - k^2 D A^-1 D)
       int this_parity, other_parity;
       mutable long long dslash_applications = 0;
 
+      // primitives
+      enum class Fuse { None, A, AinvPost }; // what the Dslash epilogue applies: nothing / A on x / A^-1 on D in
+      void hop(ColorSpinorField &out, const ColorSpinorField &in, int parity, Fuse f, const ColorSpinorField *x, double k) const;
+      void site(ColorSpinorField &out, const ColorSpinorField &in, int parity, bool inverse) const;
+
     public:
-      explicit Dirac(const DiracParam &p);
-      virtual ~Dirac() = default;
-      virtual void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const = 0;
-      virtual void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                              double k) const = 0;
-      virtual void M(ColorSpinorField &out, const ColorSpinorField &in) const = 0;
-      virtual void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const = 0;
-      virtual void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                           QudaSolutionType) const = 0;
-      virtual void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const = 0;
-      virtual bool pc() const { return false; }
+      Dirac(SiteTerm term, bool schur, const DiracParam &p);
+      // "wilson", "wilsonpc", "clover", "cloverpc", "twistedmass", "twistedmasspc"
+      static Dirac *create(const std::string &type, const DiracParam &p);
+
+      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const;
+      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x, double k) const;
+      void M(ColorSpinorField &out, const ColorSpinorField &in) const;
       void Mdag(ColorSpinorField &out, const ColorSpinorField &in) const;
+      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const;
+      void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const;
+      void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const;
+
+      bool pc() const { return schur; }
+      bool is_twisted() const { return term == SiteTerm::Twist; }
+      void setMu(double m) { mu = m; }
       void setCommDim(const int *c) { for (int d = 0; d < 4; d++) commDim[d] = c[d]; }
       void flipDagger() const { dagger = !dagger; }
       long long DslashApplications() const { return dslash_applications; }
       CommContext *Comm() const { return comm; }
-      // "wilson", "wilsonpc", "clover", "cloverpc", "twistedmass", "twistedmasspc"
-      static Dirac *create(const std::string &type, const DiracParam &p);
+      void *Stream() const { return stream; }
+      int Precision() const { return gauge->precision; }
+      Exec exec() const { return Exec {stream, comm}; }
     };
 
-    class DiracWilson : public Dirac
-    {
-    public:
-      using Dirac::Dirac;
-      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override;
-      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                      double k) const override;
-      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                   QudaSolutionType) const override;
-      void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const override;
-    };
-
-    class DiracWilsonPC : public DiracWilson
-    {
-    public:
-      using DiracWilson::DiracWilson;
-      bool pc() const override { return true; }
-      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                   QudaSolutionType) const override;
-      void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const override;
-    };
-
-    class DiracClover : public DiracWilson
-    {
-    protected:
-      const CloverField *clover;
-
-    public:
-      explicit DiracClover(const DiracParam &p);
-      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                      double k) const override; // A x + k D in
-      void Clover(ColorSpinorField &out, const ColorSpinorField &in, int parity) const;
-      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
-    };
-
-    class DiracCloverPC : public DiracClover
-    {
-    public:
-      explicit DiracCloverPC(const DiracParam &p);
-      bool pc() const override { return true; }
-      void CloverInv(ColorSpinorField &out, const ColorSpinorField &in, int parity) const;
-      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override; // A^-1 D
-      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                      double k) const override; // x + k A^-1 D in
-      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                   QudaSolutionType) const override;
-      void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const override;
-    };
-
-    // ---- degenerate (singlet) twisted mass, lib/dirac_twisted_mass.cpp
-    class DiracTwistedMass : public DiracWilson
-    {
-    protected:
-      double mu;
-
-    public:
-      explicit DiracTwistedMass(const DiracParam &p);
-      void setMu(double m) { mu = m; }
-      void Twist(ColorSpinorField &out, const ColorSpinorField &in) const; // (1 + i 2 kappa mu gamma5) in
-      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override;
-      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                      double k) const override; // k D in + (1 + i 2 mu kappa gamma5) x
-      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
-    };
-
-    class DiracTwistedMassPC : public DiracTwistedMass
-    {
-    public:
-      using DiracTwistedMass::DiracTwistedMass;
-      bool pc() const override { return true; }
-      void TwistInv(ColorSpinorField &out, const ColorSpinorField &in) const;
-      void Dslash(ColorSpinorField &out, const ColorSpinorField &in, int parity) const override; // A^-1 D / D^dag A^-dag
-      void DslashXpay(ColorSpinorField &out, const ColorSpinorField &in, int parity, const ColorSpinorField &x,
-                      double k) const override;
-      void M(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void MdagM(ColorSpinorField &out, const ColorSpinorField &in) const override;
-      void prepare(ColorSpinorField &sol, ColorSpinorField &src, ColorSpinorField &x, const ColorSpinorField &b,
-                   QudaSolutionType) const override;
-      void reconstruct(ColorSpinorField &x, const ColorSpinorField &b, QudaSolutionType) const override;
-    };
-
-    // ---- CG on MdagM with optional mixed precision + reliable updates (lib/inv_cg_quda.cpp:63-420 restated)
+    // ---- CG on MdagM with optional mixed precision + reliable updates (behaviour of lib/inv_cg_quda.cpp:63-420)
     struct SolverParam {
       double tol = 1e-10;
       int maxiter = 10000;
@@ -280,10 +220,14 @@ namespace b200
       double secs = 0.0;
       double gflops = 0.0;
       int reliable_updates = 0;
+      int host_syncs = 0; // stream synchronisations the solve needed (diagnostic: ~1 per iteration, off the critical path)
     };
 
     // Solve MdagM x = b.  `mat` is the high-precision operator, `matSloppy` the low-precision one (may be the same object).
     void invertCG(const Dirac &mat, const Dirac &matSloppy, ColorSpinorField &x, const ColorSpinorField &b, SolverParam &param);
+
+    // true if a halo wait gave up since the last call (clears the flag); the C entry points turn it into an error
+    bool halo_timed_out(CommContext *comm, void *stream);
 
   } // namespace host
 } // namespace b200

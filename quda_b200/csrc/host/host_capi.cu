@@ -23,10 +23,14 @@ struct b200_dirac_s {
   std::unique_ptr<Dirac> op;
 };
 
+// Mirror the caller's b200_comm into the operator's CommContext.  The exchange / reduction sequence numbers are NOT
+// copied: every operator created on one b200_comm advances the caller's counters through these pointers, so a precise
+// and a sloppy operator sharing an exchange (or Python code using the same HaloExchange) can never reuse a sequence
+// number or disagree on the buffer parity.
 static void pull_comm(b200_dirac_s *h)
 {
   if (!h->has_comm) return;
-  const b200_comm *c = h->user_comm;
+  b200_comm *c = h->user_comm;
   CommContext &k = h->comm;
   memcpy(k.comm_dim, c->comm_dim, sizeof(k.comm_dim));
   memcpy(k.send_dst, c->send_dst, sizeof(k.send_dst));
@@ -35,22 +39,16 @@ static void pull_comm(b200_dirac_s *h)
   memcpy(k.recv_flag, c->recv_flag, sizeof(k.recv_flag));
   k.block_counter = c->block_counter;
   k.timeout_flag = c->timeout_flag;
-  k.seq = c->seq;
+  k.seq_shared = &c->seq;
   k.pack_stream = c->pack_stream;
   k.allreduce_sum = c->allreduce_sum;
   k.user = c->user;
   k.rank = c->rank;
   k.n_ranks = c->n_ranks;
   memcpy(k.reduce_peer, c->reduce_peer, sizeof(k.reduce_peer));
-  k.reduce_seq = c->reduce_seq;
+  k.reduce_seq_shared = &c->reduce_seq;
 }
-static void push_comm(b200_dirac_s *h)
-{
-  if (h->has_comm) {
-    h->user_comm->seq = h->comm.seq;
-    h->user_comm->reduce_seq = h->comm.reduce_seq;
-  }
-}
+static void push_comm(b200_dirac_s *) { }
 
 template <typename F> static int guarded(F &&f)
 {
@@ -111,9 +109,8 @@ int b200_dirac_set_twist(b200_dirac *op, double mu)
 {
   return guarded([&] {
     if (!op) throw Error("b200_dirac_set_twist: null operator");
-    auto *tm = dynamic_cast<DiracTwistedMass *>(op->op.get());
-    if (!tm) throw Error("b200_dirac_set_twist: not a twisted-mass operator");
-    tm->setMu(mu);
+    if (!op->op->is_twisted()) throw Error("b200_dirac_set_twist: not a twisted-mass operator");
+    op->op->setMu(mu);
   });
 }
 
@@ -150,6 +147,19 @@ int b200_dirac_apply(b200_dirac *h, int what, const b200_spinor *out, const b200
     }
     if (dagger) h->op->flipDagger();
     push_comm(h);
+  });
+}
+
+/* 0 if no halo wait has given up since the last check on this exchange; B200_ERR_CUDA (and the flag is cleared) otherwise.
+ * Synchronises `stream`.  b200_invert_cg checks by itself; callers of b200_dirac_apply / b200_dslash_apply on partitioned
+ * lattices call this at their own synchronisation points. */
+int b200_comm_check(b200_comm *c, void *stream)
+{
+  return guarded([&] {
+    if (!c) throw Error("b200_comm_check: null exchange");
+    CommContext k;
+    k.timeout_flag = c->timeout_flag;
+    if (halo_timed_out(&k, stream)) throw Error("a halo wait timed out (a neighbour's faces never arrived): results since the last check are not valid");
   });
 }
 
@@ -200,6 +210,7 @@ int b200_invert_cg(b200_dirac *precise, b200_dirac *sloppy, const b200_spinor *x
     param->true_res = sp.true_res;
     param->secs = sp.secs;
     param->gflops = sp.gflops;
+    param->host_syncs = sp.host_syncs;
     push_comm(precise);
     if (sloppy != precise) push_comm(sloppy);
   });

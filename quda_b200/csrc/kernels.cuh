@@ -118,7 +118,8 @@ namespace b200
   }
 
   // Block until every partitioned face has arrived (flag >= seq, wrap-safe).  One thread polls, the CTA follows.
-  // Gives up after ~2 s of SM clock so that a lost peer can never hang the GPU; the host sees timeout_flag.
+  // Gives up after ~10 s of SM clock so that a lost peer can never hang the GPU; the host layer checks (and clears)
+  // timeout_flag at its synchronisation points and turns it into an error (b200_comm_check, b200_invert_cg).
   template <class Arg> __device__ __forceinline__ void wait_for_halo(const Arg &arg)
   {
     if (threadIdx.x == 0) {
@@ -130,7 +131,7 @@ namespace b200
           const unsigned *f = arg.wait_flag[d][dir];
           if (!f) continue;
           while ((int)(ld_acquire_sys(f) - arg.seq) < 0) {
-            if (clock64() - t0 > 4000000000LL) {
+            if (clock64() - t0 > 20000000000LL) {
               if (arg.timeout_flag) *arg.timeout_flag = 1;
               break;
             }
@@ -174,7 +175,7 @@ namespace b200
     const int x_cb = blockIdx.x * blockDim.x + threadIdx.x;
     if (x_cb >= volume_cb) return;
     typename P::real v[24];
-    in.template load<Cache::STREAM>(v, x_cb);
+    in.template load<Cache::COHERENT>(v, x_cb); // `out` may be `in` (in-place apply): not the .nc path
     clover_apply_site<P, inverse>(v, A, x_cb, parity);
     out.save(v, x_cb);
   }
@@ -187,7 +188,7 @@ namespace b200
     const int x_cb = blockIdx.x * blockDim.x + threadIdx.x;
     if (x_cb >= volume_cb) return;
     typename P::real v[24];
-    in.template load<Cache::STREAM>(v, x_cb);
+    in.template load<Cache::COHERENT>(v, x_cb); // `out` may be `in`
     twist_apply(v, a, b);
     out.save(v, x_cb);
   }

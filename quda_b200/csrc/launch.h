@@ -22,7 +22,11 @@ namespace b200
     int asymmetric; // twisted-mass preconditioned: asymmetric variant
     int march_t; // > 0: every CTA walks `march_t` consecutive time slices with its (x,y,z) tile (L1 reuse of the slices)
     int tma;     // 1: unpartitioned single-source requests go to the TMA-staged marching kernel when it serves the shape
-    int tma_ty, tma_tz, tma_grid, tma_link_slots; // tuning overrides of that kernel (0: built-in choice)
+    int tma_ty, tma_tz, tma_grid; // tuning overrides of that kernel (0: built-in choice)
+    int tma_link_slots;           // 0: links through shared memory, as many stages as fit; >= 2: that many; -1: register stream
+    int tma_center_slots, tma_halo_slots; // cap the spinor rings (0: as deep as shared memory allows)
+    int tma_l2_prefetch;          // shared-memory link stages: L2 prefetch look-ahead in items (0: built-in; < 0: off)
+    int tma_prefetch;             // register-stream links: prefetch distance in direction pairs (2, 3 or 4; 0: built-in)
     double a;
     b200_spinor out, in, x;
     b200_gauge U;
@@ -337,7 +341,7 @@ namespace b200
     }
     rq.march_t = 0;
     rq.tma = 0;
-    rq.tma_ty = rq.tma_tz = rq.tma_grid = rq.tma_link_slots = 0;
+    rq.tma_ty = rq.tma_tz = rq.tma_grid = rq.tma_link_slots = rq.tma_center_slots = rq.tma_halo_slots = rq.tma_prefetch = rq.tma_l2_prefetch = 0;
     rq.out = a->out;
     rq.in = a->in;
     rq.x = a->x;

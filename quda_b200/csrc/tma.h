@@ -4,14 +4,21 @@
 // cp.async.bulk.tensor) live in tma_kernel.cuh.
 //
 // What it replaces: the reference's interior kernel gathers the 8 neighbour spinors straight from global memory and
-// leaves their reuse to L1/L2 (/root/reference/include/kernels/dslash_wilson.cuh:84-161); on B200 that makes the
-// SM <- L2 fill path, not HBM, the limiter for fp32 recon-12.  Here a persistent CTA owns an
-// (all x) x TY x TZ tile of one parity and marches through t:
+// leaves their reuse to L1/L2 (/root/reference/include/kernels/dslash_wilson.cuh:84-161); on B200 that pulls 404 MB
+// through the L2 -> SM crossbar for 302 MB of compulsory traffic (fp32 recon-12).  Here a persistent
+// CTA owns an (all x) x TY x TZ tile of one parity and marches through t:
 //   * the input-spinor slice t+1 (tile rows only) and the y/z halo rows of slice t arrive in shared memory by TMA box
-//     loads, one slice ahead of their use; slices t-1, t, t+1 stay resident, so every input site crosses the
+//     loads, several slices ahead of their use; slices t-1, t, t+1 stay resident, so every input site crosses the
 //     L2 -> SM path (1 + halo) times instead of ~4 times;
-//   * the 8 links of a site arrive the same way, one direction pair (forward + backward link of dimension d) per
-//     pipeline stage, so no thread ever waits on a global load: all stencil operands are LDS;
+//   * the 8 links of a site are a pure stream (each is read exactly once).  Two ways of feeding them, selected by
+//     TmaPlan::n_link_slots:
+//       >0 (default) TMA stages: one direction pair (forward + backward link of dimension d) per stage through a ring in
+//          shared memory.  Shared memory only holds ~2 stages in flight (48 KB), less than bandwidth x DRAM latency, so
+//          the producer first pulls the link boxes into L2 two items ahead (cp.async.bulk.prefetch.tensor) and the
+//          staged loads only have to cover the L2 -> SM latency;
+//       0  register stream: a thread re-issues the loads of a direction pair for a later step into the registers the
+//          pair just consumed.  Measured slower on B200 (profiles/r02_tma_regstream_*): under the 168-register cap of a
+//          9-warp CTA ptxas sinks the prefetch loads back down to their first use;
 //   * a producer warp issues the box loads, the consumer warps wait on mbarriers -- no __syncthreads in the loop.
 // Work is the linearised (tile, t) sequence cut into gridDim.x equal ranges (148 SMs do not divide 2^k tiles).
 #pragma once
@@ -21,8 +28,8 @@
 namespace b200
 {
 
-  constexpr int kTmaCenterSlots = 4; // slices t-1, t, t+1 live + one in flight
-  constexpr int kTmaHaloSlots = 2;   // halo rows of slice t live + one in flight
+  constexpr int kTmaMaxCenterSlots = 8; // slices t-1, t, t+1 live + look-ahead
+  constexpr int kTmaMaxHaloSlots = 4;   // halo rows of slice t live + look-ahead
   constexpr int kTmaMaxLinkSlots = 4;
   constexpr int kTmaSmemBudget = 227 * 1024;
   constexpr int kTmaMaxConsumers = 256;
@@ -48,7 +55,7 @@ namespace b200
     unsigned long long dim[5];    // elements (u32) / planes / sites
     unsigned long long stride[5]; // bytes; stride[0] = 4
     unsigned box[5];
-    int valid;                    // 0: shape has a zero extent (TY == 1 or TZ == 1), never issued
+    int valid;                    // 0: shape has a zero extent (TY == 1 or TZ == 1) or is not used in this mode
   };
 
   struct TmaPlan {
@@ -63,7 +70,8 @@ namespace b200
     int srow, grow;   // bytes of one (y,z) row record: SP * svec * Xh, GP * gvec * Xh
     int NC, NH;       // tile rows, halo rows
     int center_bytes, halo_bytes, link_bytes; // per slot (128-byte aligned)
-    int n_link_slots;
+    int n_center_slots, n_halo_slots, n_link_slots; // n_link_slots == 0: links are a register stream
+    int l2_prefetch_items; // shared-memory link stages: items of look-ahead of the L2 prefetch of the link boxes (0: off)
     int off_center, off_halo, off_link, off_bar, smem_bytes;
   };
 
@@ -71,17 +79,39 @@ namespace b200
 
   // mbarrier slots inside the barrier block (8 bytes each)
   B2_HD int tma_bar_full_c(int s) { return s; }
-  B2_HD int tma_bar_empty_c(int s) { return kTmaCenterSlots + s; }
-  B2_HD int tma_bar_full_h(int s) { return 2 * kTmaCenterSlots + s; }
-  B2_HD int tma_bar_empty_h(int s) { return 2 * kTmaCenterSlots + kTmaHaloSlots + s; }
-  B2_HD int tma_bar_full_l(int s) { return 2 * kTmaCenterSlots + 2 * kTmaHaloSlots + s; }
-  B2_HD int tma_bar_empty_l(int s) { return 2 * kTmaCenterSlots + 2 * kTmaHaloSlots + kTmaMaxLinkSlots + s; }
-  constexpr int kTmaBarriers = 2 * kTmaCenterSlots + 2 * kTmaHaloSlots + 2 * kTmaMaxLinkSlots;
+  B2_HD int tma_bar_empty_c(int s) { return kTmaMaxCenterSlots + s; }
+  B2_HD int tma_bar_full_h(int s) { return 2 * kTmaMaxCenterSlots + s; }
+  B2_HD int tma_bar_empty_h(int s) { return 2 * kTmaMaxCenterSlots + kTmaMaxHaloSlots + s; }
+  B2_HD int tma_bar_full_l(int s) { return 2 * kTmaMaxCenterSlots + 2 * kTmaMaxHaloSlots + s; }
+  B2_HD int tma_bar_empty_l(int s) { return 2 * kTmaMaxCenterSlots + 2 * kTmaMaxHaloSlots + kTmaMaxLinkSlots + s; }
+  constexpr int kTmaBarriers = 2 * kTmaMaxCenterSlots + 2 * kTmaMaxHaloSlots + 2 * kTmaMaxLinkSlots;
+
+  // position in a ring of R slots: slot index + parity of the current pass over the ring (the mbarrier phase parity)
+  struct TmaPos {
+    int slot;
+    unsigned phase;
+  };
+  B2_HD TmaPos tma_pos_next(TmaPos p, int R)
+  {
+    if (++p.slot == R) {
+      p.slot = 0;
+      p.phase ^= 1u;
+    }
+    return p;
+  }
+
+  // tuning knobs of the plan (0 = built-in choice)
+  struct TmaKnobs {
+    int ty, tz;          // tile
+    int link_slots;      // 0: shared-memory stages, as many as fit (default); >= 2: that many stages; -1: register stream
+    int center_slots, halo_slots; // register-stream mode: cap the spinor rings
+    int l2_prefetch;     // shared-memory link stages: L2 prefetch look-ahead in items (<= 0: off, the default)
+  };
 
   // Build the plan for a lattice / precision / reconstruct.  Returns false if this shape is not served by the TMA
   // kernel (the caller falls back to the gather kernel): x rows must fit one box, the tile must divide the lattice and
-  // spinor slices + >= 2 link stages must fit in shared memory.
-  template <class P, int recon> B2_HD bool tma_make_plan(TmaPlan &p, const Geom &g, int n_parity, int parity, int want_ty, int want_tz)
+  // the spinor slices (+ >= 2 link stages in the shared-memory link mode) must fit in shared memory.
+  template <class P, int recon> B2_HD bool tma_make_plan(TmaPlan &p, const Geom &g, int n_parity, int parity, const TmaKnobs &k)
   {
     using GV = GaugeView<P, recon>;
     p.Xh = g.Xh0;
@@ -101,9 +131,9 @@ namespace b200
     // tile: powers of two dividing Y and Z, grown alternately (y first) up to the consumer budget
     const int budget = sizeof(typename P::real) == 8 ? 128 : kTmaMaxConsumers;
     int ty = 1, tz = 1;
-    if (want_ty > 0 && want_tz > 0) {
-      ty = want_ty;
-      tz = want_tz;
+    if (k.ty > 0 && k.tz > 0) {
+      ty = k.ty;
+      tz = k.tz;
       if (p.Y % ty || p.Z % tz) return false;
     } else {
       for (;;) {
@@ -137,17 +167,39 @@ namespace b200
       if (bwd < tma_align128(p.NC * p.grow)) bwd = tma_align128(p.NC * p.grow);
       p.link_bytes = tma_align128(p.NC * p.grow) + bwd;
     }
-    const int fixed_bytes = kTmaCenterSlots * p.center_bytes + kTmaHaloSlots * p.halo_bytes + 1024;
-    int nl = (kTmaSmemBudget - fixed_bytes) / p.link_bytes;
-    if (nl > kTmaMaxLinkSlots) nl = kTmaMaxLinkSlots;
-    if (nl < 2) return false;
-    p.n_link_slots = nl;
+    const int avail = kTmaSmemBudget - 1024;
+    if (k.link_slots >= 0) { // links through shared memory: minimal spinor rings, the rest to link stages
+      p.n_center_slots = 4;
+      p.n_halo_slots = 2;
+      int nl = (avail - 4 * p.center_bytes - 2 * p.halo_bytes) / p.link_bytes;
+      if (nl > kTmaMaxLinkSlots) nl = kTmaMaxLinkSlots;
+      if (k.link_slots >= 2 && k.link_slots < nl) nl = k.link_slots;
+      if (nl < 2) return false;
+      p.n_link_slots = nl;
+    } else { // register stream: shared memory holds spinors only -> deeper rings (a centre slot per halo slot first)
+      p.n_link_slots = 0;
+      int nc = 4, nh = 2;
+      for (;;) {
+        if (nc < kTmaMaxCenterSlots && nc - 2 <= nh && (nc + 1) * p.center_bytes + nh * p.halo_bytes <= avail)
+          nc++;
+        else if (nh < kTmaMaxHaloSlots && nc * p.center_bytes + (nh + 1) * p.halo_bytes <= avail)
+          nh++;
+        else
+          break;
+      }
+      if (k.center_slots >= 4 && k.center_slots < nc) nc = k.center_slots;
+      if (k.halo_slots >= 2 && k.halo_slots < nh) nh = k.halo_slots;
+      if (nc * p.center_bytes + nh * p.halo_bytes > avail) return false;
+      p.n_center_slots = nc;
+      p.n_halo_slots = nh;
+    }
+    p.l2_prefetch_items = k.l2_prefetch <= 0 ? 0 : k.l2_prefetch; // (measured: the extra producer work costs more than it hides)
     p.off_center = 0;
-    p.off_halo = p.off_center + kTmaCenterSlots * p.center_bytes;
-    p.off_link = p.off_halo + kTmaHaloSlots * p.halo_bytes;
-    p.off_bar = p.off_link + nl * p.link_bytes;
+    p.off_halo = p.off_center + p.n_center_slots * p.center_bytes;
+    p.off_link = p.off_halo + p.n_halo_slots * p.halo_bytes;
+    p.off_bar = p.off_link + p.n_link_slots * p.link_bytes;
     p.smem_bytes = p.off_bar + 1024;
-    return true;
+    return p.smem_bytes <= kTmaSmemBudget;
   }
 
   // byte offsets of the regions inside a halo slot / a link stage
@@ -162,7 +214,7 @@ namespace b200
   }
 
   // ---- tensor-map descriptions ------------------------------------------------------------------------------------
-  // spinor field of one parity: (u32 lane, plane, y, z, t)
+  // field of one parity: (u32 lane, plane, y, z, t)
   B2_HD void tma_desc_field(TmaDesc &d, const void *base, int vec_bytes, int planes, size_t plane_stride_sites, const TmaPlan &p,
                             int box_planes, int by, int bz)
   {
@@ -201,6 +253,8 @@ namespace b200
     tma_desc_field(d[TM_GYB], gb, p.gvec, 4 * p.GP, gst, p, p.GP, p.TY - 1, p.TZ);
     tma_desc_field(d[TM_GZA], gb, p.gvec, 4 * p.GP, gst, p, p.GP, p.TY, 1);
     tma_desc_field(d[TM_GZB], gb, p.gvec, 4 * p.GP, gst, p, p.GP, p.TY, p.TZ - 1);
+    if (p.n_link_slots == 0)
+      for (int k = TM_GF; k < TM_COUNT; k++) d[k].valid = 0; // register-stream links: no gauge maps
   }
 
   // a tensor map is only usable if the hardware constraints hold (cuTensorMapEncodeTiled): 16-byte aligned base and strides
@@ -231,6 +285,17 @@ namespace b200
     it.par = p.n_parity == 2 ? pi : p.parity;
     it.y0 = (r - tzi * p.nty) * p.TY;
     it.z0 = tzi * p.TZ;
+  }
+
+  // item w + 1 given item w (the common case -- same tile, next slice -- without integer division)
+  B2_HD void tma_item_next(TmaItem &nx, const TmaItem &it, const TmaPlan &p, int w_next)
+  {
+    if (it.t + 1 < p.T) {
+      nx = it;
+      nx.t = it.t + 1;
+    } else {
+      tma_item(nx, p, w_next);
+    }
   }
 
   B2_HD void tma_work_range(int &w0, int &w1, const TmaPlan &p, int cta, int n_cta)
@@ -289,10 +354,12 @@ namespace b200
   // may block until its ring slot has been released, so the order must follow the order in which the slots become free:
   //   link stage (w, d)      -- slot of stage (w, d) - NL, released when the consumers are done with that direction pair;
   //   "early" loads of w + 1 -- the slice the item needs first that its predecessor did not already hold (t + 1, or
-  //                             t - 1 at the start of a chunk) and its halo rows: slots released at the end of item w - 1,
-  //                             i.e. together with link stage (w - 1, 3): requested just before link stage (w, NL);
+  //                             t - 1 at the start of a chunk) and its halo rows: with minimal rings their slots are
+  //                             released at the end of item w - 1, i.e. together with link stage (w - 1, 3): requested
+  //                             just before link stage (w, NL);
   //   "late" loads           -- chunk start only: slices t and t + 1, whose slots the previous chunk releases at its very
   //                             end: requested after the last link stage of item w.
+  // Centre, halo and link requests each carry consecutive sequence numbers (n-th load of that ring).
   // `Issuer` provides center(n, item, slice), halo(n, item), link(ln, item, d): the CUDA kernel waits on the empty
   // barrier and issues the TMA loads, the host twin records / replays them.
   template <class Issuer> B2_HD void tma_producer_program(const TmaPlan &plan, int w0, int w1, Issuer &is)
@@ -307,12 +374,27 @@ namespace b200
     is.halo(hn, it);
     is.center(cn + 1, it, it.t);
     is.center(cn + 2, it, tma_wrap(it.t + 1, plan.T));
+    // Shared memory holds only ~2 link stages in flight, less than bandwidth x DRAM latency: the link boxes are therefore
+    // first pulled into L2 `pf` items ahead (cp.async.bulk.prefetch.tensor, no shared memory involved), so that the
+    // staged loads only have to cover the L2 -> SM latency.
+    const int pf = NL > 0 ? plan.l2_prefetch_items : 0;
+    for (int k = 1; k < pf && w0 + k < w1; k++) {
+      TmaItem pi;
+      tma_item(pi, plan, w0 + k);
+      for (int d = 0; d < 4; d++) is.prefetch_link(pi, d);
+    }
     for (int w = w0; w < w1; w++) {
+      if (pf > 0 && w + pf < w1) {
+        TmaItem pi;
+        tma_item(pi, plan, w + pf);
+        for (int d = 0; d < 4; d++) is.prefetch_link(pi, d);
+      }
       const bool last = (w == w1 - 1) || (it.t == plan.T - 1);
       const int cn_next = cn + (last ? 3 : 1);
       TmaItem nx = it;
       const bool have_next = w + 1 < w1;
-      if (have_next) tma_item(nx, plan, w + 1);
+      if (have_next) tma_item_next(nx, it, plan, w + 1);
+#pragma unroll
       for (int d = 0; d <= 4; d++) {
         if (have_next && (d == NL || (d == 4 && NL >= 4))) { // early loads of the next item
           if (last)
@@ -321,7 +403,7 @@ namespace b200
             is.center(cn_next + 2, nx, tma_wrap(nx.t + 1, plan.T));
           is.halo(hn + 1, nx);
         }
-        if (d < 4) is.link(ln++, it, d);
+        if (d < 4 && NL > 0) is.link(ln++, it, d);
       }
       if (have_next && last) {
         is.center(cn_next + 1, nx, nx.t);
@@ -368,6 +450,29 @@ namespace b200
     th.g_bt = th.g_bx;
     th.g_by = th.ly == 0 ? tma_link_bwd_a(p) + th.lz * p.grow : tma_link_bwd_b(p) + (th.lz * (p.TY - 1) + th.ly - 1) * p.grow;
     th.g_bz = th.lz == 0 ? tma_link_bwd_a(p) + th.ly * p.grow : tma_link_bwd_b(p) + ((th.lz - 1) * p.TY + th.ly) * p.grow;
+  }
+
+  // Checkerboard indices of one output site of an item: the site itself (forward links, output, x, clover), its four
+  // backward neighbours (backward links; periodic wrap inside the local lattice) and rpar = (y + z + t + parity) & 1,
+  // which fixes x = 2 xh + rpar and with it which x lane of the input row the +-x neighbours sit in.
+  struct TmaSite {
+    int x_cb, b[4], rpar, par;
+  };
+
+  B2_HD void tma_site(TmaSite &s, const TmaPlan &p, const TmaThread &th, const TmaItem &it)
+  {
+    const int y = it.y0 + th.ly, z = it.z0 + th.lz;
+    const int row = z * p.Y + y;
+    const int slice = p.Xh * p.Y * p.Z;
+    const int in_slice = row * p.Xh + th.xh;
+    s.par = it.par;
+    s.rpar = (y + z + it.t + it.par) & 1;
+    s.x_cb = it.t * slice + in_slice;
+    const int xhm = s.rpar ? th.xh : (th.xh == 0 ? p.Xh - 1 : th.xh - 1);
+    s.b[0] = it.t * slice + row * p.Xh + xhm;
+    s.b[1] = s.x_cb + (y == 0 ? (p.Y - 1) * p.Xh : -p.Xh);
+    s.b[2] = s.x_cb + (z == 0 ? (p.Z - 1) * p.Y * p.Xh : -p.Y * p.Xh);
+    s.b[3] = (it.t == 0 ? p.T - 1 : it.t - 1) * slice + in_slice;
   }
 
   // ---- shared-memory loads --------------------------------------------------------------------------------------------
@@ -418,17 +523,14 @@ namespace b200
     for (int i = 0; i < GV::M; i++) raw.w[i] = lds<typename GV::V>(rec + i * row_bytes);
   }
 
-  // One hop with every operand in shared memory; arithmetic identical to hop_from (dslash_site.h) operation for operation.
-  template <class P, int recon, bool dagger, bool fwd, int d>
-  B2_HD void tma_hop(typename P::real *acc, const GaugeView<P, recon> &U, sptr spinor_rec, int srow_bytes, sptr link_rec,
-                     int grow_bytes, int link_idx)
+  // One hop with the neighbour spinor in shared memory and the link already unpacked; arithmetic identical to hop_from
+  // (dslash_site.h) operation for operation.
+  template <class P, bool dagger, bool fwd, int d>
+  B2_HD void tma_hop(typename P::real *acc, const typename P::real *u, sptr spinor_rec, int srow_bytes)
   {
     using real = typename P::real;
     constexpr int sign = fwd ? (dagger ? +1 : -1) : (dagger ? -1 : +1);
-    typename GaugeView<P, recon>::Raw raw;
-    lds_link<P, recon>(raw, link_rec, grow_bytes);
-    real u[18], h[12], r[12];
-    U.unpack(u, raw, d, link_idx);
+    real h[12], r[12];
     if constexpr (d == 3) {
       constexpr int np = 12 / P::Ns;
       real t[12];
@@ -449,28 +551,84 @@ namespace b200
     sptr cm, c0, cp, halo; // centre slots holding slices t-1, t, t+1; halo slot of slice t
   };
 
-  // forward + backward hop of dimension d.  `rpar` = (y + z + t + parity) & 1 of the output site: x = 2 xh + rpar.
-  template <class P, int recon, bool dagger, int d>
-  B2_HD void tma_hop_pair(typename P::real *acc, const GaugeView<P, recon> &U, const TmaPlan &p, const TmaThread &th,
-                          const TmaBases &b, sptr stage, int rpar, int x_cb, int x_cb_tm)
+  // shared-memory records of the forward / backward neighbour spinor of dimension d (x lane included)
+  template <int d> B2_HD void tma_neighbours(sptr &nf, sptr &nb, const TmaPlan &p, const TmaThread &th, const TmaBases &b, int rpar)
   {
-    const int svec = p.svec, gvec = p.gvec;
-    const int srow_b = svec * p.Xh, grow_b = gvec * p.Xh; // plane strides inside a record
-    const int xs = th.xh * svec, xg = th.xh * gvec;
+    const int xs = th.xh * p.svec;
     if constexpr (d == 0) {
       const int xhp = rpar ? (th.xh + 1 == p.Xh ? 0 : th.xh + 1) : th.xh;
       const int xhm = rpar ? th.xh : (th.xh == 0 ? p.Xh - 1 : th.xh - 1);
-      tma_hop<P, recon, dagger, true, 0>(acc, U, b.c0 + th.o_row + xhp * svec, srow_b, stage + th.g_f + xg, grow_b, x_cb);
-      tma_hop<P, recon, dagger, false, 0>(acc, U, b.c0 + th.o_row + xhm * svec, srow_b, stage + th.g_bx + xhm * gvec, grow_b, x_cb);
+      nf = b.c0 + th.o_row + xhp * p.svec;
+      nb = b.c0 + th.o_row + xhm * p.svec;
     } else if constexpr (d == 1) {
-      tma_hop<P, recon, dagger, true, 1>(acc, U, (th.h_yp ? b.halo : b.c0) + th.o_yp + xs, srow_b, stage + th.g_f + xg, grow_b, x_cb);
-      tma_hop<P, recon, dagger, false, 1>(acc, U, (th.h_ym ? b.halo : b.c0) + th.o_ym + xs, srow_b, stage + th.g_by + xg, grow_b, x_cb);
+      nf = (th.h_yp ? b.halo : b.c0) + th.o_yp + xs;
+      nb = (th.h_ym ? b.halo : b.c0) + th.o_ym + xs;
     } else if constexpr (d == 2) {
-      tma_hop<P, recon, dagger, true, 2>(acc, U, (th.h_zp ? b.halo : b.c0) + th.o_zp + xs, srow_b, stage + th.g_f + xg, grow_b, x_cb);
-      tma_hop<P, recon, dagger, false, 2>(acc, U, (th.h_zm ? b.halo : b.c0) + th.o_zm + xs, srow_b, stage + th.g_bz + xg, grow_b, x_cb);
+      nf = (th.h_zp ? b.halo : b.c0) + th.o_zp + xs;
+      nb = (th.h_zm ? b.halo : b.c0) + th.o_zm + xs;
     } else {
-      tma_hop<P, recon, dagger, true, 3>(acc, U, b.cp + th.o_row + xs, srow_b, stage + th.g_f + xg, grow_b, x_cb);
-      tma_hop<P, recon, dagger, false, 3>(acc, U, b.cm + th.o_row + xs, srow_b, stage + th.g_bt + xg, grow_b, x_cb_tm);
+      nf = b.cp + th.o_row + xs;
+      nb = b.cm + th.o_row + xs;
+    }
+  }
+
+  // forward + backward hop of dimension d, links from the shared-memory stage `stage`
+  template <class P, int recon, bool dagger, int d>
+  B2_HD void tma_hop_pair(typename P::real *acc, const GaugeView<P, recon> &U, const TmaPlan &p, const TmaThread &th,
+                          const TmaBases &b, sptr stage, const TmaSite &s)
+  {
+    using real = typename P::real;
+    const int srow_b = p.svec * p.Xh, grow_b = p.gvec * p.Xh; // plane strides inside a record
+    sptr nf, nb;
+    tma_neighbours<d>(nf, nb, p, th, b, s.rpar);
+    const int xhm = s.rpar ? th.xh : (th.xh == 0 ? p.Xh - 1 : th.xh - 1);
+    const int g_b = d == 0 ? th.g_bx + xhm * p.gvec : (d == 1 ? th.g_by : (d == 2 ? th.g_bz : th.g_bt)) + th.xh * p.gvec;
+    typename GaugeView<P, recon>::Raw raw;
+    real u[18];
+    lds_link<P, recon>(raw, stage + th.g_f + th.xh * p.gvec, grow_b);
+    U.unpack(u, raw, d, s.x_cb);
+    tma_hop<P, dagger, true, d>(acc, u, nf, srow_b);
+    lds_link<P, recon>(raw, stage + g_b, grow_b);
+    U.unpack(u, raw, d, s.b[d]);
+    tma_hop<P, dagger, false, d>(acc, u, nb, srow_b);
+  }
+
+  // Register-stream links: lk[2e], lk[2e+1] hold the packed forward / backward link of dimension e.  At step d the pair
+  // of dimension d is consumed (unpacked right here) and the loads of the pair that will be needed PD steps later --
+  // dimension (d + PD) % 4 of this item, or of the next one (`nx`) once d + PD wraps -- are issued into its registers,
+  // which have been dead since that pair was consumed.  PD = 4 gives every load a whole item (~4 us) at 96 live link
+  // registers (fp32 recon-12), PD = 2 half an item at 48.
+  template <class P, int recon, bool dagger, int d, int PD>
+  B2_HD void tma_hop_pair_stream(typename P::real *acc, const GaugeView<P, recon> &U, typename GaugeView<P, recon>::Raw *lk,
+                                 const TmaPlan &p, const TmaThread &th, const TmaBases &b, const TmaSite &s, const TmaSite &nx,
+                                 bool have_next)
+  {
+    using real = typename P::real;
+    static_assert(PD >= 1 && PD <= 4, "prefetch distance in direction pairs");
+    constexpr int e = (d + PD) & 3;
+    constexpr bool wraps = d + PD >= 4;
+    const int srow_b = p.svec * p.Xh;
+    sptr nf, nb;
+    tma_neighbours<d>(nf, nb, p, th, b, s.rpar);
+    real u[18];
+    const bool reload = !wraps || have_next;
+    const TmaSite &tg = wraps ? nx : s;
+    U.unpack(u, lk[2 * d], d, s.x_cb);
+    if (reload) U.template load_raw<Cache::STREAM>(lk[2 * e], e, tg.x_cb, tg.par);
+    tma_hop<P, dagger, true, d>(acc, u, nf, srow_b);
+    U.unpack(u, lk[2 * d + 1], d, s.b[d]);
+    if (reload) U.template load_raw<Cache::STREAM>(lk[2 * e + 1], e, tg.b[e], 1 - tg.par);
+    tma_hop<P, dagger, false, d>(acc, u, nb, srow_b);
+  }
+
+  // the first PD direction pairs of a site (start of a work range: nothing has been prefetched yet)
+  template <class P, int recon, int PD>
+  B2_HD void tma_load_links(typename GaugeView<P, recon>::Raw *lk, const GaugeView<P, recon> &U, const TmaSite &s)
+  {
+#pragma unroll
+    for (int d = 0; d < PD; d++) {
+      U.template load_raw<Cache::STREAM>(lk[2 * d], d, s.x_cb, s.par);
+      U.template load_raw<Cache::STREAM>(lk[2 * d + 1], d, s.b[d], 1 - s.par);
     }
   }
 
@@ -495,17 +653,6 @@ namespace b200
       }
     }
     arg.out[parity].save(acc, x_cb);
-  }
-
-  // checkerboard index of (xh, y, z, t) and of the same site one slice back (periodic)
-  B2_HD void tma_site_index(int &x_cb, int &x_cb_tm, int &rpar, const TmaPlan &p, const TmaThread &th, const TmaItem &it)
-  {
-    const int y = it.y0 + th.ly, z = it.z0 + th.lz;
-    const int slice = p.Xh * p.Y * p.Z;
-    const int in_slice = (z * p.Y + y) * p.Xh + th.xh;
-    x_cb = it.t * slice + in_slice;
-    x_cb_tm = (it.t == 0 ? p.T - 1 : it.t - 1) * slice + in_slice;
-    rpar = (y + z + it.t + it.par) & 1;
   }
 
 } // namespace b200

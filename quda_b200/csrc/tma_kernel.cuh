@@ -37,15 +37,25 @@ namespace b200
                  : "memory");
     return ok != 0;
   }
-  // Wait for the phase with parity `parity` to complete.  A pipeline bug must never hang the GPU: after ~1 s of SM
-  // clocks the kernel traps (the launch fails with an error instead of spinning until the watchdog).
+  // Wait for the phase with parity `parity` to complete.  A pipeline bug must never hang the GPU: after 2^26 failed
+  // probes (each try_wait suspends the thread for a while, so this is seconds) the kernel traps -- the launch fails with
+  // an error instead of spinning until the watchdog.
   __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
   {
     if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try(bar, parity)) {
-      if (clock64() - t0 > 2000000000LL) __trap();
+      if (++spins > (1 << 26)) __trap();
     }
+  }
+
+  // one lane of a converged warp (elect.sync): ptxas knows that exactly one thread executes the guarded code, which lets
+  // it issue uniform-datapath instructions (UTMALDG, SYNCS) there without a per-lane serialisation loop
+  __device__ __forceinline__ bool elect_one()
+  {
+    unsigned pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
   }
 
   __device__ __forceinline__ unsigned long long l2_policy_evict_first()
@@ -70,37 +80,34 @@ namespace b200
                  : "memory");
   }
 
-  // sequential ring position (slot + phase parity of the current pass)
-  struct TmaRing {
-    int slot;
-    unsigned phase;
-    __device__ __forceinline__ void advance(int n)
-    {
-      if (++slot == n) {
-        slot = 0;
-        phase ^= 1u;
-      }
-    }
-  };
+  // pull one box into L2 only (no shared memory, no completion tracking)
+  __device__ __forceinline__ void tma_prefetch_box(const CUtensorMap *map, const int *c)
+  {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c[0]), "r"(c[1]),
+                 "r"(c[2]), "r"(c[3]), "r"(c[4])
+                 : "memory");
+  }
 
-  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  template <class P, int recon, bool dagger, bool xpay, OpType op, int PD>
   __global__ void __launch_bounds__(kTmaMaxConsumers + 32, 1)
     dslash_tma_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TmaPlan plan,
                       const __grid_constant__ TmaMaps maps)
   {
     using real = typename P::real;
+    using Raw = typename GaugeView<P, recon>::Raw;
+    constexpr bool LSTREAM = PD > 0; // PD: prefetch distance of the register-stream links (0: links via shared memory)
     extern __shared__ __align__(1024) unsigned char tma_smem[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(tma_smem);
     const unsigned bars = sbase + plan.off_bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NL = plan.n_link_slots;
+    const int NCS = plan.n_center_slots, NHS = plan.n_halo_slots, NL = plan.n_link_slots;
 
     if (tid == 0) {
-      for (int s = 0; s < kTmaCenterSlots; s++) {
+      for (int s = 0; s < kTmaMaxCenterSlots; s++) {
         mbar_init(bars + 8 * tma_bar_full_c(s), 1);
         mbar_init(bars + 8 * tma_bar_empty_c(s), plan.n_cwarps);
       }
-      for (int s = 0; s < kTmaHaloSlots; s++) {
+      for (int s = 0; s < kTmaMaxHaloSlots; s++) {
         mbar_init(bars + 8 * tma_bar_full_h(s), 1);
         mbar_init(bars + 8 * tma_bar_empty_h(s), plan.n_cwarps);
       }
@@ -118,55 +125,77 @@ namespace b200
 
     if (warp == plan.n_cwarps) {
       // ================================================================== producer: one thread issues every box load
-      if (lane != 0) return;
-      const unsigned long long pol_links = l2_policy_evict_first(), pol_spinor = l2_policy_evict_last();
-      const unsigned center_tx = plan.NC * plan.srow, halo_tx = plan.NH * plan.srow, link_tx = 2 * plan.NC * plan.grow;
-
+      // The whole warp runs the (warp-uniform) program so that its address arithmetic stays on the uniform datapath; only
+      // lane 0 touches the mbarriers' transaction counts and issues the TMA instructions.
       struct Issuer {
         const TmaPlan &plan;
         const TmaMaps &maps;
         unsigned sbase, bars, center_tx, halo_tx, link_tx;
         unsigned long long pol_links, pol_spinor;
-        TmaRing lr;
+        bool leader;
+        TmaPos cp, hp, lp; // ring positions of the next centre / halo / link load (loads are requested in sequence)
+        int cn, hn;
+        long long ln;
         __device__ __forceinline__ const CUtensorMap *map(const TmaItem &it, int id) const
         {
           return &maps.m[plan.n_parity == 2 ? it.par : 0][id];
         }
         __device__ __forceinline__ void center(int n, const TmaItem &it, int slice)
         {
-          const int s = n & (kTmaCenterSlots - 1);
-          if (n >= kTmaCenterSlots) mbar_wait(bars + 8 * tma_bar_empty_c(s), ((n >> 2) - 1) & 1);
-          const unsigned full = bars + 8 * tma_bar_full_c(s);
-          mbar_expect_tx(full, center_tx);
+          if (n != cn) __trap(); // the program requests centre loads in sequence
+          if (n >= plan.n_center_slots) mbar_wait(bars + 8 * tma_bar_empty_c(cp.slot), cp.phase ^ 1u);
+          const unsigned full = bars + 8 * tma_bar_full_c(cp.slot);
           TmaBox b;
           tma_center_box(b, it, slice);
-          tma_load_box(sbase + plan.off_center + s * plan.center_bytes + b.dst, map(it, b.map), full, b.c, pol_spinor);
+          if (elect_one()) {
+            mbar_expect_tx(full, center_tx);
+            tma_load_box(sbase + plan.off_center + cp.slot * plan.center_bytes + b.dst, map(it, b.map), full, b.c, pol_spinor);
+          }
+          cp = tma_pos_next(cp, plan.n_center_slots);
+          cn++;
         }
         __device__ __forceinline__ void halo(int n, const TmaItem &it)
         {
-          const int s = n & (kTmaHaloSlots - 1);
-          if (n >= kTmaHaloSlots) mbar_wait(bars + 8 * tma_bar_empty_h(s), ((n >> 1) - 1) & 1);
-          const unsigned full = bars + 8 * tma_bar_full_h(s);
-          mbar_expect_tx(full, halo_tx);
+          if (n != hn) __trap();
+          if (n >= plan.n_halo_slots) mbar_wait(bars + 8 * tma_bar_empty_h(hp.slot), hp.phase ^ 1u);
+          const unsigned full = bars + 8 * tma_bar_full_h(hp.slot);
           TmaBox b[4];
           tma_halo_boxes(b, plan, it);
+          if (elect_one()) {
+            mbar_expect_tx(full, halo_tx);
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            tma_load_box(sbase + plan.off_halo + s * plan.halo_bytes + b[k].dst, map(it, b[k].map), full, b[k].c, pol_spinor);
+            for (int k = 0; k < 4; k++)
+              tma_load_box(sbase + plan.off_halo + hp.slot * plan.halo_bytes + b[k].dst, map(it, b[k].map), full, b[k].c, pol_spinor);
+          }
+          hp = tma_pos_next(hp, plan.n_halo_slots);
+          hn++;
         }
-        __device__ __forceinline__ void link(long long ln, const TmaItem &it, int d)
+        __device__ __forceinline__ void prefetch_link(const TmaItem &it, int d)
         {
-          if (ln >= plan.n_link_slots) mbar_wait(bars + 8 * tma_bar_empty_l(lr.slot), lr.phase ^ 1u);
-          const unsigned full = bars + 8 * tma_bar_full_l(lr.slot);
-          mbar_expect_tx(full, link_tx);
           TmaBox b[3];
           const int nb = tma_link_boxes(b, plan, it, d);
-          for (int k = 0; k < nb; k++)
-            tma_load_box(sbase + plan.off_link + lr.slot * plan.link_bytes + b[k].dst, map(it, b[k].map), full, b[k].c, pol_links);
-          lr.advance(plan.n_link_slots);
+          if (elect_one())
+            for (int k = 0; k < nb; k++) tma_prefetch_box(map(it, b[k].map), b[k].c);
+        }
+        __device__ __forceinline__ void link(long long n, const TmaItem &it, int d)
+        {
+          if (n != ln) __trap();
+          if (n >= plan.n_link_slots) mbar_wait(bars + 8 * tma_bar_empty_l(lp.slot), lp.phase ^ 1u);
+          const unsigned full = bars + 8 * tma_bar_full_l(lp.slot);
+          TmaBox b[3];
+          const int nb = tma_link_boxes(b, plan, it, d);
+          if (elect_one()) {
+            mbar_expect_tx(full, link_tx);
+            for (int k = 0; k < nb; k++)
+              tma_load_box(sbase + plan.off_link + lp.slot * plan.link_bytes + b[k].dst, map(it, b[k].map), full, b[k].c, pol_links);
+          }
+          lp = tma_pos_next(lp, plan.n_link_slots);
+          ln++;
         }
       };
-      Issuer is {plan, maps, sbase, bars, center_tx, halo_tx, link_tx, pol_links, pol_spinor, TmaRing {0, 0}};
+      Issuer is {plan, maps, sbase, bars, (unsigned)(plan.NC * plan.srow), (unsigned)(plan.NH * plan.srow),
+                 (unsigned)(2 * plan.NC * plan.grow), l2_policy_evict_first(), l2_policy_evict_last(), lane == 0,
+                 TmaPos {0, 0}, TmaPos {0, 0}, TmaPos {0, 0}, 0, 0, 0};
       tma_producer_program(plan, w0, w1, is);
       return;
     }
@@ -174,56 +203,80 @@ namespace b200
     // ==================================================================== consumers: one thread per site of the tile
     TmaThread th;
     tma_thread_init(th, plan, tid);
-    TmaRing lr {0, 0};
-    int cn = 0, hn = 0;
+    TmaPos c0p {0, 0}; // ring position of the centre load holding slice t-1 of the current item
+    TmaPos hp {0, 0}, lp {0, 0};
+    TmaItem it;
+    tma_item(it, plan, w0);
+    TmaSite cur;
+    tma_site(cur, plan, th, it);
+    Raw lk[LSTREAM ? 8 : 1];
+    if constexpr (LSTREAM) {
+      if (th.active) tma_load_links<P, recon, PD>(lk, arg.U, cur);
+    }
     for (int w = w0; w < w1; w++) {
-      TmaItem it;
-      tma_item(it, plan, w);
       const bool first = (w == w0) || (it.t == 0);
       const bool last = (w == w1 - 1) || (it.t == plan.T - 1);
-      if (first) {
-        mbar_wait(bars + 8 * tma_bar_full_c(cn & 3), (cn >> 2) & 1);
-        mbar_wait(bars + 8 * tma_bar_full_c((cn + 1) & 3), ((cn + 1) >> 2) & 1);
+      const bool have_next = w + 1 < w1;
+      TmaItem nit = it;
+      TmaSite nxt = cur;
+      if (have_next) {
+        tma_item_next(nit, it, plan, w + 1);
+        tma_site(nxt, plan, th, nit);
       }
-      mbar_wait(bars + 8 * tma_bar_full_c((cn + 2) & 3), ((cn + 2) >> 2) & 1);
-      mbar_wait(bars + 8 * tma_bar_full_h(hn & 1), (hn >> 1) & 1);
+      const TmaPos c1p = tma_pos_next(c0p, NCS), c2p = tma_pos_next(c1p, NCS);
+      if (first) {
+        mbar_wait(bars + 8 * tma_bar_full_c(c0p.slot), c0p.phase);
+        mbar_wait(bars + 8 * tma_bar_full_c(c1p.slot), c1p.phase);
+      }
+      mbar_wait(bars + 8 * tma_bar_full_c(c2p.slot), c2p.phase);
+      mbar_wait(bars + 8 * tma_bar_full_h(hp.slot), hp.phase);
       TmaBases b;
-      b.cm = sbase + plan.off_center + (cn & 3) * plan.center_bytes;
-      b.c0 = sbase + plan.off_center + ((cn + 1) & 3) * plan.center_bytes;
-      b.cp = sbase + plan.off_center + ((cn + 2) & 3) * plan.center_bytes;
-      b.halo = sbase + plan.off_halo + (hn & 1) * plan.halo_bytes;
-      int x_cb, x_cb_tm, rpar;
-      tma_site_index(x_cb, x_cb_tm, rpar, plan, th, it);
+      b.cm = sbase + plan.off_center + c0p.slot * plan.center_bytes;
+      b.c0 = sbase + plan.off_center + c1p.slot * plan.center_bytes;
+      b.cp = sbase + plan.off_center + c2p.slot * plan.center_bytes;
+      b.halo = sbase + plan.off_halo + hp.slot * plan.halo_bytes;
       real acc[24];
 #pragma unroll
       for (int i = 0; i < 24; i++) acc[i] = 0;
 
+      if constexpr (LSTREAM) {
+        if (th.active) {
+          tma_hop_pair_stream<P, recon, dagger, 0, PD>(acc, arg.U, lk, plan, th, b, cur, nxt, have_next);
+          tma_hop_pair_stream<P, recon, dagger, 1, PD>(acc, arg.U, lk, plan, th, b, cur, nxt, have_next);
+          tma_hop_pair_stream<P, recon, dagger, 2, PD>(acc, arg.U, lk, plan, th, b, cur, nxt, have_next);
+          tma_hop_pair_stream<P, recon, dagger, 3, PD>(acc, arg.U, lk, plan, th, b, cur, nxt, have_next);
+        }
+        __syncwarp();
+      } else {
 #define B2_TMA_DIM(D)                                                                                                  \
   {                                                                                                                    \
-    mbar_wait(bars + 8 * tma_bar_full_l(lr.slot), lr.phase);                                                           \
-    const unsigned stage = sbase + plan.off_link + lr.slot * plan.link_bytes;                                          \
-    if (th.active) tma_hop_pair<P, recon, dagger, D>(acc, arg.U, plan, th, b, stage, rpar, x_cb, x_cb_tm);             \
+    mbar_wait(bars + 8 * tma_bar_full_l(lp.slot), lp.phase);                                                           \
+    const unsigned stage = sbase + plan.off_link + lp.slot * plan.link_bytes;                                          \
+    if (th.active) tma_hop_pair<P, recon, dagger, D>(acc, arg.U, plan, th, b, stage, cur);                             \
     __syncwarp();                                                                                                      \
-    if (lane == 0) mbar_arrive(bars + 8 * tma_bar_empty_l(lr.slot));                                                   \
-    lr.advance(NL);                                                                                                    \
+    if (lane == 0) mbar_arrive(bars + 8 * tma_bar_empty_l(lp.slot));                                                   \
+    lp = tma_pos_next(lp, NL);                                                                                         \
   }
-      B2_TMA_DIM(0)
-      B2_TMA_DIM(1)
-      B2_TMA_DIM(2)
-      B2_TMA_DIM(3)
+        B2_TMA_DIM(0)
+        B2_TMA_DIM(1)
+        B2_TMA_DIM(2)
+        B2_TMA_DIM(3)
 #undef B2_TMA_DIM
+      }
       // every shared-memory operand of this item has been read: hand the oldest slice and the halo rows back
       if (lane == 0) {
-        mbar_arrive(bars + 8 * tma_bar_empty_c(cn & 3));
-        mbar_arrive(bars + 8 * tma_bar_empty_h(hn & 1));
+        mbar_arrive(bars + 8 * tma_bar_empty_c(c0p.slot));
+        mbar_arrive(bars + 8 * tma_bar_empty_h(hp.slot));
         if (last) {
-          mbar_arrive(bars + 8 * tma_bar_empty_c((cn + 1) & 3));
-          mbar_arrive(bars + 8 * tma_bar_empty_c((cn + 2) & 3));
+          mbar_arrive(bars + 8 * tma_bar_empty_c(c1p.slot));
+          mbar_arrive(bars + 8 * tma_bar_empty_c(c2p.slot));
         }
       }
-      if (th.active) tma_epilogue<P, recon, dagger, xpay, op>(acc, arg, x_cb, it.par);
-      cn += last ? 3 : 1;
-      hn++;
+      if (th.active) tma_epilogue<P, recon, dagger, xpay, op>(acc, arg, cur.x_cb, cur.par);
+      c0p = last ? tma_pos_next(c2p, NCS) : c1p;
+      hp = tma_pos_next(hp, NHS);
+      it = nit;
+      cur = nxt;
     }
   }
 
@@ -278,12 +331,8 @@ namespace b200
   int launch_tma(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
   {
     TmaPlan plan;
-    if (!tma_make_plan<P, recon>(plan, arg.geom, arg.n_parity, arg.parity, rq.tma_ty, rq.tma_tz)) return kTmaSkip;
-    if (rq.tma_link_slots >= 2 && rq.tma_link_slots < plan.n_link_slots) {
-      plan.n_link_slots = rq.tma_link_slots;
-      plan.off_bar = plan.off_link + plan.n_link_slots * plan.link_bytes;
-      plan.smem_bytes = plan.off_bar + 1024;
-    }
+    TmaKnobs knobs {rq.tma_ty, rq.tma_tz, rq.tma_link_slots, rq.tma_center_slots, rq.tma_halo_slots, rq.tma_l2_prefetch};
+    if (!tma_make_plan<P, recon>(plan, arg.geom, arg.n_parity, arg.parity, knobs)) return kTmaSkip;
     TmaMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int pi = 0; pi < arg.n_parity; pi++) {
@@ -295,16 +344,26 @@ namespace b200
         if (int rc = tma_encode(maps.m[pi][k], d[k])) return rc;
       }
     }
-    auto kern = dslash_tma_kernel<P, recon, dagger, xpay, op>;
-    static int smem_set = 0;
-    if (smem_set < plan.smem_bytes) {
-      if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes), "TMA kernel smem attribute"))
-        return rc;
-      smem_set = plan.smem_bytes;
-    }
     int grid = rq.tma_grid > 0 ? rq.tma_grid : tma_sm_count();
     if (grid > plan.n_items) grid = plan.n_items;
-    kern<<<grid, (plan.n_cwarps + 1) * 32, plan.smem_bytes, (cudaStream_t)rq.stream>>>(arg, plan, maps);
+    const int threads = (plan.n_cwarps + 1) * 32;
+    cudaStream_t s = (cudaStream_t)rq.stream;
+    auto go = [&](auto kern) -> int {
+      if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBudget), "TMA kernel smem attribute"))
+        return rc;
+      kern<<<grid, threads, plan.smem_bytes, s>>>(arg, plan, maps);
+      return 0;
+    };
+    int rc = 0;
+    if (plan.n_link_slots > 0)
+      rc = go(dslash_tma_kernel<P, recon, dagger, xpay, op, 0>);
+    else if (rq.tma_prefetch == 2)
+      rc = go(dslash_tma_kernel<P, recon, dagger, xpay, op, 2>);
+    else if (rq.tma_prefetch == 4)
+      rc = go(dslash_tma_kernel<P, recon, dagger, xpay, op, 4>);
+    else
+      rc = go(dslash_tma_kernel<P, recon, dagger, xpay, op, 3>);
+    if (rc) return rc;
     count_launch();
     return check_cuda(cudaGetLastError(), "dslash TMA launch");
   }

@@ -72,7 +72,8 @@ ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_void_p)
 
 class SolverParam(C.Structure):
     _fields_ = [("tol", C.c_double), ("maxiter", C.c_int), ("delta", C.c_double), ("iter", C.c_int),
-                ("reliable_updates", C.c_int), ("true_res", C.c_double), ("secs", C.c_double), ("gflops", C.c_double)]
+                ("reliable_updates", C.c_int), ("true_res", C.c_double), ("secs", C.c_double), ("gflops", C.c_double),
+                ("host_syncs", C.c_int)]
 
 
 MAX_MULTI_RHS = 16
@@ -145,6 +146,7 @@ def load():
         lib.b200_dirac_reconstruct.restype = C.c_int
         lib.b200_invert_cg.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Spinor), C.POINTER(Spinor), C.POINTER(SolverParam)]
         lib.b200_invert_cg.restype = C.c_int
+        lib.b200_comm_check.argtypes, lib.b200_comm_check.restype = [C.POINTER(Comm), C.c_void_p], C.c_int
         if lib.b200_abi_version() != ABI_VERSION:
             raise B200Error("libquda_b200.so ABI version mismatch")
         _lib = lib
@@ -162,5 +164,5 @@ EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_dslash_apply_multi", "b200_clover
                     "b200_copy_spinor", "b200_copy_gauge", "b200_copy_clover", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
                     "b200_dirac_create", "b200_dirac_set_twist", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",
-                    "b200_dirac_reconstruct", "b200_invert_cg",
+                    "b200_dirac_reconstruct", "b200_invert_cg", "b200_comm_check",
                     "b200_last_error", "b200_abi_version", "b200_launch_count", "b200_reset_launch_count"]

@@ -353,6 +353,9 @@ int twin_dslash_apply(const b200_dslash_args *a)
   if (const char *e = getenv("B200_TMA_TILE")) sscanf(e, "%d %d", &rq.tma_ty, &rq.tma_tz);
   if (const char *e = getenv("B200_TMA_GRID")) rq.tma_grid = atoi(e);
   if (const char *e = getenv("B200_TMA_LINKS")) rq.tma_link_slots = atoi(e);
+  if (const char *e = getenv("B200_TMA_PREFETCH")) rq.tma_prefetch = atoi(e);
+  if (const char *e = getenv("B200_TMA_L2PF")) rq.tma_l2_prefetch = atoi(e);
+  if (const char *e = getenv("B200_TMA_RINGS")) sscanf(e, "%d %d", &rq.tma_center_slots, &rq.tma_halo_slots);
   switch (a->precision) {
   case B200_DOUBLE: return run_precision<PrecF64>(rq);
   case B200_SINGLE: return run_precision<PrecF32>(rq);

@@ -54,19 +54,24 @@ namespace b200
     void center(int n, const TmaItem &it, int slice) { ops.push_back({0, n, it, slice}); }
     void halo(int n, const TmaItem &it) { ops.push_back({1, n, it, 0}); }
     void link(long long ln, const TmaItem &it, int d) { ops.push_back({2, ln, it, d}); }
+    void prefetch_link(const TmaItem &, int) { n_prefetch++; } // L2 hint only: no functional effect
+    long n_prefetch = 0;
   };
 
   // one CTA; returns 0 or an error code (message via set_error)
-  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  template <class P, int recon, bool dagger, bool xpay, OpType op, int PD>
   int tma_emu_cta(const DslashArgs<P, recon> &arg, const TmaPlan &plan, const TmaDesc (*descs)[TM_COUNT], int cta, int n_cta, long &visited)
   {
     using real = typename P::real;
+    using Raw = typename GaugeView<P, recon>::Raw;
+    constexpr bool LSTREAM = PD > 0;
     int w0, w1;
     tma_work_range(w0, w1, plan, cta, n_cta);
     if (w0 >= w1) return 0;
-    const int NL = plan.n_link_slots;
+    const int NL = plan.n_link_slots, NCS = plan.n_center_slots, NHS = plan.n_halo_slots;
+    if (LSTREAM != (NL == 0)) return set_error(B200_ERR_INVALID, "emulation: link mode / plan mismatch");
     std::vector<unsigned char> smem(plan.smem_bytes, 0xA5);
-    std::vector<long long> own_c(kTmaCenterSlots, -1), own_h(kTmaHaloSlots, -1), own_l(NL, -1);
+    std::vector<long long> own_c(NCS, -1), own_h(NHS, -1), own_l(NL > 0 ? NL : 1, -1);
     TmaEmuRecorder rec;
     tma_producer_program(plan, w0, w1, rec);
     size_t pi = 0;
@@ -79,7 +84,7 @@ namespace b200
       while (pi < rec.ops.size()) {
         const TmaEmuOp &o = rec.ops[pi];
         if (o.ring == 0) {
-          const int s = (int)(o.n & (kTmaCenterSlots - 1));
+          const int s = (int)(o.n % NCS);
           if (own_c[s] >= 0) break;
           TmaBox b;
           tma_center_box(b, o.it, o.arg);
@@ -88,7 +93,7 @@ namespace b200
           tma_emu_box_load(smem.data() + plan.off_center + s * plan.center_bytes + b.dst, d, b.c);
           own_c[s] = o.n;
         } else if (o.ring == 1) {
-          const int s = (int)(o.n & (kTmaHaloSlots - 1));
+          const int s = (int)(o.n % NHS);
           if (own_h[s] >= 0) break;
           TmaBox b[4];
           tma_halo_boxes(b, plan, o.it);
@@ -135,63 +140,97 @@ namespace b200
     std::vector<TmaThread> th(nthr);
     for (int t = 0; t < nthr; t++) tma_thread_init(th[t], plan, t);
     std::vector<real> acc((size_t)nthr * 24);
-    int cn = 0, hn = 0;
-    long long ln = 0;
+    std::vector<Raw> lk((size_t)nthr * 8); // the consumers' link registers (register-stream mode)
+    std::vector<TmaSite> cur(nthr), nxt(nthr);
+    // ring positions exactly as the CUDA consumers track them; cn / hn / ln are the load numbers they must hold
+    TmaPos c0p {0, 0}, hp {0, 0}, lp {0, 0};
+    long long cn = 0, hn = 0, ln = 0;
     {
       const int r = produce(); // the producer starts before anybody waits
       if (r < 0) return r;
     }
+    TmaItem it;
+    tma_item(it, plan, w0);
+    for (int t = 0; t < nthr; t++) {
+      tma_site(cur[t], plan, th[t], it);
+      if (LSTREAM && th[t].active) {
+        memset(&lk[(size_t)t * 8], 0xFF, 8 * sizeof(Raw)); // registers not loaded yet hold garbage
+        if constexpr (LSTREAM) tma_load_links<P, recon, PD>(&lk[(size_t)t * 8], arg.U, cur[t]);
+      }
+    }
     for (int w = w0; w < w1; w++) {
-      TmaItem it;
-      tma_item(it, plan, w);
+      {
+        TmaItem chk;
+        tma_item(chk, plan, w);
+        if (chk.par != it.par || chk.y0 != it.y0 || chk.z0 != it.z0 || chk.t != it.t)
+          return set_error(B200_ERR_INVALID, "tma_item_next disagrees with tma_item at item %d", w);
+      }
       const bool first = (w == w0) || (it.t == 0);
       const bool last = (w == w1 - 1) || (it.t == plan.T - 1);
-      if (first) {
-        if (int e = wait(own_c, cn & 3, cn, "centre")) return e;
-        if (int e = wait(own_c, (cn + 1) & 3, cn + 1, "centre")) return e;
+      const bool have_next = w + 1 < w1;
+      TmaItem nit = it;
+      if (have_next) tma_item_next(nit, it, plan, w + 1);
+      for (int t = 0; t < nthr; t++) {
+        nxt[t] = cur[t];
+        if (have_next) tma_site(nxt[t], plan, th[t], nit);
       }
-      if (int e = wait(own_c, (cn + 2) & 3, cn + 2, "centre")) return e;
-      if (int e = wait(own_h, hn & 1, hn, "halo")) return e;
+      const TmaPos c1p = tma_pos_next(c0p, NCS), c2p = tma_pos_next(c1p, NCS);
+      if (first) {
+        if (int e = wait(own_c, c0p.slot, cn, "centre")) return e;
+        if (int e = wait(own_c, c1p.slot, cn + 1, "centre")) return e;
+      }
+      if (int e = wait(own_c, c2p.slot, cn + 2, "centre")) return e;
+      if (int e = wait(own_h, hp.slot, hn, "halo")) return e;
       // slices t-1 and t must still be the loads this item expects (they were waited for by earlier items)
-      if (own_c[cn & 3] != cn || own_c[(cn + 1) & 3] != cn + 1)
+      if (own_c[c0p.slot] != cn || own_c[c1p.slot] != cn + 1)
         return set_error(B200_ERR_INVALID, "TMA pipeline: centre slot overwritten while live (CTA %d item %d)", cta, w);
+      // the phase parity the CUDA consumer waits with must be the parity of the pass that load belongs to
+      if (c0p.phase != (unsigned)((cn / NCS) & 1) || c2p.phase != (unsigned)(((cn + 2) / NCS) & 1) || hp.phase != (unsigned)((hn / NHS) & 1))
+        return set_error(B200_ERR_INVALID, "TMA pipeline: ring phase tracking out of step (CTA %d item %d)", cta, w);
       TmaBases b;
-      b.cm = smem.data() + plan.off_center + (cn & 3) * plan.center_bytes;
-      b.c0 = smem.data() + plan.off_center + ((cn + 1) & 3) * plan.center_bytes;
-      b.cp = smem.data() + plan.off_center + ((cn + 2) & 3) * plan.center_bytes;
-      b.halo = smem.data() + plan.off_halo + (hn & 1) * plan.halo_bytes;
+      b.cm = smem.data() + plan.off_center + c0p.slot * plan.center_bytes;
+      b.c0 = smem.data() + plan.off_center + c1p.slot * plan.center_bytes;
+      b.cp = smem.data() + plan.off_center + c2p.slot * plan.center_bytes;
+      b.halo = smem.data() + plan.off_halo + hp.slot * plan.halo_bytes;
       for (size_t i = 0; i < acc.size(); i++) acc[i] = 0;
       auto dim = [&](auto D) -> int {
         constexpr int d = decltype(D)::value;
-        const int slot = (int)(ln % NL);
-        if (int e = wait(own_l, slot, ln, "link")) return e;
-        const unsigned char *stage = smem.data() + plan.off_link + slot * plan.link_bytes;
-        for (int t = 0; t < nthr; t++) {
-          if (!th[t].active) continue;
-          int x_cb, x_cb_tm, rpar;
-          tma_site_index(x_cb, x_cb_tm, rpar, plan, th[t], it);
-          tma_hop_pair<P, recon, dagger, d>(&acc[(size_t)t * 24], arg.U, plan, th[t], b, stage, rpar, x_cb, x_cb_tm);
+        if constexpr (LSTREAM) {
+          for (int t = 0; t < nthr; t++) {
+            if (!th[t].active) continue;
+            tma_hop_pair_stream<P, recon, dagger, d, (PD > 0 ? PD : 1)>(&acc[(size_t)t * 24], arg.U, &lk[(size_t)t * 8], plan, th[t], b, cur[t], nxt[t], have_next);
+          }
+          return 0;
+        } else {
+          if (int e = wait(own_l, lp.slot, ln, "link")) return e;
+          if (lp.phase != (unsigned)((ln / NL) & 1)) return set_error(B200_ERR_INVALID, "TMA pipeline: link ring phase out of step");
+          const unsigned char *stage = smem.data() + plan.off_link + lp.slot * plan.link_bytes;
+          for (int t = 0; t < nthr; t++) {
+            if (!th[t].active) continue;
+            tma_hop_pair<P, recon, dagger, d>(&acc[(size_t)t * 24], arg.U, plan, th[t], b, stage, cur[t]);
+          }
+          own_l[lp.slot] = -1; // released
+          poison(plan.off_link + lp.slot * plan.link_bytes, plan.link_bytes);
+          lp = tma_pos_next(lp, NL);
+          ln++;
+          const int r = produce(); // aggressive producer: refill as soon as a slot is free
+          return r < 0 ? r : 0;
         }
-        own_l[slot] = -1; // released
-        poison(plan.off_link + slot * plan.link_bytes, plan.link_bytes);
-        ln++;
-        const int r = produce(); // aggressive producer: refill as soon as a slot is free
-        return r < 0 ? r : 0;
       };
       if (int e = dim(std::integral_constant<int, 0> {})) return e;
       if (int e = dim(std::integral_constant<int, 1> {})) return e;
       if (int e = dim(std::integral_constant<int, 2> {})) return e;
       if (int e = dim(std::integral_constant<int, 3> {})) return e;
-      auto release_c = [&](int n) {
-        own_c[n & 3] = -1;
-        poison(plan.off_center + (n & 3) * plan.center_bytes, plan.center_bytes);
+      auto release_c = [&](int slot) {
+        own_c[slot] = -1;
+        poison(plan.off_center + slot * plan.center_bytes, plan.center_bytes);
       };
-      release_c(cn);
-      own_h[hn & 1] = -1;
-      poison(plan.off_halo + (hn & 1) * plan.halo_bytes, plan.halo_bytes);
+      release_c(c0p.slot);
+      own_h[hp.slot] = -1;
+      poison(plan.off_halo + hp.slot * plan.halo_bytes, plan.halo_bytes);
       if (last) {
-        release_c(cn + 1);
-        release_c(cn + 2);
+        release_c(c1p.slot);
+        release_c(c2p.slot);
       }
       {
         const int r = produce();
@@ -199,14 +238,18 @@ namespace b200
       }
       for (int t = 0; t < nthr; t++) {
         if (!th[t].active) continue;
-        int x_cb, x_cb_tm, rpar;
-        tma_site_index(x_cb, x_cb_tm, rpar, plan, th[t], it);
-        tma_epilogue<P, recon, dagger, xpay, op>(&acc[(size_t)t * 24], arg, x_cb, it.par);
+        tma_epilogue<P, recon, dagger, xpay, op>(&acc[(size_t)t * 24], arg, cur[t].x_cb, cur[t].par);
         visited++;
       }
+      c0p = last ? tma_pos_next(c2p, NCS) : c1p;
       cn += last ? 3 : 1;
+      hp = tma_pos_next(hp, NHS);
       hn++;
+      it = nit;
+      cur.swap(nxt);
     }
+    if (NL > 0 && plan.l2_prefetch_items > 0 && rec.n_prefetch != 4L * ((w1 - w0) - 1))
+      return set_error(B200_ERR_INVALID, "TMA pipeline: CTA %d prefetched %ld link stages for %d items", cta, rec.n_prefetch, w1 - w0);
     if (pi != rec.ops.size())
       return set_error(B200_ERR_INVALID, "TMA pipeline: CTA %d finished with %zu producer ops never issued", cta, rec.ops.size() - pi);
     return 0;
@@ -221,12 +264,8 @@ namespace b200
     } else {
       if (op == OP_CLOVER_PC && dagger && xpay) return kTmaSkip;
       TmaPlan plan;
-      if (!tma_make_plan<P, recon>(plan, arg.geom, arg.n_parity, arg.parity, rq.tma_ty, rq.tma_tz)) return kTmaSkip;
-      if (rq.tma_link_slots >= 2 && rq.tma_link_slots < plan.n_link_slots) {
-        plan.n_link_slots = rq.tma_link_slots;
-        plan.off_bar = plan.off_link + plan.n_link_slots * plan.link_bytes;
-        plan.smem_bytes = plan.off_bar + 1024;
-      }
+      TmaKnobs knobs {rq.tma_ty, rq.tma_tz, rq.tma_link_slots, rq.tma_center_slots, rq.tma_halo_slots, rq.tma_l2_prefetch};
+      if (!tma_make_plan<P, recon>(plan, arg.geom, arg.n_parity, arg.parity, knobs)) return kTmaSkip;
       if (plan.smem_bytes > kTmaSmemBudget) return set_error(B200_ERR_INVALID, "TMA plan needs %d bytes of shared memory", plan.smem_bytes);
       TmaDesc descs[2][TM_COUNT];
       for (int pi = 0; pi < arg.n_parity; pi++) {
@@ -241,7 +280,15 @@ namespace b200
 #pragma omp parallel for reduction(+ : visited) schedule(dynamic)
       for (int cta = 0; cta < grid; cta++) {
         long v = 0;
-        const int e = tma_emu_cta<P, recon, dagger, xpay, op>(arg, plan, descs, cta, grid, v);
+        int e;
+        if (plan.n_link_slots > 0)
+          e = tma_emu_cta<P, recon, dagger, xpay, op, 0>(arg, plan, descs, cta, grid, v);
+        else if (rq.tma_prefetch == 2)
+          e = tma_emu_cta<P, recon, dagger, xpay, op, 2>(arg, plan, descs, cta, grid, v);
+        else if (rq.tma_prefetch == 4)
+          e = tma_emu_cta<P, recon, dagger, xpay, op, 4>(arg, plan, descs, cta, grid, v);
+        else
+          e = tma_emu_cta<P, recon, dagger, xpay, op, 3>(arg, plan, descs, cta, grid, v);
         visited += v;
         if (e) {
 #pragma omp critical

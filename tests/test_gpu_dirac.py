@@ -57,11 +57,11 @@ def test_clover_mat_and_matpc(prec, dynamic):
             assert_close(ref, P.to_host(out), prec, 12, f"clover Mpc type={matpc} dag={dagger}")
 
 
-def _solve_full_system(P, kind_pc, X, tol, mixed, matpc=DR.MATPC_EVEN_EVEN):
+def _solve_full_system(P, kind_pc, X, tol, mixed, matpc=DR.MATPC_EVEN_EVEN, stream=None):
     """invertQuda-style: prepare -> CG on MpcdagMpc -> reconstruct, then verify M x = b on the host."""
     import torch
     kw = dict(clover=P.A, clover_inv=P.Ainv) if "clover" in kind_pc else {}
-    pc = DR.Dirac(kind_pc, P.U, KAPPA, matpc_type=matpc, **kw)
+    pc = DR.Dirac(kind_pc, P.U, KAPPA, matpc_type=matpc, stream=stream, **kw)
     b = P.spinor(seed=77, nparity=2)
     bdev, xdev = P.to_dev(b, 2), P.empty(2)
     src_p, sol_p = pc.prepare(xdev, bdev)
@@ -78,7 +78,7 @@ def _solve_full_system(P, kind_pc, X, tol, mixed, matpc=DR.MATPC_EVEN_EVEN):
     if mixed:
         Ps = Problem(X, 4, 12, CudaMem, clover=P.clover is not None, compressed=True, dynamic=True)
         kws = dict(clover=Ps.A, clover_inv=Ps.Ainv) if "clover" in kind_pc else {}
-        sloppy = DR.Dirac(kind_pc, Ps.U, KAPPA, matpc_type=matpc, **kws)
+        sloppy = DR.Dirac(kind_pc, Ps.U, KAPPA, matpc_type=matpc, stream=stream, **kws)
         sloppy._keep = Ps
     res = DR.invert_cg(pc, sloppy, sol, rhs, tol=tol, maxiter=2000)
     pc.reconstruct(xdev, bdev)
@@ -137,15 +137,9 @@ def test_partitioned_operators_through_cpp_layer():
     assert not ex.timed_out()
 
 
-# The C++ twisted-mass operator classes were written after the last GPU session of round 1; their building blocks
-# (ApplyTwistedMass*, ApplyTwistGamma) are covered by tests/test_gpu_ops.py::test_twisted_mass, the classes themselves wait
-# for their first run on hardware: B200_EXPERIMENTAL=1.
-_experimental = pytest.mark.skipif(not __import__("os").environ.get("B200_EXPERIMENTAL"),
-                                   reason="first hardware run pending, enable with B200_EXPERIMENTAL=1")
 MU = 0.1
 
 
-@_experimental
 @pytest.mark.parametrize("prec", [8, 4])
 def test_twisted_mass_mat_and_matpc(prec):
     """DiracTwistedMass / DiracTwistedMassPC (lib/dirac_twisted_mass.cpp) against tm_mat / tm_matpc"""
@@ -167,7 +161,6 @@ def test_twisted_mass_mat_and_matpc(prec):
             assert_close(ref, P.to_host(out), prec, 12, f"twisted-mass Mpc type={matpc} dag={dagger}")
 
 
-@_experimental
 @pytest.mark.parametrize("matpc", [DR.MATPC_EVEN_EVEN, DR.MATPC_ODD_ODD_ASYMMETRIC])
 def test_cg_twisted_mass_full_system(matpc):
     """prepare -> CG on MpcdagMpc -> reconstruct for the twisted-mass operator, verified with the oracle's tm_mat"""
@@ -190,3 +183,37 @@ def test_cg_twisted_mass_full_system(matpc):
     Mx = oracle.tm_mat(P.gauge, x, X, KAPPA, MU, 0)
     true_res = np.linalg.norm(Mx.ravel() - b.ravel()) / np.linalg.norm(b.ravel())
     assert res.iter < 2000 and true_res < 1e-8, (res.iter, true_res)
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_cg_on_a_non_blocking_stream(mixed):
+    """Every kernel of the operator / blas / solver layer must run on the operator's stream: build the operators on a
+    cudaStreamNonBlocking stream (any torch side stream is one -- it does NOT synchronise with the legacy default stream)
+    while the default stream is kept busy with unrelated work, and solve.  With blas kernels on the default stream (the
+    round-1 bug) axpyNorm / reDotProduct would race against MdagM and the solve would diverge or return garbage."""
+    import torch
+    X = (8, 8, 8, 8)
+    P = Problem(X, 8, 18, CudaMem, clover=True, compressed=True, dynamic=True)
+    side = torch.cuda.Stream()
+    junk = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(20):
+        junk.add_(1.0)  # keeps the default stream busy during the solve
+    with torch.cuda.stream(side):
+        res, true_res = _solve_full_system(P, "cloverpc", X, 1e-10, mixed=mixed, stream=side.cuda_stream)
+        side.synchronize()
+    assert res.iter < 2000 and res.true_res < 5e-10, (res.iter, res.true_res)
+    assert true_res < 1e-8, true_res
+    # the host followed the GPU one iteration behind: about one stream synchronisation per iteration, none of them on
+    # the critical path (the reference's CG has two blocking reductions per iteration, lib/inv_cg_quda.cpp:354-377)
+    assert res.host_syncs <= res.iter + 4 * (res.reliable_updates + 2), (res.host_syncs, res.iter, res.reliable_updates)
+
+
+def test_reductions_are_bit_reproducible():
+    """two-stage reductions summed in a fixed order: the same solve twice gives bit-identical iteration counts and
+    residuals (the reference needs QUDA_DETERMINISTIC_REDUCE for this, include/communicator_quda.h:570)"""
+    X = (8, 8, 8, 8)
+    P = Problem(X, 8, 18, CudaMem)
+    a = _solve_full_system(P, "wilsonpc", X, 1e-10, mixed=False)
+    b = _solve_full_system(P, "wilsonpc", X, 1e-10, mixed=False)
+    assert a[0].iter == b[0].iter and a[0].true_res == b[0].true_res and a[1] == b[1]

@@ -35,11 +35,11 @@ def test_tma_wilson_dslash(tma, X, prec, recon):
             assert_close(ref, P.to_host(out), prec, recon, f"X={X} parity={parity} dagger={dagger}")
 
 
-@pytest.mark.parametrize("links", [2, 3, 4])
+@pytest.mark.parametrize("links", [-1, 0, 2, 3, 4])
 @pytest.mark.parametrize("grid", [1, 3, 7, 37, 148, 1000])
 def test_tma_pipeline_depths_and_work_ranges(tma, links, grid):
-    """every link-ring depth and work partition (ranges that start / end mid-tile, one item per CTA, one CTA for
-    everything): no deadlock, no slot hazard, every site visited once"""
+    """both link modes (-1: register stream, 0 / n: shared-memory stages) and every work partition (ranges that start / end
+    mid-tile, one item per CTA, one CTA for everything): no deadlock, no slot hazard, every site visited once"""
     tma.setenv("B200_TMA_LINKS", str(links))
     tma.setenv("B200_TMA_GRID", str(grid))
     be = twin_backend()
@@ -49,6 +49,41 @@ def test_tma_pipeline_depths_and_work_ranges(tma, links, grid):
     out = P.empty()
     D.ApplyWilson(out, P.to_dev(s), P.U, 0.0, None, 1, 0, backend=be)
     assert_close(oracle.wil_dslash(P.gauge, s, X, 1, 0), P.to_host(out), 4, 12, f"links={links} grid={grid}")
+
+
+@pytest.mark.parametrize("prefetch", [2, 3, 4])
+@pytest.mark.parametrize("rings", ["4 2", "5 2", "6 3", "8 4"])
+@pytest.mark.parametrize("grid", [5, 148])
+def test_tma_register_stream_links(tma, prefetch, rings, grid):
+    """register-stream links: every prefetch distance (the reload of a direction pair targets this item or the next one)
+    and spinor ring depth, with work ranges that cross tiles and parities (full field)"""
+    tma.setenv("B200_TMA_LINKS", "-1")
+    tma.setenv("B200_TMA_PREFETCH", str(prefetch))
+    tma.setenv("B200_TMA_RINGS", rings)
+    tma.setenv("B200_TMA_GRID", str(grid))
+    be = twin_backend()
+    X = (8, 4, 4, 6)
+    P = Problem(X, 4, 12, HostMem)
+    full = P.spinor(seed=3, nparity=2)
+    out = P.empty(2)
+    D.ApplyWilson(out, P.to_dev(full, 2), P.U, 0.0, None, D.QUDA_INVALID_PARITY, 1, backend=be)
+    ref = np.concatenate([oracle.wil_dslash(P.gauge, full[P.Vh:], X, 0, 1), oracle.wil_dslash(P.gauge, full[:P.Vh], X, 1, 1)])
+    assert_close(ref, P.to_host(out), 4, 12, f"prefetch={prefetch} rings={rings}")
+
+
+@pytest.mark.parametrize("l2pf", [-1, 1, 2, 5])
+def test_tma_l2_prefetch_lookahead(tma, l2pf):
+    """the L2 prefetch of the link boxes is a hint (no functional effect) but its coordinates come from the same box
+    function: every look-ahead, including one beyond the end of a CTA's work range, must leave the result unchanged"""
+    tma.setenv("B200_TMA_L2PF", str(l2pf))
+    tma.setenv("B200_TMA_GRID", "7")
+    be = twin_backend()
+    X = (16, 4, 4, 6)
+    P = Problem(X, 4, 12, HostMem)
+    s = P.spinor(seed=8)
+    out = P.empty()
+    D.ApplyWilson(out, P.to_dev(s), P.U, 0.0, None, 0, 0, backend=be)
+    assert_close(oracle.wil_dslash(P.gauge, s, X, 0, 0), P.to_host(out), 4, 12, f"l2pf={l2pf}")
 
 
 @pytest.mark.parametrize("tile", ["1 1", "2 1", "1 2", "4 2", "2 4", "4 4", "8 1"])
