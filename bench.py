@@ -20,6 +20,11 @@ import sys
 import threading
 import time
 
+# The CPU arm (reference Dslash on the host cores) is an OpenMP code: pin its threads to cores, one per place, before any
+# OpenMP runtime is loaded -- unpinned it swung 5x between otherwise identical boxes.
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "threads")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -48,7 +53,12 @@ def parse():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fp64 / half / clover-pc sub-lines of the default run")
     ap.add_argument("--breakdown", action="store_true", help="(N>1) also time pack / interior / exterior separately")
+    ap.add_argument("--grid", type=int, nargs=4, default=None,
+                    help="(N>1) process grid (x y z t), product = N; default splits t, then z, then y.  BASELINE config 4's "
+                         "2x1x1x1 is --grid 2 1 1 1 (the strided x face)")
+    ap.add_argument("--no-halo-check", action="store_true", help="(N>1) skip the partitioned-vs-global-oracle parity check")
     return ap.parse_args()
 
 
@@ -130,8 +140,24 @@ def cpu_reference(X, prec, budget_s=20.0, min_reps=2):
     dt = (time.perf_counter() - t0) / reps
     gf = 1320.0 * Vh / dt * 1e-9
     return gf, {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "ms_per_call": dt * 1e3,
+                "pinning": {"OMP_PROC_BIND": os.environ.get("OMP_PROC_BIND"), "OMP_PLACES": os.environ.get("OMP_PLACES"),
+                            "numa": numa_layout()},
                 "sample": f"{reps} applications of the single-parity Wilson Dslash on {'x'.join(map(str, X))} "
                           f"({'fp64' if hp == 8 else 'fp32'} host fields), OpenMP over {cores} threads"}
+
+
+def numa_layout():
+    """sockets / NUMA nodes / threads per core of the host (lscpu), for the CPU arm's record"""
+    try:
+        o = subprocess.check_output(["lscpu"], timeout=5).decode()
+        keep = {}
+        for line in o.splitlines():
+            k, _, v = line.partition(":")
+            if k.strip() in ("Socket(s)", "NUMA node(s)", "Thread(s) per core", "Core(s) per socket", "Model name"):
+                keep[k.strip()] = v.strip()
+        return keep
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_reference(a):
@@ -162,7 +188,62 @@ def workload(a):
                         f"{a.prec} recon-{a.recon}, interior kernel" + (" + halo" if a.gpus > 1 else ""),
             "l2": "per-step working set 8G+2S per site > 126 MB L2 at 32^4, and the steps rotate through 4 (input, output) "
                   "spinor pairs so that outputs are written back to HBM; no explicit flush",
-            "grid": process_grid(a.gpus)}
+            "grid": list(a.grid) if a.grid else process_grid(a.gpus)}
+
+
+def halo_parity_check(grid, dist, prec, recon, Xl=(16, 16, 16, 16)):
+    """N > 1: before anything is timed, apply the partitioned operator (the very call the timed loop makes: pack, NVLink
+    remote writes, interior, boundary -- one fused launch per Dslash) to seeded oracle-order fields and compare every
+    rank's block with the oracle on the GLOBAL lattice (the reference's dslash_ctest criterion, tests/dslash_ctest.cpp:
+    107-122).  Returns (max deviation over ranks, tolerance).  The oracle is the checker here, never what is measured."""
+    import numpy as np
+    import torch
+    import oracle
+    from common import CudaMem
+    from quda_b200 import comm, dirac as DR, dslash as D, fields as F
+    Xl = [int(v) for v in Xl]
+    Xg = [Xl[d] * grid.dims[d] for d in range(4)]
+    hp = 8 if prec == 8 else 4
+    gauge = oracle.random_gauge(Xg, hp, seed=137)  # the same global fields on every rank (same seeds)
+    parity, kappa = 1, 0.12195
+    s = oracle.random_spinor(Xg, hp, seed=5)
+    xs = oracle.random_spinor(Xg, hp, seed=6)
+    gl = comm.local_slice(gauge, Xg, Xl, grid.coords, "gauge")
+    ghost_from = []
+    for d in range(4):
+        c = list(grid.coords)
+        c[d] = (c[d] - 1) % grid.dims[d]
+        ghost_from.append(comm.local_slice(gauge, Xg, Xl, c, "gauge") if grid.dims[d] > 1 else None)
+    gbuf, gmeta = F.gauge_to_native(gl, Xl, prec, recon, ghost_from=ghost_from)
+    U = D.GaugeField(CudaMem.put(gbuf), Xl, prec, recon, gmeta, t_boundary=-1, first_time_slice=grid.first_time_slice(),
+                     last_time_slice=grid.last_time_slice())
+    sl = comm.local_slice(s, Xg, Xl, grid.coords, ("spinor1", 1 - parity))
+    xl = comm.local_slice(xs, Xg, Xl, grid.coords, ("spinor1", parity))
+    din = D.ColorSpinorField(CudaMem.put(F.spinor_to_native(sl, prec)), Xl, prec)
+    dx = D.ColorSpinorField(CudaMem.put(F.spinor_to_native(xl, prec)), Xl, prec)
+    out = D.ColorSpinorField(CudaMem.empty(F.spinor_bytes(Xl, prec)), Xl, prec)
+    ex = comm.HaloExchange(grid, Xl, prec, mode="p2p", dist=dist)
+    cs = ex.comm_struct()
+    op = DR.Dirac("wilson", U, 0.0, comm=cs, stream=torch.cuda.current_stream().cuda_stream)
+    dev = 0.0
+    for dagger in (0, 1):
+        for _ in range(3):  # repeated applications exercise the double-buffered ghost zones
+            op.DslashXpay(out, din, parity, dx, -kappa, dagger=bool(dagger))
+        torch.cuda.synchronize()
+        ref = xs.astype(np.float64) - kappa * oracle.wil_dslash(gauge, s, Xg, parity, dagger).astype(np.float64)
+        got = F.spinor_from_native(CudaMem.get(out.buf), F.volume_cb(Xl), prec)
+        want = comm.local_slice(ref, Xg, Xl, grid.coords, ("spinor1", parity))
+        dev = max(dev, float(oracle.compare_spinor(want, got)[1]))
+    import ctypes as C
+    from quda_b200 import lib as L_
+    L_.check(L_.load().b200_comm_check(C.byref(cs), None))
+    t = torch.tensor([dev], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del op
+    return float(t.item()), float(oracle.tolerance(PREC_NAME_BY_BYTES[prec], recon))
+
+
+PREC_NAME_BY_BYTES = {8: "double", 4: "single", 2: "half"}
 
 
 def process_grid(n):
@@ -207,7 +288,9 @@ def run_b200(a):
     grid = ex = None
     if world > 1:
         from quda_b200 import comm
-        grid = comm.ProcessGrid(comm.ProcessGrid.default_dims(world), rank)
+        dims = list(a.grid) if a.grid else comm.ProcessGrid.default_dims(world)
+        assert dims[0] * dims[1] * dims[2] * dims[3] == world, f"--grid {dims} does not have {world} ranks"
+        grid = comm.ProcessGrid(dims, rank)
     P = make_device_problem(X, prec, a.recon, grid)
     src, dst = P["in"], P["out"]
     stream = torch.cuda.current_stream().cuda_stream
@@ -222,6 +305,17 @@ def run_b200(a):
                 print(f"[bench] CUDA-IPC halo unavailable ({e}); falling back to NCCL send/recv", file=sys.stderr)
             ex = comm.HaloExchange(grid, X, prec, mode="nccl", dist=dist)
             halo_mode = "nccl-sendrecv"
+
+    halo_parity = None
+    if ex is not None and halo_mode.startswith("p2p") and not a.no_halo_check:
+        dev, tol = halo_parity_check(grid, dist, prec, a.recon)
+        halo_parity = {"parity_dev": dev, "tolerance": tol, "local_lattice": "16x16x16x16", "reference": "CPU oracle on the global lattice",
+                       "ok": bool(dev <= tol)}
+        if dev > tol:
+            if rank == 0:
+                print(json.dumps({"error": "partitioned Dslash differs from the global oracle", "halo": halo_parity}))
+            dist.destroy_process_group()
+            sys.exit(3)
 
     dirac = None
     if ex is not None and halo_mode.startswith("p2p"):
@@ -289,13 +383,18 @@ def run_b200(a):
         # the timed region above lasts only K x ~55 us, far below nvidia-smi's sampling period: keep the identical
         # kernel running for ~1.5 s more so that the clock / throttle record covers this very workload, and report
         # its (power-capped) steady-state step time next to the K-step figure
-        n_s = 0
-        t_s = time.perf_counter()
+        # (the number of extra steps is derived from the timed region, NOT from each rank's wall clock: on a partitioned
+        # lattice every rank must make exactly the same number of Dslash calls or its neighbours wait for faces forever)
+        ms_probe = ev0.elapsed_time(ev1) / a.steps
+        if world > 1:
+            tp = torch.tensor([ms_probe], device="cuda")
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            ms_probe = float(tp.item())
+        n_s = max(100, int(1500.0 / max(ms_probe, 1e-3)) // 100 * 100)
         es0.record()
-        while time.perf_counter() - t_s < 1.5:
+        for _ in range(n_s // 100):
             for _ in range(100):
                 step()
-            n_s += 100
             torch.cuda.synchronize()
         es1.record()
         barrier()
@@ -324,13 +423,14 @@ def run_b200(a):
            "sustained": {"ms_per_step": sustained_ms, "steps": n_s, "value": flops / (sustained_ms * 1e-3) * 1e-9,
                          "note": "same kernel looped for ~1.5 s after the timed steps (power-capped steady state)"},
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": ncu_traffic(a), "peak_source": peak_src,
+                        "traffic": ncu_traffic(a) if world == 1 else None,
+                        "traffic_source": "committed ncu capture of this kernel at N=1 (profiles/traffic.json), MB per launch" if world == 1 else None,
+                        "peak_source": peak_src,
                         "kernel": "dslash_interior_kernel", "algorithmic_bytes_per_launch": bmin * Vh},
            "clocks": cs.summary()}
-    if world > 1 and a.breakdown:
-        from quda_b200 import lib as LL
-        if dirac is not None:
-            ex.seq = comm_cs.seq
+    if world > 1:
+        # where the step time goes: the same GPU running the unpartitioned kernel on its local lattice (what N = 1 times),
+        # and the pack role alone (face gather + NVLink remote writes + flag protocol)
         def timed(fn, n=50):
             for _ in range(5):
                 fn()
@@ -344,18 +444,18 @@ def run_b200(a):
             t = torch.tensor([e0.elapsed_time(e1) / n * 1e3], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
-        halo_now = comm._RawHalo(ex.halo())
         out["breakdown_us"] = {
-            "pack_and_send": timed(lambda: ex.start(src, 1, 0, stream=stream)),
-            "interior": timed(lambda: D._apply(LL.OP_WILSON, dst, src, P["U"], 0.0, None, 0, 0, None, halo=comm._RawHalo(ex.halo()),
-                                               kernel=LL.KERNEL_INTERIOR, stream=stream, tile=a.tile)),
-            "exterior": timed(lambda: D._apply(LL.OP_WILSON, dst, src, P["U"], 0.0, None, 0, 0, None, halo=comm._RawHalo(ex.halo()),
-                                               kernel=LL.KERNEL_EXTERIOR, stream=stream, tile=a.tile)),
+            "step": ms * 1e3,
+            "unpartitioned_kernel_same_gpus": timed(lambda: D.ApplyWilson(pairs[0][1], pairs[0][0], P["U"], 0.0, None, 0, 0, stream=stream, tile=a.tile)),
+            "pack_and_send_alone": timed(lambda: ex.start(pairs[0][0], 1, 0, stream=stream)) if halo_mode.startswith("p2p") else None,
         }
     if world > 1:
         out["halo"] = {"mode": halo_mode, "grid": grid.dims, "bytes_per_step_per_gpu": int(sum(
             2 * ex.face_bytes[d] for d in range(4) if ex.comm_dim[d])), "timed_out": bool(ex.timed_out()) if halo_mode.startswith("p2p") else False}
         out["halo"]["gbs_per_gpu"] = out["halo"]["bytes_per_step_per_gpu"] / (ms * 1e-3) * 1e-9
+        out["halo"]["schedule"] = "one fused launch per Dslash: pack CTAs (NVLink remote write + arrival flags) | interior CTAs | boundary CTAs"
+        if halo_parity is not None:
+            out["halo"].update(halo_parity)
 
     if nsrc > 1:
         out["config"]["workload"] += f", {nsrc} sources per call (multi-RHS)"
@@ -367,11 +467,27 @@ def run_b200(a):
             out["multi_rhs"] = multi_rhs_line(a, P, D, L, stream, prec, Vh, peak)
         except Exception as e:  # noqa: BLE001  -- the single-source line above stands on its own
             out["multi_rhs"] = {"error": str(e)}
+    if world == 1 and a.op == "wilson" and nsrc == 1 and not a.no_extra and a.prec == "single" and a.recon == 12:
+        # the other precisions / BASELINE config 3 on the same box, so that they are driver-visible numbers too
+        out["other_configs"] = []
+        for pname, rc, opname in (("double", 18, "wilson"), ("half", 12, "wilson"), ("half", 8, "clover_pc"), ("half", 8, "clover_pc_static")):
+            try:
+                out["other_configs"].append(sub_line(a, pname, rc, opname, stream, peak))
+            except Exception as e:  # noqa: BLE001
+                out["other_configs"].append({"prec": pname, "recon": rc, "op": opname, "error": str(e)})
     if a.op != "wilson":
         out["metric"] = "wilson_clover_pc_dslash_gflops"
         out["config"]["workload"] = out["config"]["workload"].replace("Wilson Dslash", "Wilson-clover preconditioned Dslash (A^-1 D, compressed clover, per-site Cholesky)")
-    if rank == 0 and not a.no_e2e and a.op == "wilson":
-        out["e2e"] = e2e(a, P, lib, Vh, prec, world)
+    if not a.no_e2e and a.op == "wilson" and (world == 1 or dirac is not None):
+        # N > 1: every rank runs the pipeline on its own block through the partitioned operator (halo exchange inside,
+        # all ranks' PCIe copies in flight together); the time is the max over ranks
+        mk = None
+        if world > 1:
+            from quda_b200 import dirac as DR2
+            mk = lambda st: DR2.Dirac("wilson", P["U"], 0.0, comm=comm_cs, stream=st)  # noqa: E731
+        res = e2e(a, P, lib, Vh, prec, world, make_dirac=mk, dist=dist if world > 1 else None)
+        if rank == 0:
+            out["e2e"] = res
     if rank == 0 and not a.no_cpu_baseline:
         try:
             _, info = cpu_reference(X, a.prec, budget_s=15.0)
@@ -382,6 +498,50 @@ def run_b200(a):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sub_line(a, pname, recon, opname, stream, peak, steps=100):
+    """one more (precision, reconstruct, operator) on the same lattice: device-timed steps over 3 rotating (in, out) pairs"""
+    import torch
+    from quda_b200 import dslash as D
+    from quda_b200 import fields as F
+    from quda_b200 import lib as L
+    prec = PREC_BYTES[pname]
+    X = a.dim
+    Vh = F.volume_cb(X)
+    P = make_device_problem(X, prec, recon)
+    # clover_pc: compressed clover (56 reals / site) with the per-site Cholesky solve in the kernel (QUDA_DYNAMIC_CLOVER);
+    # clover_pc_static: the reference's default build -- A^-1 stored uncompressed (72 reals / site), applied by a 6x6 mat-vec
+    A = None
+    if opname == "clover_pc":
+        A = make_device_clover(X, prec)
+    elif opname == "clover_pc_static":
+        A = make_device_clover(X, prec, static_inverse=True)
+    pairs = [(P["in"], P["out"])] + [(new_spinor(P, seed=601 + i), new_spinor(P, seed=None)) for i in range(2)]
+
+    def step(i):
+        src, dst = pairs[i % 3]
+        if A is not None:
+            D.ApplyWilsonCloverPreconditioned(dst, src, P["U"], A, 0.0, None, 0, 0, stream=stream)
+        else:
+            D.ApplyWilson(dst, src, P["U"], 0.0, None, 0, 0, stream=stream)
+
+    for i in range(6):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    cb = (72 if opname == "clover_pc_static" else 56) * prec if A is not None else 0
+    bmin = D.min_bytes_per_site(prec, recon, clover_bytes=cb)
+    flops = D.flops_per_site(L.OP_CLOVER_PC if A is not None else L.OP_WILSON) * Vh
+    ach = bmin * Vh / (ms * 1e-3) * 1e-9
+    return {"prec": pname, "recon": recon, "op": opname, "ms_per_step": ms, "value": flops / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s",
+            "algorithmic_bytes_per_launch": bmin * Vh, "hbm_gbs_effective": ach, "frac": ach / peak, "steps": steps}
 
 
 def mrhs_flavour(prec, recon):
@@ -674,9 +834,10 @@ def make_device_problem(X, prec, recon, grid=None):
     return {"U": U, "in": inp, "out": out, "host_in": sbuf}
 
 
-def make_device_clover(X, prec):
+def make_device_clover(X, prec, static_inverse=False):
     """Synthetic clover term in the native compressed layout: 1 + small Hermitian noise with the symmetry the 28-real
-    format assumes (the construction of tests/utils/host_utils.cpp:1162-1188 with numpy's generator)."""
+    format assumes (the construction of tests/utils/host_utils.cpp:1162-1188 with numpy's generator).
+    static_inverse: an uncompressed field applied as a stored A^-1 (synthetic values: timing only)."""
     import numpy as np
     import torch
     from quda_b200 import dslash as D
@@ -687,11 +848,11 @@ def make_device_clover(X, prec):
     for dst, src in zip((3, 4, 5, 30, 31, 32, 33, 34, 35), (0, 1, 2, 6, 7, 8, 9, 16, 17)):
         c[:, :, dst] = -c[:, :, src]
     c[:, :, :6] += 1.0
-    buf, meta = F.clover_to_native(c, X, prec, compressed=True)
-    return D.CloverField(torch.from_numpy(buf).cuda(), X, prec, meta, dynamic=True)
+    buf, meta = F.clover_to_native(c, X, prec, compressed=not static_inverse)
+    return D.CloverField(torch.from_numpy(buf).cuda(), X, prec, meta, dynamic=not static_inverse)
 
 
-def e2e(a, P, lib, Vh, prec, world):
+def e2e(a, P, lib, Vh, prec, world, make_dirac=None, dist=None):
     """Same metric through the public calls with HOST spinor buffers (pinned, host interface order): every step copies
     its input spinor host->device, converts it to the native order (b200_copy_spinor), applies the Dslash, converts the
     result back and copies it device->host -- the dslashQuda flow (lib/interface_quda.cpp:1709-1783).  Steps are software-pipelined over three
@@ -711,6 +872,7 @@ def e2e(a, P, lib, Vh, prec, world):
     d_in = [D.ColorSpinorField(torch.empty(nat_bytes, dtype=torch.uint8, device="cuda"), X, prec) for _ in range(2)]
     d_out = [D.ColorSpinorField(torch.empty(nat_bytes, dtype=torch.uint8, device="cuda"), X, prec) for _ in range(2)]
     s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    op = make_dirac(s_k.cuda_stream) if make_dirac is not None else None  # partitioned operator bound to the kernel stream
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_k = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
@@ -726,7 +888,10 @@ def e2e(a, P, lib, Vh, prec, world):
                 s_k.wait_event(ev_in[b])
                 s_k.wait_event(ev_out[b])      # s_hout[b] free once its previous content went to the host
                 D.copy_spinor(d_in[b], s_hin[b], True, stream=s_k.cuda_stream)      # host order -> native (UKQCD)
-                D.ApplyWilson(d_out[b], d_in[b], P["U"], 0.0, None, 0, 0, tile=a.tile, stream=s_k.cuda_stream)
+                if op is not None:
+                    op.Dslash(d_out[b], d_in[b], 0)
+                else:
+                    D.ApplyWilson(d_out[b], d_in[b], P["U"], 0.0, None, 0, 0, tile=a.tile, stream=s_k.cuda_stream)
                 D.copy_spinor(d_out[b], s_hout[b], False, stream=s_k.cuda_stream)   # native -> host order
                 ev_k[b].record(s_k)
             with torch.cuda.stream(s_out):
@@ -736,6 +901,8 @@ def e2e(a, P, lib, Vh, prec, world):
 
     run(4)
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     n = max(6, min(a.steps, 60))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(s_in)
@@ -744,8 +911,13 @@ def e2e(a, P, lib, Vh, prec, world):
     ev1.record(s_out)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / n
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     return {"value": D.flops_per_site() * Vh * world / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": ms,
-            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": n,
+            "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": n,
+            "ranks_measured": world,
             "note": "host spinor in/out in the interface order (fp32 [site][spin][colour][2], DeGrand-Rossi, pinned); per "
                     "step: H2D, reorder+basis rotation kernel, Dslash, reorder kernel, D2H; 3-stream pipeline; gauge "
                     "resident as after loadGaugeQuda"}

@@ -178,6 +178,15 @@ typedef struct {
 } b200_pack_args;
 int b200_pack_ghost(const b200_pack_args *args);
 
+/* The whole partitioned Dslash -- what ApplyWilson* does on a partitioned lattice through its policy
+ * (lib/dslash_wilson.hpp:18-54 -> lib/dslash_policy.hpp:1471-1650: pack, exchange, interior, exterior) -- as ONE kernel
+ * launch on args->stream: pack CTAs write the faces of `in` into the neighbours' ghost slabs and raise their arrival
+ * flags, interior CTAs update every site that touches no partitioned face meanwhile, boundary CTAs acquire the
+ * neighbours' flags and update the face sites completely.  `pack` must describe the faces of args->in (parity
+ * 1 - args->parity, same dagger / precision / lattice / partitioning, pack->seq == args->halo.seq); args->kernel must be
+ * B200_KERNEL_AUTO, fields single parity.  Without partitioned dimensions it is b200_dslash_apply(args). */
+int b200_dslash_apply_fused(const b200_dslash_args *args, const b200_pack_args *pack);
+
 /* bytes of one face buffer holding BOTH parities (what b200_halo.ghost[d][dir] must point to), and of one parity */
 size_t b200_ghost_face_bytes(int precision, const int X[4], int dim);
 

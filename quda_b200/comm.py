@@ -105,10 +105,11 @@ class HaloExchange:
     """Ghost buffers + neighbour wiring for one (lattice, precision, site-subset).  Owns its buffers (allocated once,
     like the reference's static ghost buffers, lib/lattice_field.cpp:274-303)."""
 
-    def __init__(self, grid, X, prec, n_parity=1, mode="p2p", backend=None, dist=None):
+    def __init__(self, grid, X, prec, n_parity=1, mode="p2p", backend=None, dist=None, self_dims=None):
         self.grid, self.X, self.prec, self.n_parity, self.mode = grid, [int(v) for v in X], prec, n_parity, mode
         self.backend, self.dist = backend, dist
-        self.comm_dim = grid.comm_dim() if mode != "self" else [1, 1, 1, 1]
+        # "self": a single rank that is its own neighbour in the dimensions of `self_dims` (default: all four)
+        self.comm_dim = grid.comm_dim() if mode != "self" else [int(bool(v)) for v in (self_dims or (1, 1, 1, 1))]
         self._comm_struct = None
         self._seq = 0
         self.face_bytes = [n_parity * F.ghost_parity_bytes(X, prec, d) for d in range(4)]

@@ -84,7 +84,6 @@ int b200_dslash_apply(const b200_dslash_args *a)
   bool nothing_to_do = false;
   if (int rc = make_request(rq, a, nothing_to_do)) return rc;
   if (nothing_to_do) return B200_SUCCESS;
-  if (const char *e = getenv("B200_MARCH_T")) rq.march_t = atoi(e); // experimental: time-marching CTAs (kernels.cuh)
   tma_knobs(rq);
   if (rq.tma && rq.kernel == B200_KERNEL_AUTO && a->precision != B200_HALF) {
     // TMA-staged marching kernel (tma_kernel.cuh) for the shapes it serves; anything else falls through
@@ -303,12 +302,10 @@ int b200_comm_copy(void *dst, const void *src, size_t bytes)
   return check_cuda(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault), "cudaMemcpy");
 }
 
-int b200_pack_ghost(const b200_pack_args *a)
+static int make_pack_request(PackRequest &rq, const b200_pack_args *a)
 {
   if (!a || !a->in.v) return set_error(B200_ERR_INVALID, "null argument");
   if (a->abi_version != B200_ABI_VERSION) return set_error(B200_ERR_INVALID, "ABI version mismatch");
-  if (int rc = require_device()) return rc;
-  PackRequest rq;
   memcpy(rq.X, a->X, sizeof(rq.X));
   rq.parity = a->parity;
   rq.dagger = a->dagger ? 1 : 0;
@@ -326,10 +323,47 @@ int b200_pack_ghost(const b200_pack_args *a)
   rq.block_counter = a->block_counter;
   rq.seq = a->seq;
   rq.stream = a->stream;
+  return 0;
+}
+
+int b200_pack_ghost(const b200_pack_args *a)
+{
+  PackRequest rq;
+  if (int rc = make_pack_request(rq, a)) return rc;
+  if (int rc = require_device()) return rc;
   switch (a->precision) {
   case B200_DOUBLE: return launch_pack_precision<PrecF64>(rq);
   case B200_SINGLE: return launch_pack_precision<PrecF32>(rq);
   case B200_HALF: return launch_pack_precision<PrecH16>(rq);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
+}
+
+int b200_dslash_apply_fused(const b200_dslash_args *a, const b200_pack_args *p)
+{
+  if (int rc = require_device()) return rc;
+  LaunchRequest rq;
+  bool nothing_to_do = false;
+  if (int rc = make_request(rq, a, nothing_to_do)) return rc;
+  PackRequest pk;
+  if (int rc = make_pack_request(pk, p)) return rc;
+  if (a->kernel != B200_KERNEL_AUTO) return set_error(B200_ERR_INVALID, "the fused Dslash is the B200_KERNEL_AUTO schedule");
+  if (p->in.v != a->in.v || p->precision != a->precision || p->parity != 1 - a->parity || (p->dagger != 0) != (a->dagger != 0))
+    return set_error(B200_ERR_INVALID, "pack arguments do not describe the faces of this Dslash's input");
+  if (a->out.n_parity != 1) return set_error(B200_ERR_INVALID, "the fused Dslash works on single-parity fields");
+  bool any = false;
+  for (int d = 0; d < 4; d++) {
+    if ((p->comm_dim[d] != 0) != (a->halo.comm_dim[d] != 0)) return set_error(B200_ERR_INVALID, "pack / halo partitioning differ in dimension %d", d);
+    if (p->X[d] != a->X[d]) return set_error(B200_ERR_INVALID, "pack / Dslash lattice extents differ");
+    any |= a->halo.comm_dim[d] != 0;
+  }
+  if (!any) return b200_dslash_apply(a); // nothing partitioned: the plain launch
+  if (a->halo.seq != p->seq) return set_error(B200_ERR_INVALID, "pack and halo carry different sequence numbers");
+  rq.fused_pack = &pk;
+  switch (a->precision) {
+  case B200_DOUBLE: return launch_precision<PrecF64>(rq);
+  case B200_SINGLE: return launch_precision<PrecF32>(rq);
+  case B200_HALF: return launch_precision<PrecH16>(rq);
   }
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
 }

@@ -104,22 +104,6 @@ namespace b200
     return tile_thread_site(x, x_cb, g, tm, parity, tm.org[0] + b0, tm.org[1] + b1, tm.org[2] + b2, tm.org[3] + b3, tid);
   }
 
-  // marching launch (launch.h::march_grid): the CTA's (x,y,z) tile and the first time slice of its chunk
-  B2_HD void march_tile(int &b0, int &b1, int &b2, int &t0, int &parity, const TileMap &tm, int n_parity, int arg_parity,
-                        int n_chunks, int march, unsigned bx, unsigned by, unsigned bz)
-  {
-    b1 = tm.cnt[0] == 1 ? (int)bx : (int)mulhi_u32(bx, tm.cnt0_magic);
-    b0 = (int)bx - b1 * tm.cnt[0];
-    b2 = (int)by;
-    int k = (int)bz;
-    parity = arg_parity;
-    if (n_parity == 2) {
-      parity = k >= n_chunks ? 1 : 0;
-      k -= parity * n_chunks;
-    }
-    t0 = k * march;
-  }
-
   // slab launch: grid = (total CTAs of all slabs, n_parity)
   B2_HD bool slab_site(int *x, int &x_cb, const Geom &g, const TileMap &tm, const SlabTable &st, int parity, unsigned bx,
                        unsigned tid)

@@ -145,13 +145,12 @@ namespace b200
       h.timeout_flag = comm->timeout_flag;
     }
 
-    // ship the faces of `in` (single-parity field holding parity `in_parity`) to the neighbours
-    static void exchange_start(const ColorSpinorField &in, int in_parity, bool dagger, const int *comm_override,
-                               CommContext *comm, void *stream)
+    // describe the faces of `in` (single-parity field holding parity `in_parity`) and where they go; advances the exchange
+    static void pack_args_for(b200_pack_args &a, const ColorSpinorField &in, int in_parity, bool dagger, const int *comm_override,
+                              CommContext *comm)
     {
       const unsigned seq = ++comm->seq();
       const int b = seq & 1;
-      b200_pack_args a;
       memset(&a, 0, sizeof(a));
       a.abi_version = B200_ABI_VERSION;
       a.precision = in.precision;
@@ -168,6 +167,14 @@ namespace b200
       a.in = in.desc();
       a.block_counter = comm->block_counter;
       a.seq = seq;
+    }
+
+    // two-stream schedule: ship the faces on the side stream
+    static void exchange_start(const ColorSpinorField &in, int in_parity, bool dagger, const int *comm_override,
+                               CommContext *comm, void *stream)
+    {
+      b200_pack_args a;
+      pack_args_for(a, in, in_parity, dagger, comm_override, comm);
       if (comm->pack_stream && comm->pack_stream != stream) {
         // fork: the pack kernel runs on its own stream, concurrently with the interior tiles (joined in apply())
         StreamEvents &ev = events_of(comm);
@@ -178,6 +185,18 @@ namespace b200
         a.stream = stream;
       }
       abi_ok(b200_pack_ghost(&a));
+    }
+
+    // B200_HALO_SCHEDULE=streams selects the round-1 schedule (pack + boundary tiles on a side stream, interior tiles on
+    // the main stream); the default is the single fused launch
+    static bool fused_schedule()
+    {
+      static int v = -1;
+      if (v < 0) {
+        const char *e = getenv("B200_HALO_SCHEDULE");
+        v = (e && strcmp(e, "streams") == 0) ? 0 : 1;
+      }
+      return v == 1;
     }
 
     // `b`, `asymmetric`: twisted mass only; with_x: 1 / 0 force x on / off (the twisted-mass preconditioned operator's
@@ -209,10 +228,18 @@ namespace b200
       bool part = false;
       if (comm)
         for (int d = 0; d < 4; d++) part |= (comm->comm_dim[d] && (!comm_override || comm_override[d]));
-      if (part) {
-        if (in.n_parity != 1) throw Error("a partitioned Dslash works on one parity at a time");
-        exchange_start(in, 1 - parity, dagger, comm_override, comm, stream);
+      if (part && in.n_parity != 1) throw Error("a partitioned Dslash works on one parity at a time");
+      if (part && fused_schedule()) {
+        // pack + interior + boundary: one launch on the operator's stream
+        b200_pack_args pk;
+        pack_args_for(pk, in, 1 - parity, dagger, comm_override, comm);
+        pk.stream = stream;
+        halo_fill(args.halo, comm_override, comm);
+        args.stream = stream;
+        abi_ok(b200_dslash_apply_fused(&args, &pk));
+        return;
       }
+      if (part) exchange_start(in, 1 - parity, dagger, comm_override, comm, stream);
       halo_fill(args.halo, comm_override, part ? comm : nullptr);
       const bool two_streams = part && comm->pack_stream && comm->pack_stream != stream;
       if (two_streams) {

@@ -85,26 +85,6 @@ namespace b200
     dslash_site_interior<P, recon, dagger, xpay, op, part>(arg, x, x_cb, parity);
   }
 
-  // Marching variant (experimental, B200_MARCH_T): a CTA keeps its (x,y,z) tile and walks `march` consecutive time
-  // slices.  The stencil is bound by the SM <- L2 crossbar (~32 B/clk/SM): 8 neighbour loads per
-  // site, of which L1 catches only ~25 % when every CTA sees its tile once.  Walking in t lets the slices t-1 and t
-  // (loaded one and two steps ago by the SAME SM) be served from L1 instead of crossing the crossbar again.
-  template <class P, int recon, bool dagger, bool xpay, OpType op>
-  __global__ void __launch_bounds__(kMaxTile, MinBlocks<P>::value)
-    dslash_march_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TileMap tm, int n_chunks,
-                        int march)
-  {
-    int b0, b1, b2, t0, parity;
-    march_tile(b0, b1, b2, t0, parity, tm, arg.n_parity, arg.parity, n_chunks, march, blockIdx.x, blockIdx.y, blockIdx.z);
-    for (int dt = 0; dt < march; dt++) {
-      const int t = t0 + dt;
-      if (t >= arg.geom.X[3]) break;
-      int x[4], x_cb;
-      if (!tile_thread_site(x, x_cb, arg.geom, tm, parity, tm.org[0] + b0, tm.org[1] + b1, tm.org[2] + b2, t, threadIdx.x)) break;
-      dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, parity);
-    }
-  }
-
   // ---- system-scope flag helpers for the NVLink remote-write halo path (used by the kernels below)
   __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
   {
@@ -210,16 +190,13 @@ namespace b200
     int dagger;
   };
 
-  // grid: x = blocks over the largest face, y = face id (2*d + face)
-  template <class P> __global__ void __launch_bounds__(128) pack_kernel(const __grid_constant__ PackArgs<P> arg)
+  // one CTA of the pack: sites [blk * blockDim.x, ...) of face `face_id` = 2*d + face; `nblk` CTAs work on this face
+  template <class P> __device__ __forceinline__ void pack_block(const PackArgs<P> &arg, int face_id, int blk, int nblk)
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
-    const int d = blockIdx.y >> 1, face = blockIdx.y & 1;
-    if (!arg.comm_dim[d]) return;
-    const int nblk = (g.face_cb[d] + blockDim.x - 1) / blockDim.x;
-    if ((int)blockIdx.x >= nblk) return;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = face_id >> 1, face = face_id & 1;
+    const int idx = blk * blockDim.x + threadIdx.x;
     if (idx < g.face_cb[d]) {
       int x[4];
       coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, arg.parity);
@@ -242,14 +219,78 @@ namespace b200
       __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0) {
-        const int prev = atomicAdd(arg.counter + blockIdx.y, 1);
+        const int prev = atomicAdd(arg.counter + face_id, 1);
         if (prev == nblk - 1) {
-          arg.counter[blockIdx.y] = 0;
+          arg.counter[face_id] = 0;
           __threadfence_system();
           st_release_sys(sig, arg.seq);
         }
       }
     }
+  }
+
+  // grid: x = blocks over the largest face, y = face id (2*d + face)
+  template <class P> __global__ void __launch_bounds__(128) pack_kernel(const __grid_constant__ PackArgs<P> arg)
+  {
+    const int d = blockIdx.y >> 1;
+    if (!arg.comm_dim[d]) return;
+    const int nblk = (arg.geom.face_cb[d] + blockDim.x - 1) / blockDim.x;
+    if ((int)blockIdx.x >= nblk) return;
+    pack_block(arg, blockIdx.y, blockIdx.x, nblk);
+  }
+
+  // ------------------------------------------------------------------ ONE launch per partitioned Dslash
+  // The reference overlaps halo and interior with a policy of several kernels on several streams plus host-side event
+  // plumbing (lib/dslash_policy.hpp:1471-1650; pack CTAs folded into the interior launch: include/dslash_helper.cuh:664-713).
+  // Here the whole partitioned Dslash is one grid whose block index selects the role:
+  //   [0, n_pack)                 pack CTAs: spin-project the face sites and write them straight into the neighbours'
+  //                               ghost slabs over NVLink; the last CTA of a face raises the arrival flag there
+  //   [n_pack, n_pack + n_int)    interior CTAs: the branch-free stencil on every site that touches no partitioned face
+  //                               (threads of face sites retire at once) -- independent of the halo
+  //   the rest                    boundary CTAs: one thread per face site (corner sites owned by the highest partitioned
+  //                               dimension), acquire the neighbours' flags, then update the site completely
+  // Blocks are dispatched in index order, so the faces leave first, the interior streams while they fly, and the boundary
+  // CTAs only occupy SM slots at the tail.  No second stream, no events, no exterior read-modify-write pass.
+  struct FusedShape {
+    int n_pack, n_interior;
+    int pack_start[9]; // prefix sums of the pack CTAs per face id
+    int gx, gy;        // interior tile grid (gz implied)
+  };
+
+  template <class P, int recon, bool dagger, bool xpay, OpType op>
+  __global__ void __launch_bounds__(kMaxTile, MinBlocks<P>::value)
+    dslash_fused_kernel(const __grid_constant__ DslashArgs<P, recon> arg, const __grid_constant__ TileMap tm,
+                        const __grid_constant__ PackArgs<P> pk, const __grid_constant__ FusedShape fs)
+  {
+    int b = blockIdx.x;
+    if (b < fs.n_pack) {
+      int f = 0;
+#pragma unroll
+      for (int k = 1; k < 8; k++)
+        if (b >= fs.pack_start[k]) f = k;
+      pack_block(pk, f, b - fs.pack_start[f], fs.pack_start[f + 1] - fs.pack_start[f]);
+      return;
+    }
+    b -= fs.n_pack;
+    if (b < fs.n_interior) {
+      const int per_z = fs.gx * fs.gy;
+      const int bz = b / per_z;
+      const int r = b - bz * per_z;
+      const int by = r / fs.gx;
+      const int bx = r - by * fs.gx;
+      int x[4], x_cb, parity;
+      if (!tile_site(x, x_cb, parity, arg.geom, tm, arg.n_parity, arg.parity, bx, by, bz, threadIdx.x)) return;
+      if (!site_is_interior(arg, x)) return;
+      dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, parity);
+      return;
+    }
+    b -= fs.n_interior;
+    wait_for_halo(arg);
+    const int tid = b * blockDim.x + threadIdx.x;
+    if (tid >= arg.threads_ext[4]) return;
+    int x[4], x_cb;
+    if (!exterior_thread_site(x, x_cb, arg, tid, arg.parity)) return;
+    dslash_site_full<P, recon, dagger, xpay, op>(arg, x, x_cb, arg.parity);
   }
 
   // Host interface order <-> native order, with the DeGrand-Rossi <-> UKQCD rotation
@@ -457,6 +498,24 @@ namespace b200
     return check_cuda(cudaGetLastError(), "copy_clover launch");
   }
 
+  template <class P> int fill_pack_args(PackArgs<P> &arg, const PackRequest &rq)
+  {
+    geom_init(arg.geom, rq.X);
+    fill_spinor(arg.in, rq.in, rq.in_norm, arg.geom.volume_cb);
+    arg.parity = rq.parity;
+    arg.dagger = rq.dagger;
+    arg.counter = rq.block_counter;
+    arg.seq = rq.seq;
+    for (int d = 0; d < 4; d++) {
+      arg.comm_dim[d] = rq.comm_dim[d] ? 1 : 0;
+      for (int dir = 0; dir < 2; dir++) {
+        fill_ghost(arg.dst[d][dir], rq.dst[d][dir], rq.dst_norm[d][dir], arg.geom.face_cb[d]);
+        arg.signal[d][dir] = arg.comm_dim[d] ? reinterpret_cast<unsigned *>(rq.signal[d][dir]) : nullptr;
+      }
+    }
+    return 0;
+  }
+
   // ------------------------------------------------------------------ host-side dispatch for one precision
   template <class P, int recon, bool dagger, bool xpay, OpType op>
   int launch_config(const LaunchRequest &rq, const DslashArgs<P, recon> &arg)
@@ -469,6 +528,28 @@ namespace b200
     const bool tiles_path
       = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES;
     if (tiles_path && !partitioned && rq.kernel == B200_KERNEL_BOUNDARY_TILES) return B200_SUCCESS;
+    if (partitioned && rq.fused_pack && rq.kernel == B200_KERNEL_AUTO && arg.n_parity == 1) {
+      // pack + interior + boundary in ONE launch (dslash_fused_kernel)
+      PackArgs<P> pk;
+      if (int e = fill_pack_args(pk, *rq.fused_pack)) return e;
+      if (!rq.fused_pack->block_counter) return set_error(B200_ERR_INVALID, "fused Dslash needs the pack block_counter scratch");
+      FusedShape fs;
+      fs.pack_start[0] = 0;
+      for (int f = 0; f < 8; f++) {
+        const int d = f >> 1;
+        const int nblk = pk.comm_dim[d] ? (arg.geom.face_cb[d] + threads - 1) / threads : 0;
+        fs.pack_start[f + 1] = fs.pack_start[f] + nblk;
+      }
+      fs.n_pack = fs.pack_start[8];
+      if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+      fs.gx = gx;
+      fs.gy = gy;
+      fs.n_interior = gx * gy * gz;
+      const int n_boundary = (arg.threads_ext[4] + threads - 1) / threads;
+      dslash_fused_kernel<P, recon, dagger, xpay, op><<<fs.n_pack + fs.n_interior + n_boundary, threads, 0, s>>>(arg, tm, pk, fs);
+      count_launch();
+      return check_cuda(cudaGetLastError(), "fused dslash launch");
+    }
     if (tiles_path && partitioned) {
       // B200 schedule: tiles that touch no partitioned face run now (branch-free kernel, overlapping the halo that is
       // in flight over NVLink); the boundary tiles follow in ONE launch that acquires the arrival flags and updates
@@ -487,14 +568,6 @@ namespace b200
         dslash_boundary_kernel<P, recon, dagger, xpay, op><<<dim3(nb, arg.n_parity, 1), threads, 0, s>>>(arg, tm, st);
         count_launch();
       }
-      return check_cuda(cudaGetLastError(), "dslash launch");
-    }
-    if (rq.march_t > 0 && !partitioned && tiles_path && tm.sh[3] == 0) {
-      int n_chunks;
-      if (!march_grid(tm, arg.n_parity, arg.geom.X[3], rq.march_t, gx, gy, gz, n_chunks, rc))
-        return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
-      dslash_march_kernel<P, recon, dagger, xpay, op><<<dim3(gx, gy, gz), threads, 0, s>>>(arg, tm, n_chunks, rq.march_t);
-      count_launch();
       return check_cuda(cudaGetLastError(), "dslash launch");
     }
     if (rq.kernel != B200_KERNEL_EXTERIOR) { // AUTO / INTERIOR_TILES on an unpartitioned lattice, or reference-style INTERIOR
@@ -591,22 +664,12 @@ namespace b200
   template <class P> int launch_pack_precision(const PackRequest &rq)
   {
     PackArgs<P> arg;
-    geom_init(arg.geom, rq.X);
-    fill_spinor(arg.in, rq.in, rq.in_norm, arg.geom.volume_cb);
-    arg.parity = rq.parity;
-    arg.dagger = rq.dagger;
-    arg.counter = rq.block_counter;
-    arg.seq = rq.seq;
+    if (int e = fill_pack_args(arg, rq)) return e;
     int max_face = 0;
     bool any_signal = false;
     for (int d = 0; d < 4; d++) {
-      arg.comm_dim[d] = rq.comm_dim[d] ? 1 : 0;
       if (arg.comm_dim[d] && arg.geom.face_cb[d] > max_face) max_face = arg.geom.face_cb[d];
-      for (int dir = 0; dir < 2; dir++) {
-        fill_ghost(arg.dst[d][dir], rq.dst[d][dir], rq.dst_norm[d][dir], arg.geom.face_cb[d]);
-        arg.signal[d][dir] = arg.comm_dim[d] ? reinterpret_cast<unsigned *>(rq.signal[d][dir]) : nullptr;
-        any_signal |= (arg.signal[d][dir] != nullptr);
-      }
+      for (int dir = 0; dir < 2; dir++) any_signal |= (arg.signal[d][dir] != nullptr);
     }
     if (max_face == 0) return 0;
     if (any_signal && !arg.counter) return set_error(B200_ERR_INVALID, "signal[] given without block_counter scratch");

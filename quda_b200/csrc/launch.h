@@ -20,7 +20,6 @@ namespace b200
     int X[4], tile[4];
     double b;       // twisted mass: twist factor as passed by the caller (the dagger sign flip happens in fill_args)
     int asymmetric; // twisted-mass preconditioned: asymmetric variant
-    int march_t; // > 0: every CTA walks `march_t` consecutive time slices with its (x,y,z) tile (L1 reuse of the slices)
     int tma;     // 1: unpartitioned single-source requests go to the TMA-staged marching kernel when it serves the shape
     int tma_ty, tma_tz, tma_grid; // tuning overrides of that kernel (0: built-in choice)
     int tma_link_slots;           // 0: links through shared memory, as many stages as fit; >= 2: that many; -1: register stream
@@ -33,6 +32,7 @@ namespace b200
     b200_clover A;
     b200_halo halo;
     void *stream;
+    const struct PackRequest *fused_pack; // non-null: pack + interior + boundary in one launch (dslash_fused_kernel)
   };
 
   // multi-RHS: `base` carries everything but the spinors (its out/in/x mirror source 0 for validation)
@@ -339,7 +339,7 @@ namespace b200
     } else {
       default_tile(rq.tile, a->precision, a->X);
     }
-    rq.march_t = 0;
+    rq.fused_pack = nullptr;
     rq.tma = 0;
     rq.tma_ty = rq.tma_tz = rq.tma_grid = rq.tma_link_slots = rq.tma_center_slots = rq.tma_halo_slots = rq.tma_prefetch = rq.tma_l2_prefetch = 0;
     rq.out = a->out;
@@ -435,16 +435,6 @@ namespace b200
     gx = tm.cnt[0] * tm.cnt[1];
     gy = tm.cnt[2];
     gz = tm.cnt[3] * n_parity;
-    return true;
-  }
-
-  // Marching launch: the tile map must have t-extent 1; the CTA of (x,y,z)-tile column c and chunk k updates the slices
-  // t = k*march .. k*march + march - 1 one after the other.  grid = (cnt0*cnt1, cnt2, n_chunks * n_parity)
-  inline bool march_grid(TileMap &tm, int n_parity, int X3, int march, int &gx, int &gy, int &gz, int &n_chunks, int &rc)
-  {
-    if (!box_grid(tm, n_parity, gx, gy, gz, rc)) return false;
-    n_chunks = (X3 + march - 1) / march;
-    gz = n_chunks * n_parity;
     return true;
   }
 

@@ -99,7 +99,9 @@ class Halo:
 
 
 def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=None, kernel=L.KERNEL_AUTO, tile=None,
-           stream=None, backend=None, b=0.0, asymmetric=False):
+           stream=None, backend=None, b=0.0, asymmetric=False, fused_dst=None):
+    """`fused_dst` ([4][2] send targets as for PackGhost): run pack + interior + boundary as ONE launch
+    (b200_dslash_apply_fused) instead of a separate PackGhost call followed by the Dslash."""
     be = backend or cuda_backend()
     multi = isinstance(out, (list, tuple))  # the reference's cvector_ref batch: sources sharing U (and A)
     if multi:
@@ -132,6 +134,19 @@ def _apply(op, out, in_, U, a, x, parity, dagger, comm_override, A=None, halo=No
         i = (L.Spinor * n)(*[f.desc() for f in ins])
         xa = (L.Spinor * n)(*[f.desc() for f in xs]) if xs else None
         be.call("dslash_apply_multi", C.byref(args), n, o, i, xa)
+    elif fused_dst is not None:
+        p = L.PackArgs()
+        p.abi_version, p.precision = L.ABI_VERSION, in_.prec
+        for d in range(4):
+            p.X[d] = in_.X[d]
+            p.comm_dim[d] = args.halo.comm_dim[d]
+            for f in range(2):
+                p.dst[d][f] = _ptr(fused_dst[d][f]) if p.comm_dim[d] else None
+        p.parity, p.dagger = 1 - args.parity, args.dagger
+        p.in_ = in_.desc()
+        p.seq = args.halo.seq
+        p.stream = stream
+        be.call("dslash_apply_fused", C.byref(args), C.byref(p))
     else:
         be.call("dslash_apply", C.byref(args))
 

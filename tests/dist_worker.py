@@ -16,6 +16,9 @@ def worker(rank, world, port, grid_dims, Xl, prec, recon, q, mode="host", reps=3
     os.environ["OMP_NUM_THREADS"] = "2"
     import torch
     import torch.distributed as dist
+    fused = mode == "p2p-fused"  # the C++ operator layer's schedule: pack + interior + boundary as ONE launch per Dslash
+    if fused:
+        mode = "p2p"
     if mode == "host":
         dist.init_process_group("gloo", rank=rank, world_size=world)
     else:
@@ -50,8 +53,15 @@ def worker(rank, world, port, grid_dims, Xl, prec, recon, q, mode="host", reps=3
     dx = D.ColorSpinorField(mem.put(F.spinor_to_native(xl, prec)), Xl, prec)
     out = D.ColorSpinorField(mem.empty(F.spinor_bytes(Xl, prec)), Xl, prec)
     ex = comm.HaloExchange(grid, Xl, prec, mode=mode, backend=be, dist=dist)
-    for _ in range(reps):  # repeated applications exercise the double-buffered ghost zones
-        comm.apply_wilson_distributed(ex, out, din, U, -kappa, dx, parity, dagger)
+    if fused:
+        from quda_b200 import dirac as DR
+        cs = ex.comm_struct()
+        op = DR.Dirac("wilson", U, 0.0, comm=cs)
+        for _ in range(reps):
+            op.DslashXpay(out, din, parity, dx, -kappa, dagger=bool(dagger))
+    else:
+        for _ in range(reps):  # repeated applications exercise the double-buffered ghost zones
+            comm.apply_wilson_distributed(ex, out, din, U, -kappa, dx, parity, dagger)
     mem.sync()
     got = F.spinor_from_native(mem.get(out.buf), F.volume_cb(Xl), prec)
     want = comm.local_slice(ref, Xg, Xl, grid.coords, ("spinor1", parity))

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../quda_b200/csrc/launch.h"
 #include "tma_emu.h"
@@ -54,6 +55,34 @@ namespace b200
     };
     const bool tiles_path
       = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES;
+    if (partitioned && rq.fused_pack && rq.kernel == B200_KERNEL_AUTO && arg.n_parity == 1) {
+      // kernels.cuh::dslash_fused_kernel: (the pack role ran in twin_dslash_apply_fused) interior role over every tile with
+      // the face sites retiring, boundary role over the face-site enumeration
+      if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+      walk_box([&](const int *x, int x_cb, int par) {
+        if (site_is_interior(arg, x)) dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par);
+      });
+      long done = 0;
+      std::vector<char> seen(g.volume_cb, 0);
+      for (int tid = 0; tid < arg.threads_ext[4]; tid++) {
+        int x[4], x_cb;
+        if (!exterior_thread_site(x, x_cb, arg, tid, arg.parity)) continue;
+        if (seen[x_cb]++) return set_error(B200_ERR_INVALID, "fused boundary role visits site %d twice", x_cb);
+        if (site_is_interior(arg, x)) return set_error(B200_ERR_INVALID, "fused boundary role visits interior site %d", x_cb);
+        dslash_site_full<P, recon, dagger, xpay, op>(arg, x, x_cb, arg.parity);
+        done++;
+      }
+      // every face site exactly once: interior + boundary = all sites
+      long interior = 0;
+      for (int x_cb = 0; x_cb < g.volume_cb; x_cb++) {
+        int x[4];
+        coords_from_cb(x, g, x_cb, arg.parity);
+        if (site_is_interior(arg, x)) interior++;
+      }
+      if (interior + done != (long)g.volume_cb)
+        return set_error(B200_ERR_INVALID, "fused roles cover %ld interior + %ld boundary of %d sites", interior, done, g.volume_cb);
+      return 0;
+    }
     if (tiles_path && partitioned) {
       SlabTable st;
       const int nb = split_boundary(tm, st, arg.comm_dim);
@@ -78,29 +107,6 @@ namespace b200
       if (rq.kernel == B200_KERNEL_AUTO && visited != (long)g.volume_cb * arg.n_parity)
         return set_error(B200_ERR_INVALID, "interior box + boundary slabs visited %ld of %ld sites", visited,
                          (long)g.volume_cb * arg.n_parity);
-      return 0;
-    }
-    if (rq.march_t > 0 && !partitioned && tiles_path && tm.sh[3] == 0) { // kernels.cuh::dslash_march_kernel
-      int n_chunks;
-      if (!march_grid(tm, arg.n_parity, g.X[3], rq.march_t, gx, gy, gz, n_chunks, rc)) return rc ? rc : -1;
-#pragma omp parallel for collapse(2) reduction(+ : visited)
-      for (int bz = 0; bz < gz; bz++)
-        for (int by = 0; by < gy; by++)
-          for (int bx = 0; bx < gx; bx++)
-            for (int tid = 0; tid < threads; tid++) {
-              int b0, b1, b2, t0, par;
-              march_tile(b0, b1, b2, t0, par, tm, arg.n_parity, arg.parity, n_chunks, rq.march_t, bx, by, bz);
-              for (int dt = 0; dt < rq.march_t; dt++) {
-                const int t = t0 + dt;
-                if (t >= g.X[3]) break;
-                int x[4], x_cb;
-                if (!tile_thread_site(x, x_cb, g, tm, par, tm.org[0] + b0, tm.org[1] + b1, tm.org[2] + b2, t, tid)) break;
-                dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par);
-                visited++;
-              }
-            }
-      if (visited != (long)g.volume_cb * arg.n_parity)
-        return set_error(B200_ERR_INVALID, "marching grid visited %ld of %ld sites", visited, (long)g.volume_cb * arg.n_parity);
       return 0;
     }
     if (rq.kernel != B200_KERNEL_EXTERIOR) {
@@ -348,7 +354,6 @@ int twin_dslash_apply(const b200_dslash_args *a)
   bool nothing = false;
   if (int rc = make_request(rq, a, nothing)) return rc;
   if (nothing) return 0;
-  if (const char *e = getenv("B200_MARCH_T")) rq.march_t = atoi(e);
   if (const char *e = getenv("B200_TMA")) rq.tma = atoi(e); // (read on every call: tests toggle it)
   if (const char *e = getenv("B200_TMA_TILE")) sscanf(e, "%d %d", &rq.tma_ty, &rq.tma_tz);
   if (const char *e = getenv("B200_TMA_GRID")) rq.tma_grid = atoi(e);
@@ -356,6 +361,35 @@ int twin_dslash_apply(const b200_dslash_args *a)
   if (const char *e = getenv("B200_TMA_PREFETCH")) rq.tma_prefetch = atoi(e);
   if (const char *e = getenv("B200_TMA_L2PF")) rq.tma_l2_prefetch = atoi(e);
   if (const char *e = getenv("B200_TMA_RINGS")) sscanf(e, "%d %d", &rq.tma_center_slots, &rq.tma_halo_slots);
+  switch (a->precision) {
+  case B200_DOUBLE: return run_precision<PrecF64>(rq);
+  case B200_SINGLE: return run_precision<PrecF32>(rq);
+  case B200_HALF: return run_precision<PrecH16>(rq);
+  }
+  return -1;
+}
+
+int twin_pack_ghost(const b200_pack_args *a);
+
+int twin_dslash_apply_fused(const b200_dslash_args *a, const b200_pack_args *p)
+{
+  // same argument checks as capi.cu::b200_dslash_apply_fused
+  if (!a || !p) return set_error(B200_ERR_INVALID, "null argument");
+  if (a->kernel != B200_KERNEL_AUTO) return set_error(B200_ERR_INVALID, "the fused Dslash is the B200_KERNEL_AUTO schedule");
+  if (p->in.v != a->in.v || p->precision != a->precision || p->parity != 1 - a->parity || (p->dagger != 0) != (a->dagger != 0))
+    return set_error(B200_ERR_INVALID, "pack arguments do not describe the faces of this Dslash's input");
+  bool any = false;
+  for (int d = 0; d < 4; d++) {
+    if ((p->comm_dim[d] != 0) != (a->halo.comm_dim[d] != 0)) return set_error(B200_ERR_INVALID, "pack / halo partitioning differ");
+    any |= a->halo.comm_dim[d] != 0;
+  }
+  if (!any) return twin_dslash_apply(a);
+  if (int rc = twin_pack_ghost(p)) return rc; // the pack role (sequential emulation: all faces land before anybody waits)
+  LaunchRequest rq;
+  bool nothing = false;
+  if (int rc = make_request(rq, a, nothing)) return rc;
+  PackRequest marker {};
+  rq.fused_pack = &marker;
   switch (a->precision) {
   case B200_DOUBLE: return run_precision<PrecF64>(rq);
   case B200_SINGLE: return run_precision<PrecF32>(rq);

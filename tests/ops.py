@@ -221,16 +221,21 @@ def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4
     for parity in (0, 1):
         halo = self_halo(P, mem, comm_dim)
         din = P.to_dev(s)
-        self_exchange(P, halo, din, 1 - parity, dagger, be)
+        fused_kw = {}
+        if split == "fused":  # pack + interior + boundary in one call (b200_dslash_apply_fused); host twin only: without
+            # arrival flags the real kernel's boundary CTAs would not wait for its pack CTAs
+            fused_kw = dict(fused_dst=[[halo.ghost[d][1], halo.ghost[d][0]] if comm_dim[d] else [None, None] for d in range(4)])
+        else:
+            self_exchange(P, halo, din, 1 - parity, dagger, be)
         out = P.empty()
         a = -kappa if xpay else 0.0
         xdev = P.to_dev(xs) if xpay else None
         if split == "tiles":      # the two halves of AUTO issued separately (boundary first: they are independent)
             kws = [dict(kernel=4, tile=tile), dict(kernel=3, tile=tile)]
-        elif split:               # reference-style: masked INTERIOR then EXTERIOR read-modify-write
+        elif split and split != "fused":  # reference-style: masked INTERIOR then EXTERIOR read-modify-write
             kws = [dict(kernel=1, tile=tile), dict(kernel=2, tile=tile)]
         else:
-            kws = [dict(tile=tile)]
+            kws = [dict(tile=tile, **fused_kw)]
         if op == "wilson":
             for kw in kws:
                 D.ApplyWilson(out, din, P.U, a, xdev, parity, dagger, halo=halo, backend=be, **kw)

@@ -28,7 +28,7 @@ def _run(world, grid_dims, Xl, prec, recon, mode):
         assert dev <= tol, (rank, dev)
 
 
-@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+@pytest.mark.parametrize("mode", ["p2p-fused", "p2p", "nccl"])
 @pytest.mark.parametrize("grid_dims,Xl", [((1, 1, 1, 2), (8, 8, 8, 8)), ((2, 1, 1, 1), (4, 8, 8, 8)), ((1, 1, 2, 1), (8, 8, 4, 8))])
 @pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (2, 8)])
 def test_two_gpus_match_global_oracle(grid_dims, Xl, prec, recon, mode):
@@ -37,12 +37,15 @@ def test_two_gpus_match_global_oracle(grid_dims, Xl, prec, recon, mode):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs >= 4 GPUs")
 def test_four_gpus_two_partitioned_dims():
-    _run(4, (1, 1, 2, 2), (8, 8, 4, 4), 4, 12, "p2p")
+    _run(4, (1, 1, 2, 2), (8, 8, 4, 4), 4, 12, "p2p-fused")
+    _run(4, (2, 2, 1, 1), (8, 8, 8, 8), 8, 18, "p2p-fused")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 8, reason="needs 8 GPUs")
 def test_eight_gpus_three_partitioned_dims():
     """the 8-GPU benchmark grid (1,2,2,2): y, z and t partitioned, every rank has 3 distinct NVLink peers"""
+    _run(8, (1, 2, 2, 2), (8, 8, 8, 8), 4, 12, "p2p-fused")
+    _run(8, (2, 2, 2, 1), (8, 8, 8, 8), 8, 18, "p2p-fused")
     _run(8, (1, 2, 2, 2), (4, 4, 4, 4), 4, 12, "p2p")
 
 

@@ -153,14 +153,3 @@ def test_device_side_clover_marshaling(prec, compressed):
     out = P.empty()
     D.ApplyClover(out, P.to_dev(s), A, False, 1)
     assert_close(oracle.apply_clover(c, s.astype(c.dtype), X, 1), P.to_host(out), prec, 12, "A x on device-marshaled clover")
-
-
-@pytest.mark.skipif(not os.environ.get("B200_EXPERIMENTAL"), reason="experimental launch shape, enable with B200_EXPERIMENTAL=1")
-@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (2, 8)])
-@pytest.mark.parametrize("march", [3, 8])
-def test_time_marching_launch(monkeypatch, prec, recon, march):
-    """B200_MARCH_T: CTAs walk `march` consecutive time slices with their (x,y,z) tile (L1 reuse of the slices);
-    results must equal the plain launch (checked against the oracle)"""
-    import ops
-    monkeypatch.setenv("B200_MARCH_T", str(march))
-    ops.check_xpay_fullfield(CudaMem, None, prec, recon, X=(8, 4, 4, 6))

@@ -154,3 +154,18 @@ def test_twisted_mass_argument_checks():
     h = ops.self_halo(P, HostMem, (0, 0, 0, 1))
     with pytest.raises(B200Error, match="pack kernel"):
         D.ApplyTwistedMassPreconditioned(out, s, P.U, 1.0, 0.1, False, None, 0, 1, False, halo=h, backend=be)
+
+
+@pytest.mark.parametrize("comm_dim", MASKS)
+def test_fused_single_launch_all_masks(comm_dim):
+    """b200_dslash_apply_fused (pack + interior + boundary as one launch): the interior role (every tile, face sites
+    retire) and the boundary role (one thread per face site, corners owned by the highest partitioned dimension) must
+    cover every site exactly once and reproduce the periodic operator for all 15 partition masks"""
+    ops.check_partitioned(HostMem, twin_backend(), 8, 18, comm_dim, X=(4, 6, 4, 8), split="fused")
+
+
+@pytest.mark.parametrize("prec,recon", [(4, 12), (2, 8)])
+@pytest.mark.parametrize("op", ["wilson", "clover_pc"])
+def test_fused_single_launch_ops(prec, recon, op):
+    ops.check_partitioned(HostMem, twin_backend(), prec, recon, (1, 0, 1, 1), op=op, xpay=(op == "wilson"), dagger=1, split="fused",
+                          X=(8, 4, 4, 6))

@@ -44,17 +44,6 @@ def test_launch_tilings_cover_the_lattice(tile):
     assert_close(ref, P.to_host(out2), 4, 12, f"full-field tile {tile}")
 
 
-@pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (2, 8)])
-@pytest.mark.parametrize("march", [1, 3, 8])
-def test_time_marching_launch(monkeypatch, prec, recon, march):
-    """B200_MARCH_T (experimental launch shape: CTAs walk `march` time slices with their (x,y,z) tile): every site must
-    be visited exactly once (the twin checks the count) and results must not change; X3 = 6 is ragged for march 8 and
-    exact for 3"""
-    import ops
-    monkeypatch.setenv("B200_MARCH_T", str(march))
-    ops.check_xpay_fullfield(HostMem, twin_backend(), prec, recon, X=(4, 4, 4, 6))
-
-
 @pytest.mark.parametrize("X", [(2, 2, 2, 2), (2, 4, 2, 6), (4, 2, 2, 2), (16, 2, 4, 2)])
 @pytest.mark.parametrize("prec,recon", [(8, 12), (4, 8), (2, 18)])
 def test_degenerate_extents(X, prec, recon):
