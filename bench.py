@@ -22,8 +22,13 @@ import time
 
 # The CPU arm (reference Dslash on the host cores) is an OpenMP code: pin its threads to cores, one per place, before any
 # OpenMP runtime is loaded -- unpinned it swung 5x between otherwise identical boxes.
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "threads")
+# ONLY in a process that runs the CPU arm: under torchrun (N > 1) every rank is its own process with OMP_NUM_THREADS=1, and
+# a bound single thread lands on place 0 -- all ranks' host threads would share ONE core and the launch rate collapses
+# (measured: 2-GPU steps went from 56 to 110 us with the binding on; profiles/r02_scale2_pinned_ranks.json).
+_CPU_ARM = ("--impl" in sys.argv and "reference" in sys.argv) or int(os.environ.get("WORLD_SIZE", "1")) == 1
+if _CPU_ARM and int(os.environ.get("RANK", "0")) == 0:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "threads")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

@@ -54,7 +54,10 @@ typedef enum {
   B200_KERNEL_EXTERIOR = 2, /* fused exterior kernel only (adds ghost hops to the partial result in `out`)      */
   /* the two halves of B200_KERNEL_AUTO on a partitioned lattice, for callers that put them on different streams:  */
   B200_KERNEL_INTERIOR_TILES = 3, /* tiles that touch no partitioned face (independent of the halo)               */
-  B200_KERNEL_BOUNDARY_TILES = 4  /* boundary tiles: waits for the arrival flags, then complete site updates      */
+  B200_KERNEL_BOUNDARY_TILES = 4, /* boundary tiles: waits for the arrival flags, then complete site updates      */
+  /* the same split with 1-site-thick shells instead of whole boundary tiles (roles of the fused kernel without its pack role): */
+  B200_KERNEL_INTERIOR_SITES = 5, /* every site that touches no partitioned face (independent of the halo)         */
+  B200_KERNEL_BOUNDARY_SITES = 6  /* the face sites: waits for the arrival counters, then complete site updates    */
 } b200_kernel;
 
 /* One ColorSpinorField in native order.  n_parity == 1: a single-parity field (QUDA_PARITY_SITE_SUBSET);
@@ -100,12 +103,13 @@ typedef struct {
   int comm_dim[4];
   void *ghost[4][2];
   void *ghost_norm[4][2]; /* half precision only; NULL -> directly after the 12*face_cb shorts of each parity block */
-  /* Arrival flags (optional).  If wait_flag[d][dir] is non-NULL the exterior kernel spins until the 32-bit word it
-   * points to (in THIS GPU's memory, written by the neighbour's pack kernel over NVLink) has reached `seq`
-   * before it reads ghost[d][dir].  NULL: arrival is guaranteed by stream order (copy-engine / NCCL path). */
+  /* Arrival flags (optional).  If wait_flag[d][dir] is non-NULL the boundary / exterior kernel spins until the 32-bit
+   * site counter it points to (in THIS GPU's memory, advanced by the neighbour's pack CTAs over NVLink, see
+   * b200_pack_args.signal) shows that exchange `seq` has landed: count >= ((seq + (seq & 1)) / 2) * face_cb[d], before it
+   * reads ghost[d][dir].  NULL: arrival is guaranteed by stream order (copy-engine / NCCL path). */
   void *wait_flag[4][2];
   unsigned seq;
-  int *timeout_flag; /* device word set to 1 if a wait gave up after ~2 s (never hangs the GPU); may be NULL */
+  int *timeout_flag; /* device word set to 1 if a wait gave up after ~10 s (never hangs the GPU); may be NULL */
 } b200_halo;
 
 typedef struct {
@@ -168,9 +172,12 @@ typedef struct {
                            [d][1]: where our x[d]==X[d]-1 face goes (the forward neighbour's ghost[d][0] slot) */
   void *dst_norm[4][2]; /* half precision */
   /* Remote-write completion signalling (QUDA_P2P_REMOTE_WRITE without MPI in the critical path, cf.
-   * lib/dslash_policy.hpp:1682-1687, include/shmem_pack_helper.cuh:60-190): once every store of face (d,f) has
-   * been made visible system-wide, the 32-bit word signal[d][f] (in the RECEIVER's memory) is set to `seq`.
-   * `block_counter` is an 8-int zero-initialised scratch array in local device memory. */
+   * lib/dslash_policy.hpp:1682-1687, include/shmem_pack_helper.cuh:60-190): signal[d][f] is a 32-bit word in the
+   * RECEIVER's memory that COUNTS the face sites that have landed in that ghost buffer since the exchange was set up
+   * (per pack CTA: barrier, one system fence, a local ticket; the last CTA of the face stores the new total).  The buffer
+   * pair is used alternately (buffer seq & 1), so exchange `seq` has arrived once the count reaches
+   * ((seq + (seq & 1)) / 2) * face_cb.  `block_counter` is an 8-int zero-initialised scratch array in local device memory
+   * (the tickets). */
   void *signal[4][2];
   int *block_counter;
   unsigned seq;
@@ -183,8 +190,11 @@ int b200_pack_ghost(const b200_pack_args *args);
  * launch on args->stream: pack CTAs write the faces of `in` into the neighbours' ghost slabs and raise their arrival
  * flags, interior CTAs update every site that touches no partitioned face meanwhile, boundary CTAs acquire the
  * neighbours' flags and update the face sites completely.  `pack` must describe the faces of args->in (parity
- * 1 - args->parity, same dagger / precision / lattice / partitioning, pack->seq == args->halo.seq); args->kernel must be
- * B200_KERNEL_AUTO, fields single parity.  Without partitioned dimensions it is b200_dslash_apply(args). */
+ * 1 - args->parity, same dagger / precision / lattice / partitioning, pack->seq == args->halo.seq); fields single parity.
+ * args->kernel selects the roles of the launch: B200_KERNEL_AUTO all three; B200_KERNEL_INTERIOR_TILES the interior role
+ * alone (independent of the halo) and B200_KERNEL_BOUNDARY_TILES pack + boundary, for callers that put the two halves on
+ * different streams (the default schedule of this library's own operator layer: pack + boundary on a high-priority side
+ * stream).  Without partitioned dimensions it is b200_dslash_apply(args). */
 int b200_dslash_apply_fused(const b200_dslash_args *args, const b200_pack_args *pack);
 
 /* bytes of one face buffer holding BOTH parities (what b200_halo.ghost[d][dir] must point to), and of one parity */

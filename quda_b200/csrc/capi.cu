@@ -347,7 +347,8 @@ int b200_dslash_apply_fused(const b200_dslash_args *a, const b200_pack_args *p)
   if (int rc = make_request(rq, a, nothing_to_do)) return rc;
   PackRequest pk;
   if (int rc = make_pack_request(pk, p)) return rc;
-  if (a->kernel != B200_KERNEL_AUTO) return set_error(B200_ERR_INVALID, "the fused Dslash is the B200_KERNEL_AUTO schedule");
+  if (a->kernel != B200_KERNEL_AUTO && a->kernel != B200_KERNEL_INTERIOR_TILES && a->kernel != B200_KERNEL_BOUNDARY_TILES)
+    return set_error(B200_ERR_INVALID, "fused Dslash: kernel must be AUTO (all roles), INTERIOR_TILES (interior role) or BOUNDARY_TILES (pack + boundary roles)");
   if (p->in.v != a->in.v || p->precision != a->precision || p->parity != 1 - a->parity || (p->dagger != 0) != (a->dagger != 0))
     return set_error(B200_ERR_INVALID, "pack arguments do not describe the faces of this Dslash's input");
   if (a->out.n_parity != 1) return set_error(B200_ERR_INVALID, "the fused Dslash works on single-parity fields");
@@ -357,7 +358,7 @@ int b200_dslash_apply_fused(const b200_dslash_args *a, const b200_pack_args *p)
     if (p->X[d] != a->X[d]) return set_error(B200_ERR_INVALID, "pack / Dslash lattice extents differ");
     any |= a->halo.comm_dim[d] != 0;
   }
-  if (!any) return b200_dslash_apply(a); // nothing partitioned: the plain launch
+  if (!any) return a->kernel == B200_KERNEL_BOUNDARY_TILES ? B200_SUCCESS : b200_dslash_apply(a); // nothing partitioned: the plain launch
   if (a->halo.seq != p->seq) return set_error(B200_ERR_INVALID, "pack and halo carry different sequence numbers");
   rq.fused_pack = &pk;
   switch (a->precision) {

@@ -58,7 +58,12 @@ namespace b200
     if constexpr (sizeof(V) == 16) {
       uint4 r;
       if constexpr (c == Cache::COHERENT) {
-        asm volatile("ld.relaxed.sys.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+        // weak coherent load: ordered after the flag acquire (thread 0, system scope) + CTA barrier by causality order;
+        // L1::no_allocate so that no line of a ghost slab is ever kept in the (non-coherent) L1
+#ifndef B2_GHOST_LD
+#define B2_GHOST_LD "ld.global.L1::no_allocate"
+#endif
+        asm volatile(B2_GHOST_LD ".v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                      : "l"(p)
                      : "memory");
@@ -81,7 +86,7 @@ namespace b200
     } else if constexpr (sizeof(V) == 8) {
       uint2 r;
       if constexpr (c == Cache::COHERENT)
-        asm volatile("ld.relaxed.sys.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+        asm volatile(B2_GHOST_LD ".v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
       else if constexpr (c == Cache::STREAM)
         asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
       else
@@ -90,7 +95,7 @@ namespace b200
     } else {
       unsigned r;
       if constexpr (c == Cache::COHERENT)
-        asm volatile("ld.relaxed.sys.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+        asm volatile(B2_GHOST_LD ".u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
       else
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
       return *reinterpret_cast<V *>(&r);

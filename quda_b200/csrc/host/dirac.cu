@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <cuda_runtime.h>
 
 #include "dirac.h"
@@ -107,6 +108,7 @@ namespace b200
           stream(stream_), f(pool().get(stream_, like.X, like.precision, n_parity))
         {
         }
+        Scratch(void *stream_, const int *X, int precision, int n_parity) : stream(stream_), f(pool().get(stream_, X, precision, n_parity)) { }
         ~Scratch() { pool().put(stream, f); }
         operator ColorSpinorField &() { return f; }
       };
@@ -187,16 +189,30 @@ namespace b200
       abi_ok(b200_pack_ghost(&a));
     }
 
-    // B200_HALO_SCHEDULE=streams selects the round-1 schedule (pack + boundary tiles on a side stream, interior tiles on
-    // the main stream); the default is the single fused launch
-    static bool fused_schedule()
+    // How a partitioned Dslash is issued (B200_HALO_SCHEDULE):
+    //   split  two launches of dslash_fused_kernel: [pack | boundary] on the high-priority side stream, [interior] on the
+    //          operator's stream, joined by an event (measured worst: the boundary CTAs spin from the start of the launch)
+    //   fused  ONE launch [pack | interior | boundary] on the operator's stream (no side stream, no events)
+    //   streams  the round-1 schedule: pack kernel + boundary-tile kernel on the side stream, interior tiles on the main one
+    //   sites  as streams, but with 1-site-thick shells: pack kernel, then the boundary-site role on the side stream, the
+    //          interior-site role on the main stream (18.75 % instead of 28 % of the sites take the branchy path at 8 GPUs)
+    enum HaloSchedule { SCHED_SPLIT = 0, SCHED_FUSED = 1, SCHED_STREAMS = 2, SCHED_SITES = 3 };
+#ifndef B2_SCHED_DEFAULT
+#define B2_SCHED_DEFAULT SCHED_STREAMS
+#endif
+    constexpr int SCHED_DEFAULT = B2_SCHED_DEFAULT;
+    static HaloSchedule halo_schedule()
     {
       static int v = -1;
       if (v < 0) {
         const char *e = getenv("B200_HALO_SCHEDULE");
-        v = (e && strcmp(e, "streams") == 0) ? 0 : 1;
+        v = SCHED_DEFAULT;
+        if (e && strcmp(e, "split") == 0) v = SCHED_SPLIT;
+        if (e && strcmp(e, "fused") == 0) v = SCHED_FUSED;
+        if (e && strcmp(e, "streams") == 0) v = SCHED_STREAMS;
+        if (e && strcmp(e, "sites") == 0) v = SCHED_SITES;
       }
-      return v == 1;
+      return (HaloSchedule)v;
     }
 
     // `b`, `asymmetric`: twisted mass only; with_x: 1 / 0 force x on / off (the twisted-mass preconditioned operator's
@@ -229,7 +245,8 @@ namespace b200
       if (comm)
         for (int d = 0; d < 4; d++) part |= (comm->comm_dim[d] && (!comm_override || comm_override[d]));
       if (part && in.n_parity != 1) throw Error("a partitioned Dslash works on one parity at a time");
-      if (part && fused_schedule()) {
+      const bool side_stream = part && comm->pack_stream && comm->pack_stream != stream;
+      if (part && (halo_schedule() == SCHED_FUSED || (halo_schedule() == SCHED_SPLIT && !side_stream))) {
         // pack + interior + boundary: one launch on the operator's stream
         b200_pack_args pk;
         pack_args_for(pk, in, 1 - parity, dagger, comm_override, comm);
@@ -239,16 +256,37 @@ namespace b200
         abi_ok(b200_dslash_apply_fused(&args, &pk));
         return;
       }
+      if (part && halo_schedule() == SCHED_SPLIT) {
+        // [pack | boundary] on the side stream (after `in` is complete), [interior] on the main stream, then join
+        b200_pack_args pk;
+        pack_args_for(pk, in, 1 - parity, dagger, comm_override, comm);
+        halo_fill(args.halo, comm_override, comm);
+        StreamEvents &ev = events_of(comm);
+        cuda_ok(cudaEventRecord(ev.fork, cs(stream)), "record");
+        cuda_ok(cudaStreamWaitEvent(cs(comm->pack_stream), ev.fork, 0), "wait");
+        pk.stream = comm->pack_stream;
+        args.stream = comm->pack_stream;
+        args.kernel = B200_KERNEL_BOUNDARY_TILES;
+        abi_ok(b200_dslash_apply_fused(&args, &pk));
+        pk.stream = stream;
+        args.stream = stream;
+        args.kernel = B200_KERNEL_INTERIOR_TILES;
+        abi_ok(b200_dslash_apply_fused(&args, &pk));
+        cuda_ok(cudaEventRecord(ev.join, cs(comm->pack_stream)), "record");
+        cuda_ok(cudaStreamWaitEvent(cs(stream), ev.join, 0), "wait");
+        return;
+      }
       if (part) exchange_start(in, 1 - parity, dagger, comm_override, comm, stream);
       halo_fill(args.halo, comm_override, part ? comm : nullptr);
       const bool two_streams = part && comm->pack_stream && comm->pack_stream != stream;
       if (two_streams) {
         // side stream (behind the pack kernel): boundary sites -- they depend only on the halo, not on the interior
         // launch; main stream: the interior.  Both halves write disjoint sites.
-        args.kernel = B200_KERNEL_BOUNDARY_TILES;
+        const bool shells = halo_schedule() == SCHED_SITES;
+        args.kernel = shells ? B200_KERNEL_BOUNDARY_SITES : B200_KERNEL_BOUNDARY_TILES;
         args.stream = comm->pack_stream;
         abi_ok(b200_dslash_apply(&args));
-        args.kernel = B200_KERNEL_INTERIOR_TILES;
+        args.kernel = shells ? B200_KERNEL_INTERIOR_SITES : B200_KERNEL_INTERIOR_TILES;
         args.stream = stream;
         abi_ok(b200_dslash_apply(&args));
         // join: `out` is complete, and `in` may be overwritten, only after the side stream has drained
@@ -954,15 +992,22 @@ namespace b200
       const bool host_ar = host_allreduce(ex);
       int syncs = 0;
 
-      auto r = ColorSpinorField::create(x.X, x.precision, x.n_parity);  // high-precision residual
-      auto y = ColorSpinorField::create(x.X, x.precision, x.n_parity);  // high-precision accumulated solution
-      auto tmp = ColorSpinorField::create(x.X, x.precision, x.n_parity);
+      // work fields come from the per-stream scratch pool: a second solve on the same stream allocates nothing
+      Scratch r_s(ex.stream, x.X, x.precision, x.n_parity), y_s(ex.stream, x.X, x.precision, x.n_parity),
+        tmp_s(ex.stream, x.X, x.precision, x.n_parity);
+      ColorSpinorField &r = r_s.f;     // high-precision residual
+      ColorSpinorField &y = y_s.f;     // high-precision accumulated solution
+      ColorSpinorField &tmp = tmp_s.f;
       const bool same_prec = sp == x.precision;
-      auto rS = same_prec ? r : ColorSpinorField::create(x.X, sp, x.n_parity);
-      auto xS = ColorSpinorField::create(x.X, sp, x.n_parity);
-      auto p = ColorSpinorField::create(x.X, sp, x.n_parity);
-      auto Ap = ColorSpinorField::create(x.X, sp, x.n_parity);
-      auto tS = same_prec ? tmp : ColorSpinorField::create(x.X, sp, x.n_parity); // sloppy-precision staging
+      Scratch xS_s(ex.stream, x.X, sp, x.n_parity), p_s(ex.stream, x.X, sp, x.n_parity), Ap_s(ex.stream, x.X, sp, x.n_parity);
+      std::unique_ptr<Scratch> rS_s, tS_s;
+      if (!same_prec) {
+        rS_s.reset(new Scratch(ex.stream, x.X, sp, x.n_parity));
+        tS_s.reset(new Scratch(ex.stream, x.X, sp, x.n_parity));
+      }
+      ColorSpinorField rS = same_prec ? r : rS_s->f;
+      ColorSpinorField &xS = xS_s.f, &p = p_s.f, &Ap = Ap_s.f;
+      ColorSpinorField tS = same_prec ? tmp : tS_s->f; // sloppy-precision staging
 
       const double b2 = norm2(b, ex);
       syncs++;

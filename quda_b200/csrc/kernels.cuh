@@ -3,6 +3,7 @@
 // so the three compile in parallel.
 #pragma once
 
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "dslash_site.h"
@@ -96,21 +97,29 @@ namespace b200
   {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
   }
+  __device__ __forceinline__ void red_release_sys_add(unsigned *p, unsigned v)
+  {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  }
 
-  // Block until every partitioned face has arrived (flag >= seq, wrap-safe).  One thread polls, the CTA follows.
+  // Block until every partitioned face of exchange `seq` has arrived.  A flag word counts the face sites its buffer has
+  // received since the exchange was created; buffer b = seq & 1 is used by every second exchange, so exchange `seq` is
+  // complete once the count reaches ((seq + b) / 2) * face_cb[d] (compared wrap-safe).  One thread polls, the CTA follows.
   // Gives up after ~10 s of SM clock so that a lost peer can never hang the GPU; the host layer checks (and clears)
   // timeout_flag at its synchronisation points and turns it into an error (b200_comm_check, b200_invert_cg).
   template <class Arg> __device__ __forceinline__ void wait_for_halo(const Arg &arg)
   {
     if (threadIdx.x == 0) {
       const long long t0 = clock64();
+      const unsigned uses = (arg.seq + (arg.seq & 1u)) >> 1;
 #pragma unroll
       for (int d = 0; d < 4; d++) {
 #pragma unroll
         for (int dir = 0; dir < 2; dir++) {
           const unsigned *f = arg.wait_flag[d][dir];
           if (!f) continue;
-          while ((int)(ld_acquire_sys(f) - arg.seq) < 0) {
+          const unsigned target = uses * (unsigned)arg.geom.face_cb[d];
+          while ((int)(ld_acquire_sys(f) - target) < 0) {
             if (clock64() - t0 > 20000000000LL) {
               if (arg.timeout_flag) *arg.timeout_flag = 1;
               break;
@@ -178,6 +187,9 @@ namespace b200
   // Face 0 (x[d] == 0) feeds the backward neighbour's forward hop, which uses P(d, dagger ? + : -);
   // face 1 (x[d] == X[d]-1) feeds the forward neighbour's backward hop, P(d, dagger ? - : +).
   // (reference: include/kernels/dslash_pack.cuh:134-200)
+#ifndef B2_PACK_REMOTE_ADD
+#define B2_PACK_REMOTE_ADD 0
+#endif
   template <class P> struct PackArgs {
     Geom geom;
     SpinorView<P> in;
@@ -214,17 +226,28 @@ namespace b200
     }
     unsigned *sig = arg.signal[d][face];
     if (sig) {
-      // make this thread's (possibly remote) stores visible system-wide, then count the CTA in; the last CTA of the
-      // face publishes the sequence number in the receiver's memory
-      __threadfence_system();
+      // Arrival protocol: the flag word in the RECEIVER's memory holds the number of face sites that have landed in this
+      // buffer since the exchange was created; exchange `seq` is complete at ((seq + (seq & 1)) / 2) * face_cb.
+      // Per CTA: barrier (orders every thread's possibly remote stores before thread 0), ONE system fence by thread 0, then
+      // a LOCAL ticket; the CTA that draws the last ticket publishes the new total with a single remote store.  (Round 1
+      // fenced in every thread -- MEMBAR.SYS was the hottest instruction of the fused launch, profiles/r02_fused_self_*; one
+      // remote release-add per CTA avoids the tickets but serialises 512 NVLink atomics on one address: 111 us per step at
+      // 2 GPUs, profiles/r02_scale2_remote_add.json.)
       __syncthreads();
       if (threadIdx.x == 0) {
+#if B2_PACK_REMOTE_ADD
+        const int left = g.face_cb[d] - blk * (int)blockDim.x;
+        red_release_sys_add(sig, (unsigned)(left < (int)blockDim.x ? left : (int)blockDim.x));
+#else
+        __threadfence_system();
         const int prev = atomicAdd(arg.counter + face_id, 1);
         if (prev == nblk - 1) {
           arg.counter[face_id] = 0;
           __threadfence_system();
-          st_release_sys(sig, arg.seq);
+          const unsigned uses = (arg.seq + (arg.seq & 1u)) >> 1;
+          st_release_sys(sig, uses * (unsigned)g.face_cb[d]);
         }
+#endif
       }
     }
   }
@@ -247,14 +270,17 @@ namespace b200
   //                               ghost slabs over NVLink; the last CTA of a face raises the arrival flag there
   //   [n_pack, n_pack + n_int)    interior CTAs: the branch-free stencil on every site that touches no partitioned face
   //                               (threads of face sites retire at once) -- independent of the halo
-  //   the rest                    boundary CTAs: one thread per face site (corner sites owned by the highest partitioned
-  //                               dimension), acquire the neighbours' flags, then update the site completely
-  // Blocks are dispatched in index order, so the faces leave first, the interior streams while they fly, and the boundary
-  // CTAs only occupy SM slots at the tail.  No second stream, no events, no exterior read-modify-write pass.
+  //   boundary CTAs               one thread per face site (corner sites owned by the highest partitioned dimension),
+  //                               acquire the neighbours' arrival counters, then update the site completely; they sit
+  //                               behind the first ~70 % of the interior CTAs (B200_FUSED_BOUNDARY_AT) and in front of the
+  //                               rest, so their wait + latency is covered by interior work instead of forming a tail
+  // Blocks are dispatched in index order, so the faces leave first and the interior streams while they fly.  No second
+  // stream, no events, no exterior read-modify-write pass.
   struct FusedShape {
-    int n_pack, n_interior;
-    int pack_start[9]; // prefix sums of the pack CTAs per face id
-    int gx, gy;        // interior tile grid (gz implied)
+    int n_pack, n_interior, n_boundary;
+    int n_interior_first; // interior CTAs dispatched before the boundary CTAs (the rest follow them)
+    int pack_start[9];    // prefix sums of the pack CTAs per face id
+    int gx, gy;           // interior tile grid (gz implied)
   };
 
   template <class P, int recon, bool dagger, bool xpay, OpType op>
@@ -272,10 +298,18 @@ namespace b200
       return;
     }
     b -= fs.n_pack;
-    if (b < fs.n_interior) {
+    // block order after the pack CTAs: [interior part 1 | boundary | interior part 2] -- the boundary CTAs start when most of
+    // the interior is already in flight (by then the neighbours' faces have landed) and their latency is covered by the rest
+    // of the interior instead of forming the tail of the launch
+    int ib = -1;
+    if (b < fs.n_interior_first)
+      ib = b;
+    else if (b >= fs.n_interior_first + fs.n_boundary)
+      ib = b - fs.n_boundary;
+    if (ib >= 0) {
       const int per_z = fs.gx * fs.gy;
-      const int bz = b / per_z;
-      const int r = b - bz * per_z;
+      const int bz = ib / per_z;
+      const int r = ib - bz * per_z;
       const int by = r / fs.gx;
       const int bx = r - by * fs.gx;
       int x[4], x_cb, parity;
@@ -284,7 +318,7 @@ namespace b200
       dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, parity);
       return;
     }
-    b -= fs.n_interior;
+    b -= fs.n_interior_first;
     wait_for_halo(arg);
     const int tid = b * blockDim.x + threadIdx.x;
     if (tid >= arg.threads_ext[4]) return;
@@ -525,10 +559,30 @@ namespace b200
     int threads, gx, gy, gz, rc;
     if (int e = make_tile_map(tm, threads, rq.tile, arg.geom, kMaxTile)) return e;
     const bool partitioned = arg.threads_ext[4] > 0;
-    const bool tiles_path
-      = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES;
-    if (tiles_path && !partitioned && rq.kernel == B200_KERNEL_BOUNDARY_TILES) return B200_SUCCESS;
-    if (partitioned && rq.fused_pack && rq.kernel == B200_KERNEL_AUTO && arg.n_parity == 1) {
+    const bool tiles_path = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES
+      || rq.kernel == B200_KERNEL_INTERIOR_SITES || rq.kernel == B200_KERNEL_BOUNDARY_SITES;
+    if (tiles_path && !partitioned && (rq.kernel == B200_KERNEL_BOUNDARY_TILES || rq.kernel == B200_KERNEL_BOUNDARY_SITES)) return B200_SUCCESS;
+    if (partitioned && arg.n_parity == 1 && (rq.kernel == B200_KERNEL_INTERIOR_SITES || rq.kernel == B200_KERNEL_BOUNDARY_SITES)) {
+      // the interior / boundary role of the fused kernel alone (1-site-thick shells, no pack role): what a caller with its
+      // own pack launch puts on its main / side stream
+      PackArgs<P> pk {};
+      FusedShape fs {};
+      if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+      fs.gx = gx;
+      fs.gy = gy;
+      fs.n_interior = rq.kernel == B200_KERNEL_INTERIOR_SITES ? gx * gy * gz : 0;
+      fs.n_boundary = rq.kernel == B200_KERNEL_BOUNDARY_SITES ? (arg.threads_ext[4] + threads - 1) / threads : 0;
+      fs.n_interior_first = fs.n_interior;
+      dslash_fused_kernel<P, recon, dagger, xpay, op><<<fs.n_interior + fs.n_boundary, threads, 0, s>>>(arg, tm, pk, fs);
+      count_launch();
+      return check_cuda(cudaGetLastError(), "dslash launch");
+    }
+    if (partitioned && rq.fused_pack && arg.n_parity == 1
+        && (rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES)) {
+      // roles of this launch: AUTO = pack | interior | boundary in one grid; INTERIOR_TILES = the interior role alone
+      // (halo independent); BOUNDARY_TILES = pack | boundary (what a caller puts on a high-priority side stream)
+      const bool do_pack = rq.kernel != B200_KERNEL_INTERIOR_TILES, do_int = rq.kernel != B200_KERNEL_BOUNDARY_TILES,
+                 do_bnd = rq.kernel != B200_KERNEL_INTERIOR_TILES;
       // pack + interior + boundary in ONE launch (dslash_fused_kernel)
       PackArgs<P> pk;
       if (int e = fill_pack_args(pk, *rq.fused_pack)) return e;
@@ -537,16 +591,23 @@ namespace b200
       fs.pack_start[0] = 0;
       for (int f = 0; f < 8; f++) {
         const int d = f >> 1;
-        const int nblk = pk.comm_dim[d] ? (arg.geom.face_cb[d] + threads - 1) / threads : 0;
+        const int nblk = (do_pack && pk.comm_dim[d]) ? (arg.geom.face_cb[d] + threads - 1) / threads : 0;
         fs.pack_start[f + 1] = fs.pack_start[f] + nblk;
       }
       fs.n_pack = fs.pack_start[8];
       if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
       fs.gx = gx;
       fs.gy = gy;
-      fs.n_interior = gx * gy * gz;
-      const int n_boundary = (arg.threads_ext[4] + threads - 1) / threads;
-      dslash_fused_kernel<P, recon, dagger, xpay, op><<<fs.n_pack + fs.n_interior + n_boundary, threads, 0, s>>>(arg, tm, pk, fs);
+      fs.n_interior = do_int ? gx * gy * gz : 0;
+      fs.n_boundary = do_bnd ? (arg.threads_ext[4] + threads - 1) / threads : 0;
+      static int boundary_at = -1; // percent of the interior CTAs dispatched before the boundary CTAs
+      if (boundary_at < 0) {
+        const char *e = getenv("B200_FUSED_BOUNDARY_AT");
+        boundary_at = e ? atoi(e) : 70;
+        if (boundary_at < 0 || boundary_at > 100) boundary_at = 100;
+      }
+      fs.n_interior_first = (int)((long long)fs.n_interior * boundary_at / 100);
+      dslash_fused_kernel<P, recon, dagger, xpay, op><<<fs.n_pack + fs.n_interior + fs.n_boundary, threads, 0, s>>>(arg, tm, pk, fs);
       count_launch();
       return check_cuda(cudaGetLastError(), "fused dslash launch");
     }

@@ -180,7 +180,7 @@ namespace b200
       arg.ghost_norm_parity_stride[d] = rq.n_parity == 2 ? parity_elems / 2 : 0;
       for (int dir = 0; dir < 2; dir++) {
         if (arg.comm_dim[d] && rq.kernel != B200_KERNEL_INTERIOR && rq.kernel != B200_KERNEL_INTERIOR_TILES
-            && !rq.halo.ghost[d][dir])
+            && rq.kernel != B200_KERNEL_INTERIOR_SITES && !rq.halo.ghost[d][dir])
           return set_error(B200_ERR_INVALID, "dimension %d is partitioned but halo.ghost[%d][%d] is NULL", d, d, dir);
         fill_ghost(arg.ghost[d][dir], rq.halo.ghost[d][dir], rq.halo.ghost_norm[d][dir], g.face_cb[d]);
         arg.wait_flag[d][dir] = arg.comm_dim[d] ? reinterpret_cast<const unsigned *>(rq.halo.wait_flag[d][dir]) : nullptr;
@@ -352,9 +352,10 @@ namespace b200
     rq.stream = a->stream;
     bool any_comm = false;
     for (int d = 0; d < 4; d++) any_comm |= (a->halo.comm_dim[d] != 0);
-    if (rq.kernel < B200_KERNEL_AUTO || rq.kernel > B200_KERNEL_BOUNDARY_TILES)
+    if (rq.kernel < B200_KERNEL_AUTO || rq.kernel > B200_KERNEL_BOUNDARY_SITES)
       return set_error(B200_ERR_INVALID, "unknown kernel selector %d", rq.kernel);
-    if ((rq.kernel == B200_KERNEL_EXTERIOR || rq.kernel == B200_KERNEL_BOUNDARY_TILES) && !any_comm) nothing_to_do = true;
+    if ((rq.kernel == B200_KERNEL_EXTERIOR || rq.kernel == B200_KERNEL_BOUNDARY_TILES || rq.kernel == B200_KERNEL_BOUNDARY_SITES) && !any_comm)
+      nothing_to_do = true;
     return 0;
   }
 

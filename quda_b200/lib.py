@@ -13,6 +13,7 @@ ABI_VERSION = 2
 DOUBLE, SINGLE, HALF = 8, 4, 2
 OP_WILSON, OP_CLOVER, OP_CLOVER_PC, OP_TWISTED_MASS, OP_TWISTED_MASS_PC = 0, 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_INTERIOR, KERNEL_EXTERIOR, KERNEL_INTERIOR_TILES, KERNEL_BOUNDARY_TILES = 0, 1, 2, 3, 4
+KERNEL_INTERIOR_SITES, KERNEL_BOUNDARY_SITES = 5, 6
 
 
 class B200Error(RuntimeError):

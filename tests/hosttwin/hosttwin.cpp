@@ -55,6 +55,21 @@ namespace b200
     };
     const bool tiles_path
       = rq.kernel == B200_KERNEL_AUTO || rq.kernel == B200_KERNEL_INTERIOR_TILES || rq.kernel == B200_KERNEL_BOUNDARY_TILES;
+    if (partitioned && arg.n_parity == 1 && (rq.kernel == B200_KERNEL_INTERIOR_SITES || rq.kernel == B200_KERNEL_BOUNDARY_SITES)) {
+      // the interior / boundary role of dslash_fused_kernel alone
+      if (rq.kernel == B200_KERNEL_INTERIOR_SITES) {
+        if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+        walk_box([&](const int *x, int x_cb, int par) {
+          if (site_is_interior(arg, x)) dslash_site_interior<P, recon, dagger, xpay, op, false>(arg, x, x_cb, par);
+        });
+      } else {
+        for (int tid = 0; tid < arg.threads_ext[4]; tid++) {
+          int x[4], x_cb;
+          if (exterior_thread_site(x, x_cb, arg, tid, arg.parity)) dslash_site_full<P, recon, dagger, xpay, op>(arg, x, x_cb, arg.parity);
+        }
+      }
+      return 0;
+    }
     if (partitioned && rq.fused_pack && rq.kernel == B200_KERNEL_AUTO && arg.n_parity == 1) {
       // kernels.cuh::dslash_fused_kernel: (the pack role ran in twin_dslash_apply_fused) interior role over every tile with
       // the face sites retiring, boundary role over the face-site enumeration

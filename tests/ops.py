@@ -232,6 +232,8 @@ def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4
         xdev = P.to_dev(xs) if xpay else None
         if split == "tiles":      # the two halves of AUTO issued separately (boundary first: they are independent)
             kws = [dict(kernel=4, tile=tile), dict(kernel=3, tile=tile)]
+        elif split == "sites":    # the same split with 1-site-thick shells (B200_KERNEL_BOUNDARY_SITES, then INTERIOR_SITES)
+            kws = [dict(kernel=6, tile=tile), dict(kernel=5, tile=tile)]
         elif split and split != "fused":  # reference-style: masked INTERIOR then EXTERIOR read-modify-write
             kws = [dict(kernel=1, tile=tile), dict(kernel=2, tile=tile)]
         else:

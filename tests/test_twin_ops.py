@@ -169,3 +169,10 @@ def test_fused_single_launch_all_masks(comm_dim):
 def test_fused_single_launch_ops(prec, recon, op):
     ops.check_partitioned(HostMem, twin_backend(), prec, recon, (1, 0, 1, 1), op=op, xpay=(op == "wilson"), dagger=1, split="fused",
                           X=(8, 4, 4, 6))
+
+
+@pytest.mark.parametrize("comm_dim", MASKS)
+def test_site_granular_split_all_masks(comm_dim):
+    """B200_KERNEL_BOUNDARY_SITES + B200_KERNEL_INTERIOR_SITES (what the operator layer puts on its side / main stream):
+    together they update every site exactly once for all 15 partition masks"""
+    ops.check_partitioned(HostMem, twin_backend(), 4, 12, comm_dim, X=(4, 6, 4, 8), split="sites", xpay=True)

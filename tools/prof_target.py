@@ -20,10 +20,12 @@ tile = [int(v) for v in os.environ["PROF_TILE"].split()] if os.environ.get("PROF
 if nsrc > 1:
     srcs = [P["in"]] + [bench.new_spinor(P, seed=77 + i) for i in range(nsrc - 1)]
     dsts = [P["out"]] + [bench.new_spinor(P, seed=None) for i in range(nsrc - 1)]
-for _ in range(n):
+# rotate through 4 (input, output) pairs as bench.py does, so that the captured launch writes its output back to HBM
+pairs = [(P["in"], P["out"])] + [(bench.new_spinor(P, seed=501 + i), bench.new_spinor(P, seed=None)) for i in range(3)]
+for k in range(n):
     if nsrc > 1:
         D.ApplyWilson(dsts, srcs, P["U"], 0.0, None, 0, 0, stream=st, tile=tile)
     else:
-        D.ApplyWilson(P["out"], P["in"], P["U"], 0.0, None, 0, 0, stream=st, tile=tile)
+        D.ApplyWilson(pairs[k % 4][1], pairs[k % 4][0], P["U"], 0.0, None, 0, 0, stream=st, tile=tile)
 torch.cuda.synchronize()
 print("prof_target done", pname, recon)

@@ -9,7 +9,7 @@ timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "eight" 2>&
 echo "[t=$(( $(date +%s)-T0 ))s]"
 run() { # label [bench args...]
   local label=$1; shift
-  env "${ENVV[@]}" timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
+  env "${ENVV[@]}" timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29540 + RANDOM % 50)) \
      bench.py --gpus $N --steps 200 --warmup 10 --no-cpu-baseline "$@" 2>> gpurun_out/bench_err.txt | tail -1 > gpurun_out/r2_scale_${N}_${label}.json
   python - <<PY
 import json
@@ -22,9 +22,9 @@ PY
   echo "[t=$(( $(date +%s)-T0 ))s]"
 }
 ENVV=(A=1); run fused
+ENVV=(B200_HALO_SCHEDULE=streams); run streams --no-e2e
 ENVV=(A=1); run cg --op cg --steps 1 --warmup 1
 ENVV=(A=1); run xgrid --grid 2 2 2 1 --no-e2e
 ENVV=(A=1); run double --prec double --recon 18 --no-e2e
 ENVV=(A=1); run half --prec half --recon 12 --no-e2e
-ENVV=(B200_HALO_SCHEDULE=streams); run streams --no-e2e
 echo "== done"
