@@ -196,23 +196,23 @@ namespace b200
     //   streams  the round-1 schedule: pack kernel + boundary-tile kernel on the side stream, interior tiles on the main one
     //   sites  as streams, but with 1-site-thick shells: pack kernel, then the boundary-site role on the side stream, the
     //          interior-site role on the main stream (18.75 % instead of 28 % of the sites take the branchy path at 8 GPUs)
-    enum HaloSchedule { SCHED_SPLIT = 0, SCHED_FUSED = 1, SCHED_STREAMS = 2, SCHED_SITES = 3 };
-#ifndef B2_SCHED_DEFAULT
-#define B2_SCHED_DEFAULT SCHED_STREAMS
-#endif
-    constexpr int SCHED_DEFAULT = B2_SCHED_DEFAULT;
-    static HaloSchedule halo_schedule()
+    enum HaloSchedule { SCHED_AUTO = -1, SCHED_SPLIT = 0, SCHED_FUSED = 1, SCHED_STREAMS = 2, SCHED_SITES = 3 };
+    // Default (B200_HALO_SCHEDULE unset): `streams` -- measured best at 2 and 8 GPUs for y/z/t splits -- unless x is
+    // partitioned: tiles hold full x rows, so with an x split EVERY tile is a boundary tile and the tile-granular schedule has
+    // no interior left to overlap with the halo (90.6 us at 2 GPUs); there the 1-site-thick shells of `sites` are used.
+    static HaloSchedule halo_schedule(const int *comm_dim_eff)
     {
-      static int v = -1;
-      if (v < 0) {
+      static int v = -2;
+      if (v == -2) {
         const char *e = getenv("B200_HALO_SCHEDULE");
-        v = SCHED_DEFAULT;
+        v = SCHED_AUTO;
         if (e && strcmp(e, "split") == 0) v = SCHED_SPLIT;
         if (e && strcmp(e, "fused") == 0) v = SCHED_FUSED;
         if (e && strcmp(e, "streams") == 0) v = SCHED_STREAMS;
         if (e && strcmp(e, "sites") == 0) v = SCHED_SITES;
       }
-      return (HaloSchedule)v;
+      if (v != SCHED_AUTO) return (HaloSchedule)v;
+      return comm_dim_eff[0] ? SCHED_SITES : SCHED_STREAMS;
     }
 
     // `b`, `asymmetric`: twisted mass only; with_x: 1 / 0 force x on / off (the twisted-mass preconditioned operator's
@@ -246,7 +246,11 @@ namespace b200
         for (int d = 0; d < 4; d++) part |= (comm->comm_dim[d] && (!comm_override || comm_override[d]));
       if (part && in.n_parity != 1) throw Error("a partitioned Dslash works on one parity at a time");
       const bool side_stream = part && comm->pack_stream && comm->pack_stream != stream;
-      if (part && (halo_schedule() == SCHED_FUSED || (halo_schedule() == SCHED_SPLIT && !side_stream))) {
+      int eff[4] = {0, 0, 0, 0};
+      if (part)
+        for (int d = 0; d < 4; d++) eff[d] = comm->comm_dim[d] && (!comm_override || comm_override[d]);
+      const HaloSchedule sched = part ? halo_schedule(eff) : SCHED_STREAMS;
+      if (part && (sched == SCHED_FUSED || (sched == SCHED_SPLIT && !side_stream))) {
         // pack + interior + boundary: one launch on the operator's stream
         b200_pack_args pk;
         pack_args_for(pk, in, 1 - parity, dagger, comm_override, comm);
@@ -256,7 +260,7 @@ namespace b200
         abi_ok(b200_dslash_apply_fused(&args, &pk));
         return;
       }
-      if (part && halo_schedule() == SCHED_SPLIT) {
+      if (part && sched == SCHED_SPLIT) {
         // [pack | boundary] on the side stream (after `in` is complete), [interior] on the main stream, then join
         b200_pack_args pk;
         pack_args_for(pk, in, 1 - parity, dagger, comm_override, comm);
@@ -282,7 +286,7 @@ namespace b200
       if (two_streams) {
         // side stream (behind the pack kernel): boundary sites -- they depend only on the halo, not on the interior
         // launch; main stream: the interior.  Both halves write disjoint sites.
-        const bool shells = halo_schedule() == SCHED_SITES;
+        const bool shells = sched == SCHED_SITES;
         args.kernel = shells ? B200_KERNEL_BOUNDARY_SITES : B200_KERNEL_BOUNDARY_TILES;
         args.stream = comm->pack_stream;
         abi_ok(b200_dslash_apply(&args));

@@ -1,4 +1,6 @@
 #!/bin/bash
+# Round-2 experiment pack, FIRST call of round 2 (kept as the record of how profiles/r02_march_* were produced; the
+# B200_MARCH_T launch it sweeps was removed afterwards because it did not help -- DESIGN.md section 6.2).
 # Round-2 experiment pack (single GPU, ~3 min): everything that was written in round 1 after the GPU budget ran out.
 #   1. experimental GPU tests (time-marching launch)                      B200_EXPERIMENTAL=1
 #   2. time-marching sweep: does walking t slices with a fixed (x,y,z) tile cut the L2->L1 spinor traffic?

@@ -17,7 +17,5 @@ except Exception as e:
 PY
   echo "[t=$(( $(date +%s)-T0 ))s]"
 }
-ENVV=(B200_HALO_SCHEDULE=sites); run sites
-ENVV=(B200_HALO_SCHEDULE=streams); run streams
-ENVV=(B200_HALO_SCHEDULE=fused); run fused
+ENVV=(A=1); run xsplit_auto --grid 2 1 1 1
 echo "== done"
