@@ -185,6 +185,16 @@ typedef struct {
 } b200_pack_args;
 int b200_pack_ghost(const b200_pack_args *args);
 
+/* The batched (multi-RHS) form of PackGhost: the reference packs every source of a cvector_ref batch in ONE launch, the
+ * source index riding in the thread grid (lib/dslash_pack2.cu:55-403; WilsonArg::in[MAX_MULTI_RHS],
+ * include/kernels/dslash_wilson.cuh:37-40).  args->in is ignored in favour of in[0 .. n_src): source s is written
+ * s * dst_stride[d] bytes behind args->dst[d][f] (and dst_norm), i.e. the receiver holds n_src ghost slabs per face,
+ * dst_stride[d] >= one parity's face bytes apart.  args->signal[d][f] moves ONCE, to the same value as for the single
+ * exchange `seq`, when the last site of the last source has landed; each source's Dslash then runs with
+ * b200_halo.ghost[d][dir] + s * stride, the same wait_flag and the same seq.  One pack launch, one NVLink round trip and
+ * one arrival signal per face for the whole batch. */
+int b200_pack_ghost_multi(const b200_pack_args *args, int n_src, const b200_spinor *in, const size_t dst_stride[4]);
+
 /* The whole partitioned Dslash -- what ApplyWilson* does on a partitioned lattice through its policy
  * (lib/dslash_wilson.hpp:18-54 -> lib/dslash_policy.hpp:1471-1650: pack, exchange, interior, exterior) -- as ONE kernel
  * launch on args->stream: pack CTAs write the faces of `in` into the neighbours' ghost slabs and raise their arrival

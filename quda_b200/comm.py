@@ -105,22 +105,28 @@ class HaloExchange:
     """Ghost buffers + neighbour wiring for one (lattice, precision, site-subset).  Owns its buffers (allocated once,
     like the reference's static ghost buffers, lib/lattice_field.cpp:274-303)."""
 
-    def __init__(self, grid, X, prec, n_parity=1, mode="p2p", backend=None, dist=None, self_dims=None):
+    def __init__(self, grid, X, prec, n_parity=1, mode="p2p", backend=None, dist=None, self_dims=None, n_src=1):
         self.grid, self.X, self.prec, self.n_parity, self.mode = grid, [int(v) for v in X], prec, n_parity, mode
         self.backend, self.dist = backend, dist
+        # n_src > 1: every ghost region holds n_src slabs (one per source of a multi-RHS batch, src_stride[d] bytes apart) so
+        # that the faces of a whole batch travel in ONE pack launch / ONE exchange with ONE arrival signal per face
+        self.n_src = int(n_src)
+        if not 1 <= self.n_src <= L.MAX_MULTI_RHS:
+            raise L.B200Error(f"n_src {n_src} not in [1, {L.MAX_MULTI_RHS}]")
         # "self": a single rank that is its own neighbour in the dimensions of `self_dims` (default: all four)
         self.comm_dim = grid.comm_dim() if mode != "self" else [int(bool(v)) for v in (self_dims or (1, 1, 1, 1))]
         self._comm_struct = None
         self._seq = 0
         self.face_bytes = [n_parity * F.ghost_parity_bytes(X, prec, d) for d in range(4)]
         # slab layout: [buf 0|1][d][dir] ghost regions (256-byte aligned), then flags[2][4][2] (u32), counters[8], timeout
+        self.src_stride = [(fb + 255) // 256 * 256 for fb in self.face_bytes]
         self.off = {}
         o = 0
         for b in range(2):
             for d in range(4):
                 for dr in range(2):
                     self.off[(b, d, dr)] = o
-                    o += (self.face_bytes[d] + 255) // 256 * 256 if self.comm_dim[d] else 0
+                    o += self.n_src * self.src_stride[d] if self.comm_dim[d] else 0
         self.flag_off = o
         o += 2 * 8 * 4
         self.counter_off = o
@@ -206,7 +212,13 @@ class HaloExchange:
 
     # ------------------------------------------------------------------ per-application calls
     def start(self, in_field, in_parity, dagger, stream=None, parity_slot=0):
-        """Pack the faces of `in_field` (sites of parity `in_parity`) and ship them to the neighbours."""
+        """Pack the faces of `in_field` (sites of parity `in_parity`) and ship them to the neighbours.  A list of fields
+        (at most `n_src`) is one batched exchange: one pack launch, one signal per face; source s lands in slab s."""
+        batch = list(in_field) if isinstance(in_field, (list, tuple)) else None
+        if batch is not None:
+            if not 1 <= len(batch) <= self.n_src:
+                raise L.B200Error(f"batch of {len(batch)} sources on an exchange created for n_src={self.n_src}")
+            in_field = batch[0]
         self.seq += 1
         b = self.seq & 1
         g = self.grid
@@ -232,28 +244,36 @@ class HaloExchange:
             a.parity, a.dagger = in_parity, int(bool(dagger))
             a.in_ = in_field.desc()
             a.stream = stream
-            (self.backend or D.cuda_backend()).call("pack_ghost", C.byref(a))
+            be = self.backend or D.cuda_backend()
+            if batch is None:
+                be.call("pack_ghost", C.byref(a))
+            else:
+                srcs = (L.Spinor * len(batch))(*[f.desc() for f in batch])
+                stride = (C.c_size_t * 4)(*self.src_stride)
+                be.call("pack_ghost_multi", C.byref(a), len(batch), srcs, stride)
             return
-        # staged modes: pack locally, then exchange
-        dst = [[None, None] for _ in range(4)]
-        for d in range(4):
-            if self.comm_dim[d]:
-                for f in range(2):
-                    dst[d][f] = self.send[self.off[(b, d, f)]:]
-        D.PackGhost(dst, in_field, in_parity, dagger, self.comm_dim, stream=stream, backend=self.backend)
+        # staged modes: pack locally (every source into its slab), then ONE exchange of the whole batch
+        for s, f_in in enumerate(batch or [in_field]):
+            dst = [[None, None] for _ in range(4)]
+            for d in range(4):
+                if self.comm_dim[d]:
+                    for f in range(2):
+                        dst[d][f] = self.send[self.off[(b, d, f)] + s * self.src_stride[d]:]
+            D.PackGhost(dst, f_in, in_parity, dagger, self.comm_dim, stream=stream, backend=self.backend)
+        m = len(batch) if batch is not None else 1
         if self.mode == "nccl":
-            self._exchange_nccl(b)
+            self._exchange_nccl(b, m)
         else:
-            self._exchange_host(b)
+            self._exchange_host(b, m)
 
-    def _exchange_nccl(self, b):
+    def _exchange_nccl(self, b, m=1):
         import torch.distributed as dist
         ops = []
         g = self.grid
         for d in range(4):
             if not self.comm_dim[d]:
                 continue
-            n = self.face_bytes[d]
+            n = self.face_bytes[d] + (m - 1) * self.src_stride[d]
             lo, hi = self.off[(b, d, 0)], self.off[(b, d, 1)]
             # send low face backwards (arrives in their slot 1), high face forwards (arrives in their slot 0)
             ops.append(dist.P2POp(dist.isend, self.send[lo:lo + n], g.neighbor(d, -1)))
@@ -263,14 +283,14 @@ class HaloExchange:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
-    def _exchange_host(self, b):
+    def _exchange_host(self, b, m=1):
         import torch
         dist = self.dist
         g = self.grid
         for d in range(4):
             if not self.comm_dim[d]:
                 continue
-            n = self.face_bytes[d]
+            n = self.face_bytes[d] + (m - 1) * self.src_stride[d]
             lo, hi = self.off[(b, d, 0)], self.off[(b, d, 1)]
             s_lo, s_hi = torch.from_numpy(self.send[lo:lo + n]), torch.from_numpy(self.send[hi:hi + n])
             r_lo, r_hi = torch.from_numpy(self.slab[lo:lo + n]), torch.from_numpy(self.slab[hi:hi + n])
@@ -279,15 +299,16 @@ class HaloExchange:
             for r in reqs:
                 r.wait()
 
-    def halo(self):
-        """b200_halo descriptor for the exchange started last."""
+    def halo(self, src=0):
+        """b200_halo descriptor for the exchange started last (`src`: which source of a batched exchange; all sources share
+        the arrival flags and the sequence number)."""
         b = self.seq & 1
         h = L.Halo()
         for d in range(4):
             h.comm_dim[d] = self.comm_dim[d]
             for dr in range(2):
                 if self.comm_dim[d]:
-                    h.ghost[d][dr] = self.base + self.off[(b, d, dr)]
+                    h.ghost[d][dr] = self.base + self.off[(b, d, dr)] + src * self.src_stride[d]
                     if self.mode in ("p2p", "self"):
                         h.wait_flag[d][dr] = self.base + self.flag_off + ((b * 4 + d) * 2 + dr) * 4
         h.seq = self.seq
@@ -374,22 +395,33 @@ def apply_wilson_distributed(ex, out, in_, U, a, x, parity, dagger, op=L.OP_WILS
       main stream : interior tiles (no dependence on the halo), concurrently
     The side stream forks from the main stream (so `in_` is complete) and joins it again afterwards (so `out` is
     complete and nothing that follows can overwrite `in_` while it is still being packed)."""
-    if in_.n_parity != 1:
+    multi = isinstance(out, (list, tuple))
+    if multi:
+        # the reference's cvector_ref batch on a partitioned lattice (lib/dslash_pack2.cu packs all sources in one launch):
+        # ONE batched exchange (needs HaloExchange(n_src >= len(batch))), then every source's interior / boundary launches
+        # read their own ghost slab and wait on the shared arrival flags
+        outs, ins = list(out), list(in_)
+        xs = list(x) if x is not None else [None] * len(outs)
+        if len(ins) != len(outs) or len(xs) != len(outs):
+            raise L.B200Error("multi-RHS: out / in / x batches differ in length")
+    else:
+        outs, ins, xs = [out], [in_], [x]
+    if any(f.n_parity != 1 for f in ins):
         raise NotImplementedError("full-field halo exchange: pack each parity into its slot")
     side = ex.pack_stream(stream) if ex.mode == "p2p" else None
     if side is None:
-        ex.start(in_, 1 - parity, dagger, stream=stream)
-        D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(ex.halo()), stream=stream, tile=tile,
-                 backend=ex.backend)
+        ex.start(ins if multi else in_, 1 - parity, dagger, stream=stream)
+        for s in range(len(outs)):
+            D._apply(op, outs[s], ins[s], U, a, xs[s], parity, dagger, None, A=A, halo=_RawHalo(ex.halo(s)), stream=stream,
+                     tile=tile, backend=ex.backend)
         return
     import torch
     main = torch.cuda.current_stream() if stream is None else torch.cuda.ExternalStream(stream)
     side.wait_stream(main)
-    ex.start(in_, 1 - parity, dagger, stream=side.cuda_stream)
-    halo = ex.halo()
+    ex.start(ins if multi else in_, 1 - parity, dagger, stream=side.cuda_stream)
     # side stream: pack -> boundary tiles (wait for the neighbours' flags, complete updates); main stream: interior tiles
-    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(halo), stream=side.cuda_stream, tile=tile,
-             kernel=L.KERNEL_BOUNDARY_TILES, backend=ex.backend)
-    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(halo), stream=main.cuda_stream, tile=tile,
-             kernel=L.KERNEL_INTERIOR_TILES, backend=ex.backend)
+    for kernel, st in ((L.KERNEL_BOUNDARY_TILES, side), (L.KERNEL_INTERIOR_TILES, main)):
+        for s in range(len(outs)):
+            D._apply(op, outs[s], ins[s], U, a, xs[s], parity, dagger, None, A=A, halo=_RawHalo(ex.halo(s)),
+                     stream=st.cuda_stream, tile=tile, kernel=kernel, backend=ex.backend)
     main.wait_stream(side)

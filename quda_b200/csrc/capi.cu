@@ -339,6 +339,38 @@ int b200_pack_ghost(const b200_pack_args *a)
   return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
 }
 
+int b200_pack_ghost_multi(const b200_pack_args *a, int n_src, const b200_spinor *in, const size_t dst_stride[4])
+{
+  if (n_src < 1 || n_src > B200_MAX_MULTI_RHS) return set_error(B200_ERR_INVALID, "n_src %d not in [1, %d]", n_src, B200_MAX_MULTI_RHS);
+  if (!a || !in || !dst_stride) return set_error(B200_ERR_INVALID, "null argument");
+  b200_pack_args first = *a;
+  first.in = in[0];
+  PackRequest rq;
+  if (int rc = make_pack_request(rq, &first)) return rc;
+  PackBatchRequest batch {};
+  batch.n_src = n_src;
+  for (int s = 0; s < n_src; s++) {
+    if (!in[s].v) return set_error(B200_ERR_INVALID, "source %d is null", s);
+    if (in[s].n_parity != 1) return set_error(B200_ERR_INVALID, "the batched pack takes single-parity sources");
+    batch.in[s] = in[s].v;
+    batch.in_norm[s] = in[s].norm;
+  }
+  for (int d = 0; d < 4; d++) {
+    batch.dst_stride[d] = dst_stride[d];
+    // a slab stride smaller than one parity's face would make the sources overwrite each other
+    if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < b200_ghost_face_bytes(a->precision, a->X, d) / 2)
+      return set_error(B200_ERR_INVALID, "dst_stride[%d] = %zu is smaller than one face (%zu bytes)", d, dst_stride[d],
+                       b200_ghost_face_bytes(a->precision, a->X, d) / 2);
+  }
+  if (int rc = require_device()) return rc;
+  switch (a->precision) {
+  case B200_DOUBLE: return launch_pack_multi_precision<PrecF64>(rq, batch);
+  case B200_SINGLE: return launch_pack_multi_precision<PrecF32>(rq, batch);
+  case B200_HALF: return launch_pack_multi_precision<PrecH16>(rq, batch);
+  }
+  return set_error(B200_ERR_INVALID, "precision %d not in {8,4,2}", a->precision);
+}
+
 int b200_dslash_apply_fused(const b200_dslash_args *a, const b200_pack_args *p)
 {
   if (int rc = require_device()) return rc;

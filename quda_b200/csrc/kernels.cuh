@@ -202,8 +202,24 @@ namespace b200
     int dagger;
   };
 
-  // one CTA of the pack: sites [blk * blockDim.x, ...) of face `face_id` = 2*d + face; `nblk` CTAs work on this face
-  template <class P> __device__ __forceinline__ void pack_block(const PackArgs<P> &arg, int face_id, int blk, int nblk)
+  // Which field a pack CTA reads and where its faces go: the launch's own (single exchange) ...
+  template <class P> struct PackOwnViews {
+    const PackArgs<P> &arg;
+    __device__ __forceinline__ const SpinorView<P> &in() const { return arg.in; }
+    __device__ __forceinline__ const GhostView<P> &dst(int d, int face) const { return arg.dst[d][face]; }
+  };
+  // ... or those of one source of a multi-RHS batch (pack_multi_kernel)
+  template <class P> struct PackSourceViews {
+    SpinorView<P> in_;
+    GhostView<P> dst_;
+    __device__ __forceinline__ const SpinorView<P> &in() const { return in_; }
+    __device__ __forceinline__ const GhostView<P> &dst(int, int) const { return dst_; }
+  };
+
+  // one CTA of the pack: sites [blk * blockDim.x, ...) of face `face_id` = 2*d + face; `nblk` CTAs (of all sources of a
+  // batch together) work on this face before its arrival counter moves
+  template <class P, class Views>
+  __device__ __forceinline__ void pack_block(const PackArgs<P> &arg, const Views &vw, int face_id, int blk, int nblk)
   {
     using real = typename P::real;
     const Geom &g = arg.geom;
@@ -215,14 +231,14 @@ namespace b200
       const int x_cb = cb_from_coords(x, g);
       const int sign = (face == 0) ? (arg.dagger ? +1 : -1) : (arg.dagger ? -1 : +1);
       real v[24], h[12];
-      arg.in.load(v, x_cb);
+      vw.in().load(v, x_cb);
       switch (d) {
       case 0: project(h, v, 0, sign); break;
       case 1: project(h, v, 1, sign); break;
       case 2: project(h, v, 2, sign); break;
       default: project(h, v, 3, sign); break;
       }
-      arg.dst[d][face].save(h, idx);
+      vw.dst(d, face).save(h, idx);
     }
     unsigned *sig = arg.signal[d][face];
     if (sig) {
@@ -252,6 +268,11 @@ namespace b200
     }
   }
 
+  template <class P> __device__ __forceinline__ void pack_block(const PackArgs<P> &arg, int face_id, int blk, int nblk)
+  {
+    pack_block(arg, PackOwnViews<P> {arg}, face_id, blk, nblk);
+  }
+
   // grid: x = blocks over the largest face, y = face id (2*d + face)
   template <class P> __global__ void __launch_bounds__(128) pack_kernel(const __grid_constant__ PackArgs<P> arg)
   {
@@ -260,6 +281,34 @@ namespace b200
     const int nblk = (arg.geom.face_cb[d] + blockDim.x - 1) / blockDim.x;
     if ((int)blockIdx.x >= nblk) return;
     pack_block(arg, blockIdx.y, blockIdx.x, nblk);
+  }
+
+  // Batched (multi-RHS) pack: the faces of ALL sources of a cvector_ref batch leave in one launch and raise ONE arrival
+  // signal per face (reference: lib/dslash_pack2.cu:55-403 packs every source of the batch in one kernel, the source index
+  // riding in the thread grid).  grid.z = source; source s reads batch.in[s] and writes s * dst_stride[d] bytes behind the
+  // first source's slab.  The tickets count the CTAs of all sources, so the counter in the receiver's memory moves -- to
+  // the same value as for a single exchange `seq` -- only when the last source's last site has landed; each source's
+  // boundary kernel then waits on that one counter and reads its own slab.
+  template <class P> struct PackBatch {
+    typename P::store *in[B200_MAX_MULTI_RHS];
+    float *in_norm[B200_MAX_MULTI_RHS];
+    size_t dst_stride[4];
+    int n_src;
+  };
+
+  template <class P>
+  __global__ void __launch_bounds__(128) pack_multi_kernel(const __grid_constant__ PackArgs<P> arg, const __grid_constant__ PackBatch<P> batch)
+  {
+    static_assert(!B2_PACK_REMOTE_ADD, "the batched pack relies on the ticket protocol");
+    const int d = blockIdx.y >> 1, face = blockIdx.y & 1;
+    if (!arg.comm_dim[d]) return;
+    const int nblk = (arg.geom.face_cb[d] + blockDim.x - 1) / blockDim.x;
+    if ((int)blockIdx.x >= nblk) return;
+    const int s = blockIdx.z;
+    PackSourceViews<P> vw {arg.in, ghost_of_source(arg.dst[d][face], (size_t)s * batch.dst_stride[d])};
+    vw.in_.v = batch.in[s];
+    vw.in_.norm = batch.in_norm[s];
+    pack_block(arg, vw, blockIdx.y, blockIdx.x, nblk * batch.n_src);
   }
 
   // ------------------------------------------------------------------ ONE launch per partitioned Dslash
@@ -738,6 +787,33 @@ namespace b200
     pack_kernel<P><<<grid, 128, 0, (cudaStream_t)rq.stream>>>(arg);
     count_launch();
     return check_cuda(cudaGetLastError(), "pack launch");
+  }
+
+  template <class P> int launch_pack_multi_precision(const PackRequest &rq, const PackBatchRequest &b)
+  {
+    PackArgs<P> arg;
+    if (int e = fill_pack_args(arg, rq)) return e;
+    PackBatch<P> batch {};
+    batch.n_src = b.n_src;
+    for (int s = 0; s < b.n_src; s++) {
+      SpinorView<P> v;
+      fill_spinor(v, b.in[s], b.in_norm[s], arg.geom.volume_cb);
+      batch.in[s] = v.v;
+      batch.in_norm[s] = v.norm;
+    }
+    int max_face = 0;
+    bool any_signal = false;
+    for (int d = 0; d < 4; d++) {
+      batch.dst_stride[d] = b.dst_stride[d];
+      if (arg.comm_dim[d] && arg.geom.face_cb[d] > max_face) max_face = arg.geom.face_cb[d];
+      for (int dir = 0; dir < 2; dir++) any_signal |= (arg.signal[d][dir] != nullptr);
+    }
+    if (max_face == 0) return 0;
+    if (any_signal && !arg.counter) return set_error(B200_ERR_INVALID, "signal[] given without block_counter scratch");
+    dim3 grid((max_face + 127) / 128, 8, b.n_src);
+    pack_multi_kernel<P><<<grid, 128, 0, (cudaStream_t)rq.stream>>>(arg, batch);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "batched pack launch");
   }
 
 } // namespace b200

@@ -95,6 +95,14 @@ namespace b200
     void *stream;
   };
 
+  // A batch of sources packed by ONE launch (b200_pack_ghost_multi): source s reads in[s] and writes its faces
+  // dst_stride[d] * s bytes behind the first source's slab in dimension d; the arrival counters move once, for all of them.
+  struct PackBatchRequest {
+    int n_src;
+    void *in[B200_MAX_MULTI_RHS], *in_norm[B200_MAX_MULTI_RHS];
+    size_t dst_stride[4];
+  };
+
   template <class P> void fill_spinor(SpinorView<P> &v, void *base, void *norm, int volume_cb)
   {
     v.v = reinterpret_cast<typename P::store *>(base);
@@ -134,6 +142,14 @@ namespace b200
                       (base ? reinterpret_cast<float *>(reinterpret_cast<short *>(base) + (size_t)12 * face_cb) : nullptr);
     else
       g.norm = nullptr;
+  }
+
+  // ghost slab of source `s` in a batched exchange: `bytes` = s * (the caller's slab stride in this dimension)
+  template <class P> B2_HD GhostView<P> ghost_of_source(GhostView<P> g, size_t bytes)
+  {
+    g.v = reinterpret_cast<typename P::store *>(reinterpret_cast<char *>(g.v) + bytes);
+    if (g.norm) g.norm = reinterpret_cast<float *>(reinterpret_cast<char *>(g.norm) + bytes);
+    return g;
   }
 
   template <class P, int recon> int fill_args(DslashArgs<P, recon> &arg, const LaunchRequest &rq)
@@ -489,6 +505,7 @@ namespace b200
   template <class P> int launch_clover_precision(const CloverRequest &rq);
   template <class P> int launch_twist_precision(const TwistRequest &rq);
   template <class P> int launch_pack_precision(const PackRequest &rq);
+  template <class P> int launch_pack_multi_precision(const PackRequest &rq, const PackBatchRequest &batch);
   template <class P> int launch_copy_precision(const CopyRequest &rq);
   template <class P> int launch_gauge_copy_precision(const GaugeCopyRequest &rq);
   template <class P> int launch_clover_copy_precision(const CloverCopyRequest &rq);

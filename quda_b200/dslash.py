@@ -86,6 +86,7 @@ class Halo:
     def __init__(self):
         self.comm_dim = [0, 0, 0, 0]
         self.ghost = [[None, None] for _ in range(4)]
+        self.src, self.src_stride = 0, (0, 0, 0, 0)  # slab of a batched exchange this view reads (source())
 
     def desc(self, comm_override=None):
         h = L.Halo()
@@ -93,8 +94,14 @@ class Halo:
             on = self.comm_dim[d] and (comm_override is None or comm_override[d])
             h.comm_dim[d] = 1 if on else 0
             for dir_ in range(2):
-                h.ghost[d][dir_] = _ptr(self.ghost[d][dir_]) if on else None
+                h.ghost[d][dir_] = _ptr(self.ghost[d][dir_]) + self.src * self.src_stride[d] if on else None
                 h.ghost_norm[d][dir_] = None
+        return h
+
+    def source(self, s, src_stride):
+        """the view of source `s` of a batched exchange (PackGhostMulti): same buffers, slab s"""
+        h = Halo()
+        h.comm_dim, h.ghost, h.src, h.src_stride = self.comm_dim, self.ghost, s, tuple(src_stride)
         return h
 
 
@@ -211,6 +218,26 @@ def PackGhost(dst, in_, parity, dagger, comm_dim, stream=None, backend=None):
     a.in_ = in_.desc()
     a.stream = stream
     be.call("pack_ghost", C.byref(a))
+
+
+def PackGhostMulti(dst, ins, parity, dagger, comm_dim, dst_stride, stream=None, backend=None):
+    """PackGhost for a multi-RHS batch in ONE launch: source s goes to dst[d][face] + s * dst_stride[d] bytes.
+    Reference: lib/dslash_pack2.cu:55-403 (the source index rides in the thread grid)."""
+    be = backend or cuda_backend()
+    a = L.PackArgs()
+    a.abi_version, a.precision = L.ABI_VERSION, ins[0].prec
+    for d in range(4):
+        a.X[d] = ins[0].X[d]
+        a.comm_dim[d] = 1 if comm_dim[d] else 0
+        for f in range(2):
+            a.dst[d][f] = _ptr(dst[d][f]) if comm_dim[d] else None
+            a.dst_norm[d][f] = None
+    a.parity, a.dagger = parity, int(bool(dagger))
+    a.in_ = ins[0].desc()
+    a.stream = stream
+    srcs = (L.Spinor * len(ins))(*[f.desc() for f in ins])
+    stride = (C.c_size_t * 4)(*[int(v) for v in dst_stride])
+    be.call("pack_ghost_multi", C.byref(a), len(ins), srcs, stride)
 
 
 def copy_spinor(native, host_order, to_native, stream=None):

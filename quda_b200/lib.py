@@ -97,6 +97,8 @@ def declare(lib, prefix="b200"):
     f.restype = C.c_int
     f = getattr(lib, prefix + "_pack_ghost")
     f.argtypes, f.restype = [C.POINTER(PackArgs)], C.c_int
+    f = getattr(lib, prefix + "_pack_ghost_multi")
+    f.argtypes, f.restype = [C.POINTER(PackArgs), C.c_int, C.POINTER(Spinor), C.POINTER(C.c_size_t)], C.c_int
     f = getattr(lib, prefix + "_dslash_apply_fused")
     f.argtypes, f.restype = [C.POINTER(DslashArgs), C.POINTER(PackArgs)], C.c_int
     f = getattr(lib, prefix + "_last_error")
@@ -163,7 +165,7 @@ def check(rc, lib=None, prefix="b200"):
         raise B200Error(f"{prefix} error {rc}: {msg}")
 
 
-EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_dslash_apply_fused", "b200_dslash_apply_multi", "b200_clover_apply", "b200_twist_gamma5", "b200_pack_ghost", "b200_ghost_face_bytes",
+EXPORTED_SYMBOLS = ["b200_dslash_apply", "b200_dslash_apply_fused", "b200_dslash_apply_multi", "b200_clover_apply", "b200_twist_gamma5", "b200_pack_ghost", "b200_pack_ghost_multi", "b200_ghost_face_bytes",
                     "b200_copy_spinor", "b200_copy_gauge", "b200_copy_clover", "b200_comm_alloc", "b200_comm_free", "b200_ipc_get_handle", "b200_ipc_open_handle",
                     "b200_ipc_close_handle", "b200_comm_copy",
                     "b200_dirac_create", "b200_dirac_set_twist", "b200_dirac_destroy", "b200_dirac_apply", "b200_dirac_prepare",

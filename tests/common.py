@@ -121,3 +121,21 @@ def assert_close(ref, test, prec, recon=18, what=""):
     tol = oracle.tolerance(PREC_NAME[prec], recon)
     assert dev <= tol, f"{what}: deviation {dev:g} > tolerance {tol:g} (prec {prec}, recon {recon}); fails={fails[:8]}"
     return dev
+
+
+def host_self_exchange(X, prec, self_dims, n_src=1):
+    """CPU stand-in for HaloExchange(mode="self") (one rank that is its own neighbour, arrival counters and all): the slab
+    lives in numpy memory and the host twin executes the calls.  Exercises the very same Python schedule, pointer
+    arithmetic and counter protocol the GPU path uses, minus the hardware."""
+    from quda_b200 import comm
+
+    class _HostSelf(comm.HaloExchange):
+        def _init_device_slab(self):
+            self.slab = np.zeros(self.slab_bytes, dtype=np.uint8)
+            self.base = self.slab.ctypes.data
+            self.peer = {self.grid.rank: self.base}
+
+        def timed_out(self):
+            return bool(self.slab[self.timeout_off:self.timeout_off + 4].view(np.int32)[0])
+
+    return _HostSelf(comm.ProcessGrid((1, 1, 1, 1), 0), X, prec, mode="self", backend=twin_backend(), self_dims=self_dims, n_src=n_src)

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <numeric>
 #include <cstring>
 #include <vector>
 
@@ -35,6 +36,18 @@ namespace b200
     if (int e = make_tile_map(tm, threads, rq.tile, g, 128)) return e;
     const bool partitioned = arg.threads_ext[4] > 0;
     long visited = 0;
+    // kernels.cuh::wait_for_halo: every role that reads ghost zones first acquires the arrival counters.  The twin runs
+    // pack and Dslash one after the other, so a counter below its target is a deadlock (or a 10 s timeout) on the GPU.
+    if (partitioned && rq.kernel != B200_KERNEL_INTERIOR && rq.kernel != B200_KERNEL_INTERIOR_TILES && rq.kernel != B200_KERNEL_INTERIOR_SITES) {
+      const unsigned uses = (arg.seq + (arg.seq & 1u)) >> 1;
+      for (int d = 0; d < 4; d++)
+        for (int dir = 0; dir < 2; dir++)
+          if (const unsigned *f = arg.wait_flag[d][dir]) {
+            const unsigned target = uses * (unsigned)g.face_cb[d];
+            if ((int)(*f - target) < 0)
+              return set_error(B200_ERR_INVALID, "halo wait would never finish: counter[%d][%d] = %u < %u (exchange %u)", d, dir, *f, target, arg.seq);
+          }
+    }
     if (rq.tma && !partitioned && rq.kernel == B200_KERNEL_AUTO) { // capi.cu: TMA-staged marching kernel where it serves the shape
       const int rc = tma_emu_launch<P, recon, dagger, xpay, op>(rq, arg);
       if (rc != kTmaSkip) return rc;
@@ -342,6 +355,69 @@ namespace b200
     }
     return 0;
   }
+
+  // kernels.cuh::pack_multi_kernel, CTA by CTA: grid (blocks over the largest face, 8 faces, n_src sources) walked in a
+  // scrambled order (CTAs retire in any order on the GPU), each CTA = 128 threads of pack_block with the source's views
+  // (launch.h::ghost_of_source, the function the kernel uses) followed by the ticket protocol: the CTA that draws ticket
+  // nblk * n_src - 1 of its face publishes the arrival count.  Checks on the way that the count is published exactly once
+  // per face and only after every site of every source has been written.
+  template <class P> int run_pack_multi(const b200_pack_args *a, int n_src, const b200_spinor *src, const size_t *dst_stride)
+  {
+    Geom g;
+    geom_init(g, a->X);
+    int max_face = 0;
+    for (int d = 0; d < 4; d++)
+      if (a->comm_dim[d] && g.face_cb[d] > max_face) max_face = g.face_cb[d];
+    if (max_face == 0) return 0;
+    const int block = 128, gx = (max_face + block - 1) / block;
+    int tickets[8] = {0}, published[8] = {0};
+    long written[8] = {0};
+    const long n_cta = (long)gx * 8 * n_src;
+    // an odd multiplier coprime to n_cta visits every CTA exactly once in a scrambled order
+    long mul = 7919;
+    while (std::gcd(mul, n_cta) != 1) mul += 2;
+    for (long k = 0; k < n_cta; k++) {
+      const long c = (k * mul + 12345) % n_cta;
+      const int bx = (int)(c % gx), by = (int)((c / gx) % 8), s = (int)(c / ((long)gx * 8));
+      const int d = by >> 1, face = by & 1;
+      if (!a->comm_dim[d]) continue;
+      const int nblk = (g.face_cb[d] + block - 1) / block;
+      if (bx >= nblk) continue;
+      SpinorView<P> in;
+      fill_spinor(in, src[s].v, src[s].norm, g.volume_cb);
+      GhostView<P> first;
+      fill_ghost(first, a->dst[d][face], a->dst_norm[d][face], g.face_cb[d]);
+      const GhostView<P> dst = ghost_of_source(first, (size_t)s * dst_stride[d]);
+      for (int tid = 0; tid < block; tid++) {
+        const int idx = bx * block + tid;
+        if (idx >= g.face_cb[d]) continue;
+        int x[4];
+        coords_from_face(x, g, d, face ? g.X[d] - 1 : 0, idx, a->parity);
+        const int x_cb = cb_from_coords(x, g);
+        const int sign = (face == 0) ? (a->dagger ? +1 : -1) : (a->dagger ? -1 : +1);
+        typename P::real v[24], h[12];
+        in.load(v, x_cb);
+        project(h, v, d, sign);
+        dst.save(h, idx);
+        written[by]++;
+      }
+      if (a->signal[d][face]) {
+        if (!a->block_counter) return set_error(B200_ERR_INVALID, "signal[] given without block_counter scratch");
+        const int prev = tickets[by]++;
+        if (prev == nblk * n_src - 1) {
+          if (written[by] != (long)n_src * g.face_cb[d]) return set_error(B200_ERR_INVALID, "face %d signalled before all sources landed", by);
+          if (published[by]++) return set_error(B200_ERR_INVALID, "face %d signalled twice", by);
+          tickets[by] = 0;
+          const unsigned uses = (a->seq + (a->seq & 1u)) >> 1;
+          *static_cast<unsigned *>(a->signal[d][face]) = uses * (unsigned)g.face_cb[d];
+        }
+      }
+    }
+    for (int by = 0; by < 8; by++)
+      if (a->comm_dim[by >> 1] && a->signal[by >> 1][by & 1] && published[by] != 1)
+        return set_error(B200_ERR_INVALID, "face %d never signalled", by);
+    return 0;
+  }
 } // namespace b200
 
 using namespace b200;
@@ -462,8 +538,37 @@ int twin_twist_gamma5(const b200_spinor *out, const b200_spinor *in, int precisi
   return -1;
 }
 
+int twin_pack_ghost_multi(const b200_pack_args *a, int n_src, const b200_spinor *in, const size_t dst_stride[4])
+{
+  // same argument checks as capi.cu::b200_pack_ghost_multi
+  if (n_src < 1 || n_src > B200_MAX_MULTI_RHS) return set_error(B200_ERR_INVALID, "n_src %d not in [1, %d]", n_src, B200_MAX_MULTI_RHS);
+  if (!a || !in || !dst_stride) return set_error(B200_ERR_INVALID, "null argument");
+  for (int s = 0; s < n_src; s++) {
+    if (!in[s].v) return set_error(B200_ERR_INVALID, "source %d is null", s);
+    if (in[s].n_parity != 1) return set_error(B200_ERR_INVALID, "the batched pack takes single-parity sources");
+  }
+  for (int d = 0; d < 4; d++) {
+    Geom g;
+    geom_init(g, a->X);
+    const size_t one_parity = (size_t)g.face_cb[d] * (12 * (size_t)a->precision + (a->precision == B200_HALF ? 4 : 0));
+    if (a->comm_dim[d] && !(a->dst[d][0] && a->dst[d][1])) return set_error(B200_ERR_INVALID, "dst[%d] is NULL", d);
+    if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < one_parity)
+      return set_error(B200_ERR_INVALID, "dst_stride[%d] = %zu is smaller than one face (%zu bytes)", d, dst_stride[d], one_parity);
+  }
+  switch (a->precision) {
+  case B200_DOUBLE: return run_pack_multi<PrecF64>(a, n_src, in, dst_stride);
+  case B200_SINGLE: return run_pack_multi<PrecF32>(a, n_src, in, dst_stride);
+  case B200_HALF: return run_pack_multi<PrecH16>(a, n_src, in, dst_stride);
+  }
+  return -1;
+}
+
 int twin_pack_ghost(const b200_pack_args *a)
 {
+  if (a->signal[0][0] || a->signal[1][0] || a->signal[2][0] || a->signal[3][0]) { // with arrival counters: the CTA walk
+    const size_t none[4] = {0, 0, 0, 0};
+    return twin_pack_ghost_multi(a, 1, &a->in, none);
+  }
   switch (a->precision) {
   case B200_DOUBLE: return run_pack<PrecF64>(a);
   case B200_SINGLE: return run_pack<PrecF32>(a);

@@ -257,3 +257,66 @@ def check_partitioned(mem, be, prec, recon, comm_dim, op="wilson", X=(4, 4, 4, 4
             ref = oracle.apply_clover(P.clover, xs, X, parity).astype(np.float64) \
                 - kappa * oracle.wil_dslash(P.gauge, s, X, parity, dagger).astype(np.float64)
         assert_close(ref, P.to_host(out), prec, recon, f"partitioned {comm_dim} op={op} p={parity}")
+
+
+def check_partitioned_multi(mem, be, prec, recon, comm_dim, n_src, op="wilson", X=(4, 4, 4, 4), xpay=False, dagger=0,
+                            clover_kw=None, split=None, aligned=True):
+    """Batched halo of a multi-RHS batch on a self-partitioned lattice: ONE PackGhostMulti launch fills n_src ghost slabs
+    per face, then every source's Dslash reads its own slab.  Each source must match the oracle AND be bit-identical to
+    its own single-source partitioned application (same faces, same arithmetic)."""
+    P = Problem(X, prec, recon, mem, clover=(op != "wilson"), **(clover_kw or {}))
+    kappa = 0.12195
+    a = -kappa if xpay or op == "clover" else 0.0
+    src = [P.spinor(seed=60 + i) for i in range(n_src)]
+    xsrc = [P.spinor(seed=80 + i) for i in range(n_src)]
+    face = [F.ghost_parity_bytes(P.X, prec, d) for d in range(4)]
+    stride = [(fb + 255) // 256 * 256 if aligned else fb for fb in face]
+    for parity in (0, 1):
+        halo = D.Halo()
+        for d in range(4):
+            if comm_dim[d]:
+                halo.comm_dim[d] = 1
+                for dir_ in range(2):
+                    halo.ghost[d][dir_] = mem.put(np.full(n_src * stride[d], 0x7B, dtype=np.uint8))  # poison: every slab must be written
+        ins = [P.to_dev(s) for s in src]
+        xs = [P.to_dev(s) for s in xsrc]
+        dst = [[halo.ghost[d][1], halo.ghost[d][0]] if comm_dim[d] else [None, None] for d in range(4)]
+        D.PackGhostMulti(dst, ins, 1 - parity, dagger, halo.comm_dim, stride, backend=be)
+        if split == "tiles":
+            kws = [dict(kernel=4), dict(kernel=3)]
+        elif split == "sites":
+            kws = [dict(kernel=6), dict(kernel=5)]
+        else:
+            kws = [dict()]
+
+        def apply(out, i, h):
+            xi = xs[i] if (xpay or op == "clover") else None
+            for kw in kws:
+                if op == "wilson":
+                    D.ApplyWilson(out, ins[i], P.U, a, xi, parity, dagger, halo=h, backend=be, **kw)
+                elif op == "clover_pc":
+                    D.ApplyWilsonCloverPreconditioned(out, ins[i], P.U, P.A, a, xi, parity, dagger, halo=h, backend=be, **kw)
+                else:
+                    D.ApplyWilsonClover(out, ins[i], P.U, P.A, a, xi, parity, dagger, halo=h, backend=be, **kw)
+
+        for i in range(n_src):
+            out = P.empty()
+            apply(out, i, halo.source(i, stride))
+            got = P.to_host(out)
+            if op == "wilson":
+                ref = oracle.wil_dslash(P.gauge, src[i], X, parity, dagger).astype(np.float64)
+                if xpay:
+                    ref = xsrc[i].astype(np.float64) - kappa * ref
+            elif op == "clover_pc":
+                ref = oracle.clover_dslash(P.gauge, P.clover_inv, src[i], X, parity, dagger).astype(np.float64)
+                if xpay:
+                    ref = xsrc[i].astype(np.float64) - kappa * ref
+            else:
+                ref = oracle.apply_clover(P.clover, xsrc[i], X, parity).astype(np.float64) \
+                    - kappa * oracle.wil_dslash(P.gauge, src[i], X, parity, dagger).astype(np.float64)
+            assert_close(ref, got, prec, recon, f"batched halo {comm_dim} op={op} src {i}/{n_src} p={parity}")
+            single_halo = self_halo(P, mem, comm_dim)
+            self_exchange(P, single_halo, ins[i], 1 - parity, dagger, be)
+            one = P.empty()
+            apply(one, i, single_halo)
+            assert np.array_equal(got, P.to_host(one)), f"source {i}: batched halo differs from its single-source exchange"

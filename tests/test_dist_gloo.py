@@ -41,6 +41,24 @@ def test_two_rank_wilson_matches_global_oracle(grid_dims, Xl, prec, recon):
         assert dev <= tol, (rank, dev)
 
 
+@pytest.mark.parametrize("grid_dims,Xl,prec,recon", [((1, 1, 1, 2), (4, 4, 4, 4), 8, 18), ((2, 1, 1, 1), (4, 4, 6, 4), 2, 12)])
+def test_two_rank_batched_halo_matches_global_oracle(grid_dims, Xl, prec, recon):
+    """a multi-RHS batch on a partitioned lattice: one batched exchange for 3 sources (HaloExchange(n_src=3))"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, grid_dims, Xl, prec, recon, q, "host", 2, 3)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tol = {8: 1e-11, 4: 1e-4, 2: 1e-2}[prec]
+    for rank, dev, _ in res:
+        assert dev <= tol, (rank, dev)
+
+
 def test_process_grid_topology():
     from quda_b200.comm import ProcessGrid
     g = ProcessGrid((1, 2, 2, 2), 5)

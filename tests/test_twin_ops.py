@@ -176,3 +176,127 @@ def test_site_granular_split_all_masks(comm_dim):
     """B200_KERNEL_BOUNDARY_SITES + B200_KERNEL_INTERIOR_SITES (what the operator layer puts on its side / main stream):
     together they update every site exactly once for all 15 partition masks"""
     ops.check_partitioned(HostMem, twin_backend(), 4, 12, comm_dim, X=(4, 6, 4, 8), split="sites", xpay=True)
+
+
+# ---- batched (multi-RHS) halo: one pack launch for all sources, one arrival signal per face (b200_pack_ghost_multi)
+@pytest.mark.parametrize("comm_dim", MASKS)
+def test_batched_halo_all_masks(comm_dim):
+    ops.check_partitioned_multi(HostMem, twin_backend(), 8, 18, comm_dim, 3, X=(4, 6, 4, 8), xpay=True)
+
+
+@pytest.mark.parametrize("prec,recon", [(8, 12), (4, 12), (4, 8), (2, 18), (2, 12)])
+@pytest.mark.parametrize("n_src,aligned", [(1, True), (2, False), (5, True), (16, False)])
+def test_batched_halo_precisions(prec, recon, n_src, aligned):
+    ops.check_partitioned_multi(HostMem, twin_backend(), prec, recon, (1, 0, 1, 1), n_src, dagger=1, aligned=aligned)
+
+
+@pytest.mark.parametrize("op", ["clover_pc", "clover"])
+@pytest.mark.parametrize("split", [None, "tiles", "sites"])
+def test_batched_halo_ops_and_schedules(op, split):
+    ops.check_partitioned_multi(HostMem, twin_backend(), 4, 12, (0, 1, 1, 1), 4, op=op, xpay=True, split=split,
+                                clover_kw=dict(compressed=True, dynamic=True))
+
+
+def test_batched_halo_arrival_protocol():
+    """the ticket protocol of the batched pack (host-twin CTA walk in scrambled order): every face's arrival counter moves
+    exactly once, after all sources have landed, to the value a single exchange `seq` would publish"""
+    import ctypes as C
+    import numpy as np
+    from quda_b200 import dslash as D, fields as F, lib as L
+    from common import Problem
+    be = twin_backend()
+    X, prec, n_src = (4, 6, 4, 8), 4, 3
+    P = Problem(X, prec, 12, HostMem)
+    ins = [P.to_dev(P.spinor(seed=70 + i)) for i in range(n_src)]
+    flags = np.zeros(8, dtype=np.uint32)
+    counters = np.zeros(8, dtype=np.int32)
+    comm_dim = (1, 0, 1, 1)
+    for seq in (1, 2, 3, 4):
+        a = L.PackArgs()
+        a.abi_version, a.precision = L.ABI_VERSION, prec
+        bufs = []
+        stride = (C.c_size_t * 4)()
+        for d in range(4):
+            a.X[d], a.comm_dim[d] = X[d], comm_dim[d]
+            stride[d] = F.ghost_parity_bytes(X, prec, d)
+            for f in range(2):
+                if comm_dim[d]:
+                    bufs.append(np.zeros(n_src * stride[d], dtype=np.uint8))
+                    a.dst[d][f] = bufs[-1].ctypes.data
+                    a.signal[d][f] = flags.ctypes.data + 4 * (2 * d + f)
+        a.block_counter = counters.ctypes.data
+        a.seq, a.parity, a.dagger = seq, 0, 0
+        a.in_ = ins[0].desc()
+        srcs = (L.Spinor * n_src)(*[f.desc() for f in ins])
+        be.call("pack_ghost_multi", C.byref(a), n_src, srcs, stride)
+        uses = (seq + (seq & 1)) // 2
+        for d in range(4):
+            face_cb = F.volume_cb(X) // X[d]
+            for f in range(2):
+                assert flags[2 * d + f] == (uses * face_cb if comm_dim[d] else 0)
+        assert not counters.any()
+
+
+def test_batched_halo_argument_checks():
+    import ctypes as C
+    from quda_b200 import lib as L
+    from common import Problem
+    be = twin_backend()
+    P = Problem((4, 4, 4, 4), 4, 12, HostMem)
+    f = P.to_dev(P.spinor())
+    a = L.PackArgs()
+    a.abi_version, a.precision = L.ABI_VERSION, 4
+    buf = HostMem.empty(1 << 16)
+    for d in range(4):
+        a.X[d], a.comm_dim[d] = 4, 1
+        for k in range(2):
+            a.dst[d][k] = buf.ctypes.data
+    srcs = (L.Spinor * 2)(f.desc(), f.desc())
+    small = (C.c_size_t * 4)(8, 8, 8, 8)
+    with pytest.raises(L.B200Error, match="smaller than one face"):
+        be.call("pack_ghost_multi", C.byref(a), 2, srcs, small)
+    ok = (C.c_size_t * 4)(4096, 4096, 4096, 4096)
+    with pytest.raises(L.B200Error, match="n_src"):
+        be.call("pack_ghost_multi", C.byref(a), 17, srcs, ok)
+    with pytest.raises(L.B200Error, match="n_src"):
+        be.call("pack_ghost_multi", C.byref(a), 0, srcs, ok)
+
+
+@pytest.mark.parametrize("prec,recon,n_src,dims", [(8, 18, 3, (0, 0, 0, 1)), (4, 12, 8, (0, 1, 1, 1)), (2, 12, 4, (1, 1, 1, 1))])
+def test_batched_exchange_schedule_with_arrival_counters(prec, recon, n_src, dims):
+    """HaloExchange(mode="self", n_src=...) end to end on the CPU stand-in: batched and single exchanges interleaved on the
+    same double-buffered slabs; the twin refuses to run a boundary role whose arrival counter is below its target"""
+    import numpy as np
+    import oracle
+    from common import Problem, assert_close, host_self_exchange
+    from quda_b200 import comm
+    X = (8, 4, 4, 8)
+    P = Problem(X, prec, recon, HostMem)
+    ex = host_self_exchange(X, prec, dims, n_src)
+    src = [P.spinor(seed=10 + i) for i in range(n_src)]
+    dins, outs, one = [P.to_dev(s) for s in src], [P.empty() for _ in range(n_src)], P.empty()
+    for rep in range(5):
+        comm.apply_wilson_distributed(ex, outs, dins, P.U, 0.0, None, 0, 0)
+        if rep % 2:
+            comm.apply_wilson_distributed(ex, one, dins[1], P.U, 0.0, None, 0, 0)
+    for i in range(n_src):
+        assert_close(oracle.wil_dslash(P.gauge, src[i], X, 0, 0), P.to_host(outs[i]), prec, recon, f"batched self exchange src {i}")
+    assert np.array_equal(P.to_host(one), P.to_host(outs[1]))
+    assert ex.seq == 7 and not ex.timed_out()
+    with pytest.raises(Exception, match="batch of"):
+        ex.start(dins + dins[:1], 1, 0)
+
+
+def test_twin_refuses_a_halo_that_never_arrives():
+    """negative control of the check above: a Dslash whose exchange number is ahead of the counters is an error"""
+    from common import Problem, host_self_exchange
+    from quda_b200 import comm, dslash as D, lib as L
+    X = (4, 4, 4, 8)
+    P = Problem(X, 4, 12, HostMem)
+    ex = host_self_exchange(X, 4, (0, 0, 0, 1))
+    din, out = P.to_dev(P.spinor()), P.empty()
+    comm.apply_wilson_distributed(ex, out, din, P.U, 0.0, None, 0, 0)
+    h = ex.halo()
+    h.seq += 2  # same buffer, one exchange later: nobody has packed it
+    with pytest.raises(L.B200Error, match="never finish"):
+        D.ApplyWilson(out, din, P.U, 0.0, None, 0, 0, halo=comm._RawHalo(h), backend=twin_backend())
