@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 typedef enum {
   B200_SUCCESS = 0,
@@ -110,6 +110,9 @@ typedef struct {
   void *wait_flag[4][2];
   unsigned seq;
   int *timeout_flag; /* device word set to 1 if a wait gave up after ~10 s (never hangs the GPU); may be NULL */
+  /* Multi-RHS batches (b200_dslash_apply_multi after b200_pack_ghost_multi): source i reads ghost[d][dir] (and ghost_norm)
+   * + i * src_stride[d] bytes; wait_flag and seq are shared by the batch.  0 for single-source calls. */
+  size_t src_stride[4];
 } b200_halo;
 
 typedef struct {
@@ -141,7 +144,8 @@ int b200_dslash_apply(const b200_dslash_args *args);
  * `args` is read as for b200_dslash_apply except that args->out / in / x are ignored in favour of out[i], in[i], x[i]
  * (x may be NULL when a == 0).  On an unpartitioned lattice each thread updates its site for up to 4 sources at once
  * (2 in fp64) with the links held in registers, so the link stream is read once per batch; with partitioned dimensions
- * or an explicit kernel selector the sources are applied one after the other. */
+ * or an explicit kernel selector the sources are applied one after the other, source i on its own ghost slab
+ * (args->halo.src_stride, filled by ONE b200_pack_ghost_multi for the whole batch). */
 #define B200_MAX_MULTI_RHS 16
 int b200_dslash_apply_multi(const b200_dslash_args *args, int n_src, const b200_spinor *out, const b200_spinor *in,
                             const b200_spinor *x);

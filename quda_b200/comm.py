@@ -311,6 +311,7 @@ class HaloExchange:
                     h.ghost[d][dr] = self.base + self.off[(b, d, dr)] + src * self.src_stride[d]
                     if self.mode in ("p2p", "self"):
                         h.wait_flag[d][dr] = self.base + self.flag_off + ((b * 4 + d) * 2 + dr) * 4
+            h.src_stride[d] = self.src_stride[d] if self.n_src > 1 else 0
         h.seq = self.seq
         h.timeout_flag = (self.base + self.timeout_off) if self.mode in ("p2p", "self") else None
         return h
@@ -398,30 +399,27 @@ def apply_wilson_distributed(ex, out, in_, U, a, x, parity, dagger, op=L.OP_WILS
     multi = isinstance(out, (list, tuple))
     if multi:
         # the reference's cvector_ref batch on a partitioned lattice (lib/dslash_pack2.cu packs all sources in one launch):
-        # ONE batched exchange (needs HaloExchange(n_src >= len(batch))), then every source's interior / boundary launches
-        # read their own ghost slab and wait on the shared arrival flags
-        outs, ins = list(out), list(in_)
-        xs = list(x) if x is not None else [None] * len(outs)
-        if len(ins) != len(outs) or len(xs) != len(outs):
+        # ONE batched exchange (needs HaloExchange(n_src >= len(batch))), then b200_dslash_apply_multi runs every source on
+        # its own ghost slab (halo.src_stride) behind the shared arrival counters
+        if len(in_) != len(out) or (x is not None and len(x) != len(out)):
             raise L.B200Error("multi-RHS: out / in / x batches differ in length")
-    else:
-        outs, ins, xs = [out], [in_], [x]
-    if any(f.n_parity != 1 for f in ins):
+        out, in_, x = list(out), list(in_), (list(x) if x is not None else None)
+    if any(f.n_parity != 1 for f in (in_ if multi else [in_])):
         raise NotImplementedError("full-field halo exchange: pack each parity into its slot")
     side = ex.pack_stream(stream) if ex.mode == "p2p" else None
     if side is None:
-        ex.start(ins if multi else in_, 1 - parity, dagger, stream=stream)
-        for s in range(len(outs)):
-            D._apply(op, outs[s], ins[s], U, a, xs[s], parity, dagger, None, A=A, halo=_RawHalo(ex.halo(s)), stream=stream,
-                     tile=tile, backend=ex.backend)
+        ex.start(in_, 1 - parity, dagger, stream=stream)
+        D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(ex.halo()), stream=stream, tile=tile,
+                 backend=ex.backend)
         return
     import torch
     main = torch.cuda.current_stream() if stream is None else torch.cuda.ExternalStream(stream)
     side.wait_stream(main)
-    ex.start(ins if multi else in_, 1 - parity, dagger, stream=side.cuda_stream)
+    ex.start(in_, 1 - parity, dagger, stream=side.cuda_stream)
+    halo = ex.halo()
     # side stream: pack -> boundary tiles (wait for the neighbours' flags, complete updates); main stream: interior tiles
-    for kernel, st in ((L.KERNEL_BOUNDARY_TILES, side), (L.KERNEL_INTERIOR_TILES, main)):
-        for s in range(len(outs)):
-            D._apply(op, outs[s], ins[s], U, a, xs[s], parity, dagger, None, A=A, halo=_RawHalo(ex.halo(s)),
-                     stream=st.cuda_stream, tile=tile, kernel=kernel, backend=ex.backend)
+    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(halo), stream=side.cuda_stream, tile=tile,
+             kernel=L.KERNEL_BOUNDARY_TILES, backend=ex.backend)
+    D._apply(op, out, in_, U, a, x, parity, dagger, None, A=A, halo=_RawHalo(halo), stream=main.cuda_stream, tile=tile,
+             kernel=L.KERNEL_INTERIOR_TILES, backend=ex.backend)
     main.wait_stream(side)

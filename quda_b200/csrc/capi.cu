@@ -73,8 +73,7 @@ void b200_reset_launch_count(void) { g_launches.store(0); }
 
 size_t b200_ghost_face_bytes(int precision, const int X[4], int dim)
 {
-  const size_t face_cb = (size_t)X[0] * X[1] * X[2] * X[3] / X[dim] / 2;
-  return 2 * face_cb * (12 * (size_t)precision + (precision == B200_HALF ? 4 : 0));
+  return 2 * ghost_parity_bytes(precision, X, dim);
 }
 
 int b200_dslash_apply(const b200_dslash_args *a)
@@ -106,12 +105,22 @@ int b200_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spi
   MrhsRequest rq;
   bool batched = false;
   if (int rc = make_mrhs_request(rq, a, n_src, out, in, x, batched)) return rc;
-  if (!batched) { // per-source halo schedule
+  if (!batched) { // other kernel selectors / operators: source by source, each on its own ghost slab
     for (int i = 0; i < n_src; i++) {
-      b200_dslash_args one = *a;
-      one.out = out[i];
-      one.in = in[i];
-      if (a->a != 0.0) one.x = x[i];
+      const b200_dslash_args one = source_args(*a, i, out, in, x);
+      if (int rc = b200_dslash_apply(&one)) return rc;
+    }
+    return B200_SUCCESS;
+  }
+  if (rq.interior_box && a->kernel == B200_KERNEL_AUTO) {
+    // partitioned lattice, whole operator: the boundary tiles of every source (they wait for the batch's arrival counters
+    // and read the source's own ghost slab) after the batched interior below -- the order the single-source AUTO path uses
+    b200_dslash_args interior = *a;
+    interior.kernel = B200_KERNEL_INTERIOR_TILES;
+    if (int rc = b200_dslash_apply_multi(&interior, n_src, out, in, x)) return rc;
+    for (int i = 0; i < n_src; i++) {
+      b200_dslash_args one = source_args(*a, i, out, in, x);
+      one.kernel = B200_KERNEL_BOUNDARY_TILES;
       if (int rc = b200_dslash_apply(&one)) return rc;
     }
     return B200_SUCCESS;
@@ -358,9 +367,9 @@ int b200_pack_ghost_multi(const b200_pack_args *a, int n_src, const b200_spinor 
   for (int d = 0; d < 4; d++) {
     batch.dst_stride[d] = dst_stride[d];
     // a slab stride smaller than one parity's face would make the sources overwrite each other
-    if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < b200_ghost_face_bytes(a->precision, a->X, d) / 2)
+    if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < ghost_parity_bytes(a->precision, a->X, d))
       return set_error(B200_ERR_INVALID, "dst_stride[%d] = %zu is smaller than one face (%zu bytes)", d, dst_stride[d],
-                       b200_ghost_face_bytes(a->precision, a->X, d) / 2);
+                       ghost_parity_bytes(a->precision, a->X, d));
   }
   if (int rc = require_device()) return rc;
   switch (a->precision) {

@@ -47,6 +47,7 @@ namespace b200
     int l1_links;  // mode 1: link loads allocate in L1 (1, default) or stream past it (0: repeats are served by L2)
     int cta_cfg;   // mode 1: occupancy configuration 0 / 1 / 2 (mrhs.cuh::MrhsCtaCfg)
     const b200_spinor *out, *in, *x;
+    int interior_box; // partitioned lattice: only the tiles that touch no partitioned face (the boundary tiles follow per source)
   };
 
   struct CloverRequest {
@@ -94,6 +95,13 @@ namespace b200
     unsigned seq;
     void *stream;
   };
+
+  // bytes of one parity of one face buffer: 12 reals (+ a float norm in half precision) per checkerboard face site
+  inline size_t ghost_parity_bytes(int precision, const int X[4], int dim)
+  {
+    const size_t face_cb = (size_t)X[0] * X[1] * X[2] * X[3] / X[dim] / 2;
+    return face_cb * (12 * (size_t)precision + (precision == B200_HALF ? 4 : 0));
+  }
 
   // A batch of sources packed by ONE launch (b200_pack_ghost_multi): source s reads in[s] and writes its faces
   // dst_stride[d] * s bytes behind the first source's slab in dimension d; the arrival counters move once, for all of them.
@@ -412,9 +420,35 @@ namespace b200
     rq.in = in;
     rq.x = x;
     bool any_comm = false;
-    for (int d = 0; d < 4; d++) any_comm |= (a->halo.comm_dim[d] != 0);
-    batched = !any_comm && a->kernel == B200_KERNEL_AUTO && a->op <= B200_OP_CLOVER_PC;
+    for (int d = 0; d < 4; d++) {
+      any_comm |= (a->halo.comm_dim[d] != 0);
+      // every source needs its own ghost slab (one b200_pack_ghost_multi fills them all)
+      const size_t slab = (size_t)out[0].n_parity * ghost_parity_bytes(a->precision, a->X, d);
+      if (a->halo.comm_dim[d] && n_src > 1 && a->halo.src_stride[d] < slab)
+        return set_error(B200_ERR_INVALID, "multi-RHS on a lattice partitioned in dimension %d: halo.src_stride = %zu, need >= %zu (one ghost slab per source)",
+                         d, a->halo.src_stride[d], slab);
+    }
+    // batched kernels serve whole unpartitioned lattices and, on partitioned ones, the interior tiles (no ghost zones there:
+    // the same branch-free site code); boundary tiles / other kernel selectors run source by source
+    rq.interior_box = any_comm ? 1 : 0;
+    batched = a->op <= B200_OP_CLOVER_PC && (any_comm ? (a->kernel == B200_KERNEL_AUTO || a->kernel == B200_KERNEL_INTERIOR_TILES) : a->kernel == B200_KERNEL_AUTO);
     return 0;
+  }
+
+  // source `i` of a multi-RHS batch as a single-source call: its own fields and, on a partitioned lattice, its own ghost slab
+  inline b200_dslash_args source_args(const b200_dslash_args &a, int i, const b200_spinor *out, const b200_spinor *in, const b200_spinor *x)
+  {
+    b200_dslash_args one = a;
+    one.out = out[i];
+    one.in = in[i];
+    if (a.a != 0.0) one.x = x[i];
+    for (int d = 0; d < 4; d++)
+      for (int dir = 0; dir < 2; dir++) {
+        const size_t off = (size_t)i * a.halo.src_stride[d];
+        if (one.halo.ghost[d][dir]) one.halo.ghost[d][dir] = static_cast<char *>(a.halo.ghost[d][dir]) + off;
+        if (one.halo.ghost_norm[d][dir]) one.halo.ghost_norm[d][dir] = static_cast<char *>(a.halo.ghost_norm[d][dir]) + off;
+      }
+    return one;
   }
 
   // launch geometry of the interior kernel for a requested tile (extents rounded down to powers of two); the box
@@ -496,6 +530,20 @@ namespace b200
       }
     }
     return st.cta_start[st.n];
+  }
+
+  // tile box of a multi-RHS launch: every tile, or -- partitioned lattice -- the tiles that touch no partitioned face
+  // (what dslash_interior_kernel covers for B200_KERNEL_INTERIOR_TILES, same tiling, so the per-source boundary launches
+  // complete the lattice exactly).  Returns false with rc == 0 if there is nothing to launch.
+  inline bool mrhs_box(TileMap &tm, const MrhsRequest &rq, const int *comm_dim, int n_parity, int &gx, int &gy, int &gz, int &rc)
+  {
+    if (rq.interior_box) {
+      SlabTable st;
+      split_boundary(tm, st, comm_dim);
+    }
+    if (box_grid(tm, n_parity, gx, gy, gz, rc)) return true;
+    if (!rc && !rq.interior_box) rc = set_error(B200_ERR_INVALID, "empty lattice");
+    return false;
   }
 
   template <class P> int launch_precision(const LaunchRequest &rq);

@@ -78,7 +78,7 @@ namespace b200
     TileMap tm;
     int threads, gx, gy, gz, rc, nsb, n_batch;
     if (int e = make_tile_map(tm, threads, rq.base.tile, arg.geom, B2_MAXTILE)) return e;
-    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+    if (!mrhs_box(tm, rq, arg.comm_dim, arg.n_parity, gx, gy, gz, rc)) return rc;
     mrhs_cta_shape(nsb, n_batch, rq.n_src, threads, B2_MAXTILE, rq.cta_sources);
     if ((long long)gx * n_batch >= (1ll << 31)) return set_error(B200_ERR_INVALID, "lattice too large for the multi-RHS grid");
     const dim3 grid(gx * n_batch, gy, gz), block(threads, nsb, 1);
@@ -106,7 +106,7 @@ namespace b200
     TileMap tm;
     int threads, gx, gy, gz, rc;
     if (int e = make_tile_map(tm, threads, rq.base.tile, arg.geom, B2_MAXTILE)) return e;
-    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : set_error(B200_ERR_INVALID, "empty lattice");
+    if (!mrhs_box(tm, rq, arg.comm_dim, arg.n_parity, gx, gy, gz, rc)) return rc;
     dslash_mrhs_kernel<P, recon, dagger, xpay, op, NS><<<dim3(gx, gy, gz), threads, 0, (cudaStream_t)rq.base.stream>>>(arg, f, tm);
     count_launch();
     return check_cuda(cudaGetLastError(), "multi-RHS dslash launch");

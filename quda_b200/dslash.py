@@ -81,27 +81,29 @@ class CloverField:
 
 
 class Halo:
-    """Ghost buffers of one field exchange: ghost[d][dir] device buffers (both parities if the field is full)."""
+    """Ghost buffers of one field exchange: ghost[d][dir] device buffers (both parities if the field is full).
+    For a multi-RHS batch every buffer holds one slab per source, `src_stride[d]` bytes apart (PackGhostMulti fills them
+    in one launch); `source(s)` is the view of slab s for a single-source call."""
 
     def __init__(self):
         self.comm_dim = [0, 0, 0, 0]
         self.ghost = [[None, None] for _ in range(4)]
-        self.src, self.src_stride = 0, (0, 0, 0, 0)  # slab of a batched exchange this view reads (source())
+        self.src, self.src_stride = 0, [0, 0, 0, 0]
 
     def desc(self, comm_override=None):
         h = L.Halo()
         for d in range(4):
             on = self.comm_dim[d] and (comm_override is None or comm_override[d])
             h.comm_dim[d] = 1 if on else 0
+            h.src_stride[d] = int(self.src_stride[d])
             for dir_ in range(2):
-                h.ghost[d][dir_] = _ptr(self.ghost[d][dir_]) + self.src * self.src_stride[d] if on else None
+                h.ghost[d][dir_] = _ptr(self.ghost[d][dir_]) + self.src * int(self.src_stride[d]) if on else None
                 h.ghost_norm[d][dir_] = None
         return h
 
-    def source(self, s, src_stride):
-        """the view of source `s` of a batched exchange (PackGhostMulti): same buffers, slab s"""
+    def source(self, s):
         h = Halo()
-        h.comm_dim, h.ghost, h.src, h.src_stride = self.comm_dim, self.ghost, s, tuple(src_stride)
+        h.comm_dim, h.ghost, h.src, h.src_stride = self.comm_dim, self.ghost, s, self.src_stride
         return h
 
 

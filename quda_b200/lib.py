@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200_LIB lets the tuning tools load an alternative build of the same library (e.g. another occupancy target)
 LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libquda_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 DOUBLE, SINGLE, HALF = 8, 4, 2
 OP_WILSON, OP_CLOVER, OP_CLOVER_PC, OP_TWISTED_MASS, OP_TWISTED_MASS_PC = 0, 1, 2, 3, 4
@@ -38,7 +38,8 @@ class Clover(C.Structure):
 
 class Halo(C.Structure):
     _fields_ = [("comm_dim", C.c_int * 4), ("ghost", (C.c_void_p * 2) * 4), ("ghost_norm", (C.c_void_p * 2) * 4),
-                ("wait_flag", (C.c_void_p * 2) * 4), ("seq", C.c_uint), ("timeout_flag", C.c_void_p)]
+                ("wait_flag", (C.c_void_p * 2) * 4), ("seq", C.c_uint), ("timeout_flag", C.c_void_p),
+                ("src_stride", C.c_size_t * 4)]
 
 
 class DslashArgs(C.Structure):

@@ -206,7 +206,7 @@ namespace b200
     TileMap tm;
     int threads, gx, gy, gz, rc;
     if (int e = make_tile_map(tm, threads, rq.base.tile, g, 128)) return e;
-    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+    if (!mrhs_box(tm, rq, arg.comm_dim, arg.n_parity, gx, gy, gz, rc)) return rc;
     long visited = 0;
 #pragma omp parallel for collapse(2) reduction(+ : visited)
     for (int bz = 0; bz < gz; bz++)
@@ -218,7 +218,7 @@ namespace b200
             dslash_site_mrhs<P, recon, dagger, xpay, op, NS>(arg, f, x, x_cb, par);
             visited++;
           }
-    if (visited != (long)g.volume_cb * arg.n_parity) return set_error(B200_ERR_INVALID, "multi-RHS tile map visited %ld sites", visited);
+    if (!rq.interior_box && visited != (long)g.volume_cb * arg.n_parity) return set_error(B200_ERR_INVALID, "multi-RHS tile map visited %ld sites", visited);
     return 0;
   }
 
@@ -233,7 +233,7 @@ namespace b200
     TileMap tm;
     int threads, gx, gy, gz, rc, nsb, n_batch;
     if (int e = make_tile_map(tm, threads, rq.base.tile, g, 128)) return e;
-    if (!box_grid(tm, arg.n_parity, gx, gy, gz, rc)) return rc ? rc : -1;
+    if (!mrhs_box(tm, rq, arg.comm_dim, arg.n_parity, gx, gy, gz, rc)) return rc;
     mrhs_cta_shape(nsb, n_batch, rq.n_src, threads, 128, rq.cta_sources);
     long visited = 0;
 #pragma omp parallel for collapse(2) reduction(+ : visited)
@@ -250,7 +250,7 @@ namespace b200
               dslash_site_src<P, recon, dagger, xpay, op, Cache::REUSE>(arg, f.in[s][1 - par], f.out[s][par], f.x[s][par], x, x_cb, par);
               visited++;
             }
-    if (visited != (long)g.volume_cb * arg.n_parity * rq.n_src)
+    if (!rq.interior_box && visited != (long)g.volume_cb * arg.n_parity * rq.n_src)
       return set_error(B200_ERR_INVALID, "multi-RHS (CTA) grid visited %ld (site, source) pairs", visited);
     return 0;
   }
@@ -496,10 +496,18 @@ int twin_dslash_apply_multi(const b200_dslash_args *a, int n_src, const b200_spi
   if (int rc = make_mrhs_request(rq, a, n_src, out, in, x, batched)) return rc;
   if (!batched) {
     for (int i = 0; i < n_src; i++) {
-      b200_dslash_args one = *a;
-      one.out = out[i];
-      one.in = in[i];
-      if (a->a != 0.0) one.x = x[i];
+      const b200_dslash_args one = source_args(*a, i, out, in, x);
+      if (int rc = twin_dslash_apply(&one)) return rc;
+    }
+    return 0;
+  }
+  if (rq.interior_box && a->kernel == B200_KERNEL_AUTO) { // capi.cu: batched interior, then every source's boundary tiles
+    b200_dslash_args interior = *a;
+    interior.kernel = B200_KERNEL_INTERIOR_TILES;
+    if (int rc = twin_dslash_apply_multi(&interior, n_src, out, in, x)) return rc;
+    for (int i = 0; i < n_src; i++) {
+      b200_dslash_args one = source_args(*a, i, out, in, x);
+      one.kernel = B200_KERNEL_BOUNDARY_TILES;
       if (int rc = twin_dslash_apply(&one)) return rc;
     }
     return 0;
@@ -548,9 +556,7 @@ int twin_pack_ghost_multi(const b200_pack_args *a, int n_src, const b200_spinor 
     if (in[s].n_parity != 1) return set_error(B200_ERR_INVALID, "the batched pack takes single-parity sources");
   }
   for (int d = 0; d < 4; d++) {
-    Geom g;
-    geom_init(g, a->X);
-    const size_t one_parity = (size_t)g.face_cb[d] * (12 * (size_t)a->precision + (a->precision == B200_HALF ? 4 : 0));
+    const size_t one_parity = ghost_parity_bytes(a->precision, a->X, d);
     if (a->comm_dim[d] && !(a->dst[d][0] && a->dst[d][1])) return set_error(B200_ERR_INVALID, "dst[%d] is NULL", d);
     if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < one_parity)
       return set_error(B200_ERR_INVALID, "dst_stride[%d] = %zu is smaller than one face (%zu bytes)", d, dst_stride[d], one_parity);

@@ -273,6 +273,7 @@ def check_partitioned_multi(mem, be, prec, recon, comm_dim, n_src, op="wilson", 
     stride = [(fb + 255) // 256 * 256 if aligned else fb for fb in face]
     for parity in (0, 1):
         halo = D.Halo()
+        halo.src_stride = stride
         for d in range(4):
             if comm_dim[d]:
                 halo.comm_dim[d] = 1
@@ -299,10 +300,21 @@ def check_partitioned_multi(mem, be, prec, recon, comm_dim, n_src, op="wilson", 
                 else:
                     D.ApplyWilsonClover(out, ins[i], P.U, P.A, a, xi, parity, dagger, halo=h, backend=be, **kw)
 
+        # the whole batch in one call (b200_dslash_apply_multi: source i on slab i via halo.src_stride) ...
+        outs = [P.empty() for _ in range(n_src)]
+        xl = xs if (xpay or op == "clover") else None
+        for kw in kws:
+            if op == "wilson":
+                D.ApplyWilson(outs, ins, P.U, a, xl, parity, dagger, halo=halo, backend=be, **kw)
+            elif op == "clover_pc":
+                D.ApplyWilsonCloverPreconditioned(outs, ins, P.U, P.A, a, xl, parity, dagger, halo=halo, backend=be, **kw)
+            else:
+                D.ApplyWilsonClover(outs, ins, P.U, P.A, a, xl, parity, dagger, halo=halo, backend=be, **kw)
         for i in range(n_src):
             out = P.empty()
-            apply(out, i, halo.source(i, stride))
+            apply(out, i, halo.source(i))  # ... and source by source on the slab views
             got = P.to_host(out)
+            assert np.array_equal(got, P.to_host(outs[i])), f"source {i}: batch call differs from the call on its slab view"
             if op == "wilson":
                 ref = oracle.wil_dslash(P.gauge, src[i], X, parity, dagger).astype(np.float64)
                 if xpay:

@@ -23,6 +23,13 @@ def _free_port():
 from dist_worker import worker as _worker
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _twin_built():
+    """build the host twin once in the parent: two freshly spawned ranks must not race to compile it"""
+    from common import twin_backend
+    twin_backend()
+
+
 @pytest.mark.parametrize("grid_dims,Xl", [((1, 1, 1, 2), (4, 4, 4, 4)), ((2, 1, 1, 1), (4, 4, 6, 4)), ((1, 2, 1, 1), (4, 4, 4, 6))])
 @pytest.mark.parametrize("prec,recon", [(8, 18), (4, 12), (2, 8)])
 def test_two_rank_wilson_matches_global_oracle(grid_dims, Xl, prec, recon):

@@ -197,6 +197,16 @@ def test_batched_halo_ops_and_schedules(op, split):
                                 clover_kw=dict(compressed=True, dynamic=True))
 
 
+@pytest.mark.parametrize("flavour", ["thread", "cta"])
+@pytest.mark.parametrize("prec,recon,n_src", [(8, 18, 5), (4, 12, 7), (2, 8, 4)])
+def test_batched_halo_batched_interior_flavours(monkeypatch, flavour, prec, recon, n_src):
+    """on a partitioned lattice the interior tiles of a batch run through the multi-RHS kernels (both flavours; odd
+    sources out through the single-source kernel), the boundary tiles per source -- the lattice must be covered exactly once"""
+    monkeypatch.setenv("B200_MRHS_MODE", flavour)
+    ops.check_partitioned_multi(HostMem, twin_backend(), prec, recon, (0, 1, 0, 1), n_src, X=(8, 8, 4, 8), xpay=True)
+    ops.check_partitioned_multi(HostMem, twin_backend(), prec, recon, (0, 0, 1, 1), n_src, X=(4, 4, 8, 6), split="tiles")
+
+
 def test_batched_halo_arrival_protocol():
     """the ticket protocol of the batched pack (host-twin CTA walk in scrambled order): every face's arrival counter moves
     exactly once, after all sources have landed, to the value a single exchange `seq` would publish"""
@@ -260,6 +270,13 @@ def test_batched_halo_argument_checks():
         be.call("pack_ghost_multi", C.byref(a), 17, srcs, ok)
     with pytest.raises(L.B200Error, match="n_src"):
         be.call("pack_ghost_multi", C.byref(a), 0, srcs, ok)
+    # a batch on a partitioned lattice needs one ghost slab per source: src_stride 0 (all sources on slab 0) is refused
+    from quda_b200 import dslash as D
+    import ops
+    halo = ops.self_halo(P, HostMem, (0, 0, 0, 1))
+    outs, ins = [P.empty(), P.empty()], [f, P.to_dev(P.spinor(seed=3))]
+    with pytest.raises(L.B200Error, match="one ghost slab per source"):
+        D.ApplyWilson(outs, ins, P.U, 0.0, None, 0, 0, halo=halo, backend=be)
 
 
 @pytest.mark.parametrize("prec,recon,n_src,dims", [(8, 18, 3, (0, 0, 0, 1)), (4, 12, 8, (0, 1, 1, 1)), (2, 12, 4, (1, 1, 1, 1))])
