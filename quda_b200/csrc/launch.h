@@ -430,8 +430,10 @@ namespace b200
     }
     // batched kernels serve whole unpartitioned lattices and, on partitioned ones, the interior tiles (no ghost zones there:
     // the same branch-free site code); boundary tiles / other kernel selectors run source by source
+    // (a single source on a partitioned lattice gains nothing from that and keeps the plain single-source path)
     rq.interior_box = any_comm ? 1 : 0;
-    batched = a->op <= B200_OP_CLOVER_PC && (any_comm ? (a->kernel == B200_KERNEL_AUTO || a->kernel == B200_KERNEL_INTERIOR_TILES) : a->kernel == B200_KERNEL_AUTO);
+    batched = a->op <= B200_OP_CLOVER_PC
+      && (any_comm ? n_src > 1 && (a->kernel == B200_KERNEL_AUTO || a->kernel == B200_KERNEL_INTERIOR_TILES) : a->kernel == B200_KERNEL_AUTO);
     return 0;
   }
 
