@@ -364,13 +364,8 @@ int b200_pack_ghost_multi(const b200_pack_args *a, int n_src, const b200_spinor 
     batch.in[s] = in[s].v;
     batch.in_norm[s] = in[s].norm;
   }
-  for (int d = 0; d < 4; d++) {
-    batch.dst_stride[d] = dst_stride[d];
-    // a slab stride smaller than one parity's face would make the sources overwrite each other
-    if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < ghost_parity_bytes(a->precision, a->X, d))
-      return set_error(B200_ERR_INVALID, "dst_stride[%d] = %zu is smaller than one face (%zu bytes)", d, dst_stride[d],
-                       ghost_parity_bytes(a->precision, a->X, d));
-  }
+  for (int d = 0; d < 4; d++) batch.dst_stride[d] = dst_stride[d];
+  if (int rc = check_src_stride("dst_stride", n_src, a->precision, a->X, a->comm_dim, dst_stride, 1)) return rc;
   if (int rc = require_device()) return rc;
   switch (a->precision) {
   case B200_DOUBLE: return launch_pack_multi_precision<PrecF64>(rq, batch);

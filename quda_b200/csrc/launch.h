@@ -103,6 +103,22 @@ namespace b200
     return face_cb * (12 * (size_t)precision + (precision == B200_HALF ? 4 : 0));
   }
 
+  // ghost slabs of a multi-RHS batch: one per source, `stride[d]` bytes apart -- at least one slab, and 16-byte multiples so
+  // that every slab keeps the alignment of the vector loads / stores
+  inline int check_src_stride(const char *what, int n_src, int precision, const int X[4], const int comm_dim[4], const size_t stride[4],
+                              int n_parity)
+  {
+    for (int d = 0; d < 4; d++) {
+      if (!comm_dim[d] || n_src <= 1) continue;
+      const size_t slab = (size_t)n_parity * ghost_parity_bytes(precision, X, d);
+      if (stride[d] < slab)
+        return set_error(B200_ERR_INVALID, "%s[%d] = %zu is smaller than one face (%zu bytes): every source needs its own ghost slab", what, d,
+                         stride[d], slab);
+      if (stride[d] % 16) return set_error(B200_ERR_INVALID, "%s[%d] = %zu is not a multiple of 16 bytes", what, d, stride[d]);
+    }
+    return 0;
+  }
+
   // A batch of sources packed by ONE launch (b200_pack_ghost_multi): source s reads in[s] and writes its faces
   // dst_stride[d] * s bytes behind the first source's slab in dimension d; the arrival counters move once, for all of them.
   struct PackBatchRequest {
@@ -420,14 +436,9 @@ namespace b200
     rq.in = in;
     rq.x = x;
     bool any_comm = false;
-    for (int d = 0; d < 4; d++) {
-      any_comm |= (a->halo.comm_dim[d] != 0);
-      // every source needs its own ghost slab (one b200_pack_ghost_multi fills them all)
-      const size_t slab = (size_t)out[0].n_parity * ghost_parity_bytes(a->precision, a->X, d);
-      if (a->halo.comm_dim[d] && n_src > 1 && a->halo.src_stride[d] < slab)
-        return set_error(B200_ERR_INVALID, "multi-RHS on a lattice partitioned in dimension %d: halo.src_stride = %zu, need >= %zu (one ghost slab per source)",
-                         d, a->halo.src_stride[d], slab);
-    }
+    for (int d = 0; d < 4; d++) any_comm |= (a->halo.comm_dim[d] != 0);
+    // every source needs its own ghost slab (one b200_pack_ghost_multi fills them all)
+    if (int rc = check_src_stride("halo.src_stride", n_src, a->precision, a->X, a->halo.comm_dim, a->halo.src_stride, out[0].n_parity)) return rc;
     // batched kernels serve whole unpartitioned lattices and, on partitioned ones, the interior tiles (no ghost zones there:
     // the same branch-free site code); boundary tiles / other kernel selectors run source by source
     // (a single source on a partitioned lattice gains nothing from that and keeps the plain single-source path)

@@ -555,12 +555,9 @@ int twin_pack_ghost_multi(const b200_pack_args *a, int n_src, const b200_spinor 
     if (!in[s].v) return set_error(B200_ERR_INVALID, "source %d is null", s);
     if (in[s].n_parity != 1) return set_error(B200_ERR_INVALID, "the batched pack takes single-parity sources");
   }
-  for (int d = 0; d < 4; d++) {
-    const size_t one_parity = ghost_parity_bytes(a->precision, a->X, d);
+  for (int d = 0; d < 4; d++)
     if (a->comm_dim[d] && !(a->dst[d][0] && a->dst[d][1])) return set_error(B200_ERR_INVALID, "dst[%d] is NULL", d);
-    if (a->comm_dim[d] && n_src > 1 && dst_stride[d] < one_parity)
-      return set_error(B200_ERR_INVALID, "dst_stride[%d] = %zu is smaller than one face (%zu bytes)", d, dst_stride[d], one_parity);
-  }
+  if (int rc = check_src_stride("dst_stride", n_src, a->precision, a->X, a->comm_dim, dst_stride, 1)) return rc;
   switch (a->precision) {
   case B200_DOUBLE: return run_pack_multi<PrecF64>(a, n_src, in, dst_stride);
   case B200_SINGLE: return run_pack_multi<PrecF32>(a, n_src, in, dst_stride);

@@ -265,6 +265,9 @@ def test_batched_halo_argument_checks():
     small = (C.c_size_t * 4)(8, 8, 8, 8)
     with pytest.raises(L.B200Error, match="smaller than one face"):
         be.call("pack_ghost_multi", C.byref(a), 2, srcs, small)
+    odd = (C.c_size_t * 4)(4104, 4104, 4104, 4104)
+    with pytest.raises(L.B200Error, match="multiple of 16"):
+        be.call("pack_ghost_multi", C.byref(a), 2, srcs, odd)
     ok = (C.c_size_t * 4)(4096, 4096, 4096, 4096)
     with pytest.raises(L.B200Error, match="n_src"):
         be.call("pack_ghost_multi", C.byref(a), 17, srcs, ok)
@@ -275,7 +278,7 @@ def test_batched_halo_argument_checks():
     import ops
     halo = ops.self_halo(P, HostMem, (0, 0, 0, 1))
     outs, ins = [P.empty(), P.empty()], [f, P.to_dev(P.spinor(seed=3))]
-    with pytest.raises(L.B200Error, match="one ghost slab per source"):
+    with pytest.raises(L.B200Error, match="own ghost slab"):
         D.ApplyWilson(outs, ins, P.U, 0.0, None, 0, 0, halo=halo, backend=be)
 
 
