@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--global-dim", type=int, nargs=4, default=[48, 48, 48, 96], help="--op cg: global lattice (config 5)")
     ap.add_argument("--tol", type=float, default=1e-10, help="--op cg: relative residual target")
     ap.add_argument("--kappa", type=float, default=0.12195)
-    ap.add_argument("--nsrc", type=int, default=1, help="sources per call (multi-RHS batch sharing the gauge field); 1 GPU")
+    ap.add_argument("--nsrc", type=int, default=1, help="sources per call (multi-RHS batch sharing the gauge field); at N > 1 with one batched halo exchange per call")
     ap.add_argument("--no-mrhs", action="store_true", help="skip the extra multi-RHS measurement of the default line")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -343,15 +343,22 @@ def run_b200(a):
     rot = [0]
 
     nsrc = max(1, a.nsrc)
+    ex_batch = None
     if nsrc > 1:
-        assert world == 1, "--nsrc is a single-GPU measurement"
         srcs = [src] + [new_spinor(P, seed=77 + i) for i in range(nsrc - 1)]
         dsts = [dst] + [new_spinor(P, seed=None) for i in range(nsrc - 1)]
+        if world > 1:
+            # a multi-RHS batch on the partitioned lattice: ONE batched exchange per step (one pack launch and one arrival
+            # signal per face for all sources, b200_pack_ghost_multi), batched interior tiles, per-source boundary tiles
+            assert a.op == "wilson" and halo_mode.startswith("p2p"), "--nsrc at N > 1: Wilson over the NVLink peer-write halo"
+            ex_batch = comm.HaloExchange(grid, X, prec, mode="p2p", dist=dist, n_src=nsrc)
 
     def step(tile=None):
         src, dst = pairs[rot[0] % NROT]
         rot[0] += 1
-        if nsrc > 1:
+        if ex_batch is not None:
+            comm.apply_wilson_distributed(ex_batch, dsts, srcs, P["U"], 0.0, None, 0, 0, stream=stream, tile=tile or a.tile)
+        elif nsrc > 1:
             fn = D.ApplyWilsonCloverPreconditioned if a.op == "clover_pc" else D.ApplyWilson
             extra = (P["A"],) if a.op == "clover_pc" else ()
             fn(dsts, srcs, P["U"], *extra, 0.0, None, 0, 0, tile=tile or a.tile, stream=stream)
@@ -461,6 +468,12 @@ def run_b200(a):
         out["halo"]["schedule"] = "one fused launch per Dslash: pack CTAs (NVLink remote write + arrival flags) | interior CTAs | boundary CTAs"
         if halo_parity is not None:
             out["halo"].update(halo_parity)
+        if ex_batch is not None:
+            out["halo"]["schedule"] = "multi-RHS batch: one batched pack (one arrival signal per face for all sources) + boundary tiles per source " \
+                                      "on the side stream, batched interior tiles on the main stream"
+            out["halo"]["bytes_per_step_per_gpu"] *= nsrc
+            out["halo"]["gbs_per_gpu"] *= nsrc
+            out["halo"]["timed_out"] = bool(ex_batch.timed_out())
 
     if nsrc > 1:
         out["config"]["workload"] += f", {nsrc} sources per call (multi-RHS)"
