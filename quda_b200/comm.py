@@ -14,6 +14,10 @@ No host polling, no MPI in the critical path.  Modes:
   "nccl"  portable fallback: pack into local send buffers, grouped ncclSend/ncclRecv via torch.distributed
   "self"  single rank that is its own neighbour (the reference's --partition trick) -- used by tests
   "host"  CPU-tier tests only: numpy buffers + gloo send/recv, compute by the host twin
+
+Multi-RHS batches (`HaloExchange(n_src=...)`, lists of fields in `apply_wilson_distributed`): every ghost region holds one
+slab per source and the whole batch travels in ONE exchange -- one pack launch and one arrival signal per face
+(b200_pack_ghost_multi; reference: lib/dslash_pack2.cu:55-403), one message per face in the staged modes.
 """
 import ctypes as C
 import os
