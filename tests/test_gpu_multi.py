@@ -18,10 +18,16 @@ def _run(world, grid_dims, Xl, prec, recon, mode, n_src=1):
     procs = [ctx.Process(target=worker, args=(r, world, port, grid_dims, Xl, prec, recon, q, mode, 6, n_src)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = [q.get(timeout=600) for _ in procs]
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:  # never leave a rank behind on the GPUs (a hung rank would starve every later test)
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+                p.join(timeout=30)
     tol = {8: 1e-11, 4: 1e-4, 2: 1e-2}[prec]
     for rank, dev, timed_out in res:
         assert not timed_out, f"rank {rank}: exterior kernel timed out waiting for its neighbour"
