@@ -320,3 +320,20 @@ def test_twin_refuses_a_halo_that_never_arrives():
     h.seq += 2  # same buffer, one exchange later: nobody has packed it
     with pytest.raises(L.B200Error, match="never finish"):
         D.ApplyWilson(out, din, P.U, 0.0, None, 0, 0, halo=comm._RawHalo(h), backend=twin_backend())
+
+
+# ---- smallest / ragged local lattices (extent 2 is the smallest even extent; a partitioned dimension needs >= 4)
+@pytest.mark.parametrize("X", [(2, 2, 2, 2), (4, 2, 2, 2), (2, 4, 6, 2), (6, 2, 2, 10)])
+def test_minimal_and_ragged_lattices(X):
+    be = twin_backend()
+    ops.check_xpay_fullfield(HostMem, be, 8, 18, X=X)
+    ops.check_xpay_fullfield(HostMem, be, 2, 12, X=X)
+    for d in range(4):
+        mask = tuple(int(e == d) for e in range(4))
+        if X[d] >= 4:
+            for split in (False, "tiles", "sites", "fused"):
+                ops.check_partitioned(HostMem, be, 4, 12, mask, X=X, xpay=True, split=split)
+        else:
+            from quda_b200 import lib as L
+            with pytest.raises(L.B200Error, match="needs local extent >= 4"):
+                ops.check_partitioned(HostMem, be, 4, 12, mask, X=X)
