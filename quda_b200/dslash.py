@@ -97,7 +97,8 @@ class Halo:
             h.comm_dim[d] = 1 if on else 0
             h.src_stride[d] = int(self.src_stride[d])
             for dir_ in range(2):
-                h.ghost[d][dir_] = _ptr(self.ghost[d][dir_]) + self.src * int(self.src_stride[d]) if on else None
+                base = _ptr(self.ghost[d][dir_]) if on else None
+                h.ghost[d][dir_] = base + self.src * int(self.src_stride[d]) if base is not None else None
                 h.ghost_norm[d][dir_] = None
         return h
 
