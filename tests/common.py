@@ -24,7 +24,8 @@ def twin_backend():
     global _twin
     if _twin is None:
         subprocess.check_call(["make", "-s", "-C", TWIN_DIR])
-        lib = C.CDLL(os.path.join(TWIN_DIR, "_build", "libhosttwin.so"))
+        # B200_TWIN_LIB: another build of the same source, e.g. `make -C tests/hosttwin asan` + LD_PRELOAD=libasan.so
+        lib = C.CDLL(os.environ.get("B200_TWIN_LIB") or os.path.join(TWIN_DIR, "_build", "libhosttwin.so"))
         L.declare(lib, "twin")
         _twin = D.Backend(lib, "twin")
     return _twin
