@@ -123,3 +123,67 @@ def test_model_catches_an_early_batch_signal():
     """a batched pack that publishes after the first source's CTAs lets the boundary role read slabs that have not landed"""
     v = explore(2, 2, n_src=2, publish_after=2)
     assert v is not None and "holds exchange" in v
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The in-kernel NVLink all-reduce of the solver's scalars (quda_b200/csrc/host/dirac.cu::finish_reduction): thread t of the
+# finishing block of rank r stores its partial sum into slot [k & 1][r] of rank t's mailbox (value, then the sequence tag with
+# release semantics), then spins on its OWN slot [k & 1][t] until the tag has reached k (acquire) and reads the value; the
+# next reduction is a later launch, i.e. starts when all threads of this one are done.
+def explore_allreduce(n_ranks, K, slots=2, tag_first=False):
+    def slot(k):
+        return k & 1 if slots == 2 else 0
+
+    # rank state: (k, per-thread stage) with stage 0 = store value, 1 = store tag, 2 = wait for the tag, 3 = read, 4 = done
+    init_rank = (1, (0,) * n_ranks)
+    box0 = tuple(tuple((0, 0) for _ in range(n_ranks)) for _ in range(slots))  # [slot][source] = (value's reduction, tag)
+    start = (tuple(init_rank for _ in range(n_ranks)), tuple(box0 for _ in range(n_ranks)))
+    seen, stack = set(), [start]
+    while stack:
+        st = stack.pop()
+        if st in seen:
+            continue
+        seen.add(st)
+        ranks, boxes = st
+        if all(r[0] > K for r in ranks):
+            continue
+        moves = 0
+        for me in range(n_ranks):
+            k, stages = ranks[me]
+            if k > K:
+                continue
+            b = slot(k)
+            for t in range(n_ranks):
+                sg = stages[t]
+                if sg == 4:
+                    continue
+                nb = boxes
+                if sg in (0, 1):  # the two stores into rank t's box, slot [b][me]
+                    write_value = (sg == 0) != tag_first
+                    box = [list(s) for s in boxes[t]]
+                    v, tag = box[b][me]
+                    box[b][me] = (k, tag) if write_value else (v, k)
+                    nb = boxes[:t] + (tuple(tuple(s) for s in box),) + boxes[t + 1:]
+                elif sg == 2:
+                    if boxes[me][b][t][1] < k:
+                        continue  # still spinning
+                else:  # read
+                    if boxes[me][b][t][0] != k:
+                        return f"rank {me}, reduction {k}: slot of rank {t} holds the value of reduction {boxes[me][b][t][0]}"
+                ns = stages[:t] + (sg + 1,) + stages[t + 1:]
+                nr = (k + 1, (0,) * n_ranks) if all(x == 4 for x in ns) else (k, ns)
+                stack.append((ranks[:me] + (nr,) + ranks[me + 1:], nb))
+                moves += 1
+        if moves == 0:
+            return f"deadlock: {ranks}"
+    return None
+
+
+@pytest.mark.parametrize("n_ranks,K", [(2, 6), (3, 1)])
+def test_mailbox_allreduce_is_race_and_deadlock_free(n_ranks, K):
+    assert explore_allreduce(n_ranks, K) is None
+
+
+def test_model_catches_single_slot_mailboxes_and_tag_before_value():
+    assert "holds the value" in (explore_allreduce(2, 3, slots=1) or "")       # a fast rank overwrites the sum being read
+    assert "holds the value" in (explore_allreduce(2, 2, tag_first=True) or "")  # publishing the tag before the value
